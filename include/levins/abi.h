@@ -1,0 +1,209 @@
+/*
+ * levins/abi.h -- C ABI of liblevins_b200.so: the B200-native LiDAR depth-enhancement path of LE-VINS.
+ *
+ * The reference (i2Nav-WHU/LE-VINS) has no plugin / FFI boundary for this path: it is plain C++ member
+ * and static functions inside the estimator.  This header is therefore the boundary a
+ * maintainer binds instead; every entry point names the reference code it replaces (file:line, relative
+ * to the reference checkout).  Plain pointers and sizes only; no C++/torch types.  All host pointers are
+ * caller-owned.  The library has NO CPU fallback: every compute entry point runs hand-written sm_100a
+ * kernels and fails with LEVINS_ERR_CUDA when no such device is present.
+ *
+ * Threading: a context is bound to one GPU and is not thread-safe, except levins_append_scan(), which may
+ * be called from another thread (the reference appends from the ROS callback thread under a mutex,
+ * le_vins.cc:149-163).
+ */
+#ifndef LEVINS_ABI_H
+#define LEVINS_ABI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEVINS_ABI_VERSION 1
+
+/* ---- status codes (the reference has bool/int returns and no error codes) ---- */
+#define LEVINS_OK 0
+#define LEVINS_EMPTY 1            /* the reference's `return false` / empty cloud (le_vins.cc:426-429, tracking.cc:356-358) */
+#define LEVINS_ERR_ARG (-1)
+#define LEVINS_ERR_CUDA (-2)
+#define LEVINS_ERR_CAPACITY (-3)
+#define LEVINS_ERR_STATE (-4)
+
+/* ---- record layouts (byte-identical to the reference's) ---- */
+
+/* PointXYZIT, le_vins/lidar/lidar.h:28-33: 32 B, 16-aligned, time = GPS seconds of week (f64). */
+typedef struct levins_point_xyzit {
+    float x, y, z, pad0;
+    float intensity, pad1;
+    double time;
+} levins_point_xyzit;
+
+/* PointType = pcl::PointXYZI, le_vins/lidar/lidar.h:89: 32 B; w (data[3]) = 1.0f. */
+typedef struct levins_point_xyzi {
+    float x, y, z, w;
+    float intensity, pad[3];
+} levins_point_xyzi;
+
+/* Pose, le_vins/common/types.h:51-54: Matrix3d R (column-major) + Vector3d t. */
+typedef struct levins_pose {
+    double R[9];
+    double t[3];
+} levins_pose;
+
+/* One element of ins_window_ (std::deque<std::pair<IMU, IntegrationState>>, le_vins.h):
+ * `time` = pair.first.time (what MISC::getInsWindowIndex compares, misc.cc:28,40-41),
+ * `state_time`, `p`, `q` = pair.second.{time,p,q} (what statePoseInterpolation reads, misc.cc:84-94).
+ * q = (x, y, z, w), Eigen coefficient order. */
+typedef struct levins_ins_sample {
+    double time;
+    double state_time;
+    double p[3];
+    double q[4];
+} levins_ins_sample;
+
+/* MapPointType, le_vins/visual/visual_mappoint.h:38-42 */
+#define LEVINS_MAPPOINT_NONE (-1)
+#define LEVINS_MAPPOINT_TRIANGULATED 0
+#define LEVINS_MAPPOINT_DEPTH_ASSOCIATED 1
+
+/* range image geometry: compile-time constants in the reference (tracking.h:119-126) and here */
+#define LEVINS_IMAGE_SIZE 300
+#define LEVINS_IMAGE_CELLS (LEVINS_IMAGE_SIZE * LEVINS_IMAGE_SIZE)
+
+/* decision-path bits reported per feature (diagnostic, same meaning as the oracle's) */
+#define LEVINS_FLAG_FEW_POINTS 1    /* fewer than 5 neighbours exist (reference: UB, build: NONE) */
+#define LEVINS_FLAG_TOO_FAR 2       /* tracking.cc:573-575 */
+#define LEVINS_FLAG_RESIDUAL 4      /* tracking.cc:596-605 */
+#define LEVINS_FLAG_RANGE_SPREAD 8  /* tracking.cc:607-611 */
+#define LEVINS_FLAG_BAD_T 16        /* tracking.cc:621-623 */
+
+/* All association thresholds are compile-time constants in the reference; they are run-time here with
+ * the reference's values as defaults (levins_config_default). */
+typedef struct levins_config {
+    uint32_t struct_size;            /* sizeof(levins_config), for forward compatibility */
+    int32_t libm_mode;               /* 0: unqualified atan2/sqrt resolve to the float overloads (default), 1: double (SURVEY 8a note 3) */
+    double stack_interval;           /* LIDAR_DEPTH_POINT_STACK_INTERVAL = 0.5 s, le_vins.h:130 */
+    double reserved_buffer_length;   /* RESERVED_BUFFER_LENGTH = 10 s; eviction at length + 2*interval, le_vins.cc:156 */
+    double nearest_depth;            /* VisualMapPoint::NEAREST_DEPTH = 1, visual_mappoint.h:50 */
+    double farthest_depth;           /* VisualMapPoint::FARTHEST_DEPTH = 200, visual_mappoint.h:51 */
+    double plane_residual_threshold; /* 0.1 m, tracking.cc:600 */
+    double range_spread_threshold;   /* 0.5 m, tracking.cc:609 */
+    int32_t nearest_distance_counts; /* ASSOCIATE_NEAREST_DISTANCE_COUNTS = 3, tracking.h:121 */
+    int32_t reserved0;
+    uint64_t max_points;             /* device ring-buffer capacity in points (streaming API) */
+    uint64_t max_ins;                /* INS samples per keyframe (reference: MAXIMUM_INS_NUMBER 1000 + RESERVED 400) */
+    uint64_t max_features;           /* feature queries per keyframe */
+} levins_config;
+
+typedef struct levins_ctx levins_ctx;
+
+/* ------------------------------------------------------------------------------------------------
+ * lifecycle
+ * ------------------------------------------------------------------------------------------------ */
+int levins_abi_version(void);
+void levins_config_default(levins_config *cfg);
+/* device = CUDA ordinal.  Fails with LEVINS_ERR_CUDA when the device is missing or is not sm_100. */
+int levins_create(int device, const levins_config *cfg, levins_ctx **out);
+void levins_destroy(levins_ctx *ctx);
+const char *levins_last_error(const levins_ctx *ctx);
+const char *levins_status_string(int status);
+/* Run on an externally owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int levins_set_stream(levins_ctx *ctx, void *cuda_stream);
+int levins_synchronize(levins_ctx *ctx);
+
+/* pose_b_c_, pose_c_l_, td_b_l_ of class VINS (le_vins.cc:83-99) */
+int levins_set_extrinsics(levins_ctx *ctx, const levins_pose *pose_b_c, const levins_pose *pose_c_l, double td_b_l);
+
+/* ------------------------------------------------------------------------------------------------
+ * streaming API -- one keyframe at a time, host buffers in and out
+ * ------------------------------------------------------------------------------------------------ */
+
+/* VINS::addNewPointCloud (le_vins.cc:149-163): append one scan to the device-resident lidar_point_buffer_
+ * and evict from the front while |t_back - t_front| > reserved_buffer_length + 2*stack_interval.
+ * Points must be time-sorted within and across scans (the reference assumes it, le_vins.cc:431-437). */
+int levins_append_scan(levins_ctx *ctx, const levins_point_xyzit *points, size_t n);
+/* current deque size and its front/back times (synchronises) */
+int levins_buffer_info(levins_ctx *ctx, size_t *n_points, double *t_front, double *t_back);
+int levins_buffer_clear(levins_ctx *ctx);
+
+/* VINS::pointcloudStackForVisualTracking (le_vins.cc:392-470) + MISC::getPoseFromInsWindow (misc.cc:25-103)
+ * + PointCloudCommon::relativeProjectionToCamera (pointcloud.cc:36-48,65-71):
+ * pops points older than stamp - stack_interval, takes the points up to `stamp`, range-gates and deskews
+ * each with the INS pose interpolated at time + td_b_l into the camera frame of the keyframe at `stamp`.
+ * out_cloud (nullable): receives n_out points (gated points are default points (0,0,0,1;0), as after
+ * PointCloud::resize, le_vins.cc:438); out_capacity in points.  The deskewed cloud also stays resident
+ * on the device for levins_build_range_image(ctx, NULL, ...).
+ * Returns LEVINS_OK, LEVINS_EMPTY (reference returns false), or an error. */
+int levins_stack_deskew(levins_ctx *ctx, double stamp, const levins_ins_sample *ins, size_t n_ins,
+                        levins_point_xyzi *out_cloud, size_t out_capacity, size_t *n_out);
+
+/* Tracking::depthAssociationProjection (tracking.cc:298-368): 300x300 spherical range image that keeps the
+ * nearest point per 0.3-degree cell, row-major compaction to the unit sphere (xyz = unit vector,
+ * intensity = range).  The KD-tree build of tracking.cc:361-362 has no counterpart: the cell grid is the index.
+ * cloud == NULL: use the resident result of the last levins_stack_deskew.
+ * unit_sphere_out (nullable, capacity unit_capacity), cell_winner_out (nullable, 90000 entries: index into the
+ * cloud of the point kept per cell or -1), m_out = number of non-empty cells.
+ * Returns LEVINS_OK, LEVINS_EMPTY when M == 0 (reference returns false), or an error. */
+int levins_build_range_image(levins_ctx *ctx, const levins_point_xyzi *cloud, size_t n,
+                             levins_point_xyzi *unit_sphere_out, size_t unit_capacity, int32_t *cell_winner_out,
+                             size_t *m_out);
+
+/* Tracking::depthAssociationPlaneFitting (tracking.cc:564-634) for F query rays against the range image built
+ * by the last levins_build_range_image / levins_keyframe (the per-feature loops of tracking.cc:399-413 and
+ * 512-525).  query_xyz: F x 3 f32 unit vectors (Camera::pixel2unitcam cast to float, tracking.cc:387-395).
+ * Outputs (each nullable): type[F] MapPointType; xyz_depth[F*4] = camera-frame x,y,z and depth (= z), the
+ * query unchanged with depth 0 when type is NONE; knn_idx[F*5] indices into the compacted unit-sphere cloud,
+ * ascending (d2, index), -1 where fewer exist inside the search window; knn_d2[F*5]; flags[F] LEVINS_FLAG_*.
+ * Neighbours farther than the acceptance threshold (tracking.cc:573) can never influence a result and are only
+ * guaranteed to be reported when they lie inside the 9 x 13-cell search window. */
+int levins_associate(levins_ctx *ctx, const float *query_xyz, size_t n_features, int8_t *type, float *xyz_depth,
+                     int32_t *knn_idx, float *knn_d2, int32_t *flags);
+
+/* Fused keyframe: levins_stack_deskew + levins_build_range_image + levins_associate with no intermediate
+ * host round trip (the deskewed cloud is never written; one device->host copy of the results).
+ * n_projected_out / m_out nullable. */
+int levins_keyframe(levins_ctx *ctx, double stamp, const levins_ins_sample *ins, size_t n_ins, const float *query_xyz,
+                    size_t n_features, int8_t *type, float *xyz_depth, size_t *n_projected_out, size_t *m_out);
+
+/* PointCloudCommon::pointCloudProjection (pointcloud.cc:50-63): dst[k] = f32(R * f64(src[k]) + t). */
+int levins_point_cloud_projection(levins_ctx *ctx, const levins_pose *pose, const levins_point_xyzi *src,
+                                  levins_point_xyzi *dst, size_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * batch API -- many independent keyframes resident in HBM (BASELINE config 5 and the bench workload)
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct levins_keyframe_desc {
+    uint64_t pt_begin, pt_count;   /* slice of the point pool holding this keyframe's buffer (time-sorted) */
+    uint64_t ins_begin, ins_count; /* slice of the INS pool */
+    uint64_t q_begin, q_count;     /* slice of the query pool (in queries, 3 floats each) */
+    double stamp;
+} levins_keyframe_desc;
+
+/* Copy the pools and descriptors to the device (host -> device).  Replaces any previous batch. */
+int levins_batch_upload(levins_ctx *ctx, const levins_point_xyzit *points, size_t n_points,
+                        const levins_ins_sample *ins, size_t n_ins, const float *query_xyz, size_t n_queries,
+                        const levins_keyframe_desc *descs, size_t n_keyframes);
+/* Enqueue the whole batch on the context's stream: per keyframe window search + INS table (one launch for the
+ * batch), then per wave of keyframes deskew+bin, cell finalisation and association.  Asynchronous. */
+int levins_batch_run(levins_ctx *ctx);
+/* Copy results to the host (device -> host, synchronises).  All outputs nullable.  type / xyz_depth / flags are
+ * laid out by descriptor q_begin (i.e. parallel to the query pool); n_projected[K], m[K] per keyframe. */
+int levins_batch_download(levins_ctx *ctx, int8_t *type, float *xyz_depth, int32_t *flags, uint32_t *n_projected,
+                          uint32_t *m);
+/* Waves: how many keyframes share one set of launches (their z-buffers stay L2-resident). 0 = default. */
+int levins_batch_set_wave(levins_ctx *ctx, int keyframes_per_wave);
+/* Per-kernel device time of the last levins_batch_run, measured with CUDA events on the launching stream when
+ * profiling is on.  ms[0] prepare, ms[1] deskew+bin, ms[2] finalise cells, ms[3] associate; launches[i] = number
+ * of launches of that kernel. */
+int levins_set_profiling(levins_ctx *ctx, int enabled);
+int levins_batch_kernel_ms(levins_ctx *ctx, float ms[4], uint32_t launches[4]);
+/* number of kernel launches issued by this context since creation */
+uint64_t levins_launch_count(const levins_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEVINS_ABI_H */

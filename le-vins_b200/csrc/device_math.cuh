@@ -1,0 +1,657 @@
+// device_math.cuh -- device-side arithmetic of the LiDAR depth-enhancement path (sm_100a).
+//
+// This translation unit is compiled with -fmad=false: wherever the reference's result is an integer / index /
+// validity decision (range gate, cell id, k-NN order, plane validity, depth in f32) the operation order of the
+// reference's x86-64 SSE2 build is reproduced exactly and must not be contracted.  Where only a tolerance applies
+// (stage 1, FP64 rigid-body algebra) fused multiply-adds are requested explicitly with fma().
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace lv {
+
+constexpr int IMG = 300;
+constexpr int CELLS = IMG * IMG;
+constexpr unsigned long long EMPTY_KEY = ~0ull;
+
+// ---- records (layout-identical to include/levins/abi.h) ----
+struct __align__(16) PointXYZIT {
+    float x, y, z, pad0;
+    float intensity, pad1;
+    double time;
+};
+struct __align__(16) PointXYZI {
+    float x, y, z, w;
+    float intensity, pad[3];
+};
+struct InsSample {
+    double time, state_time;
+    double p[3];
+    double q[4];
+};
+static_assert(sizeof(PointXYZIT) == 32 && sizeof(PointXYZI) == 32 && sizeof(InsSample) == 72, "ABI layout");
+
+// One INS interval [i-1, i] pre-digested for the per-point deskew ("stage 1 algebra"):
+//   p_c0 = A * Rod(k, -s*theta) * (R_bc p_c1 + t_bc) + c0 + s * c1,   s = (t - ts0) * inv_dts
+// entry 0 of each keyframe's table is the out-of-window fallback (newest state, misc.cc:74-77).
+struct __align__(16) Interval {
+    double t_lo, t_hi;   // IMU times of samples i-1, i (search keys, misc.cc:40-43)
+    double ts0, inv_dts; // state time of sample i-1 and 1 / (ts1 - ts0)   (misc.cc:88)
+    double A[9];         // R0^T R(q0), row-major
+    double k[3];         // rotation axis of dq = q1^-1 q0   (misc.cc:85-86)
+    double theta;        // its angle
+    double c0[3];        // R0^T (p0 - t0)
+    double c1[3];        // R0^T (p1 - p0)
+    double pad;
+};
+static_assert(sizeof(Interval) == 192, "interval entry");
+
+// fixed extrinsics (class VINS: pose_c_l_, pose_b_c_, td_b_l_), R column-major like Eigen
+struct Extrinsics {
+    double Rcl[9], tcl[3];
+    double Rbc[9], tbc[3];
+    double td_b_l;
+};
+
+// constants evaluated on the host with the reference's own double expressions (tracking.h:119-135)
+struct Consts {
+    double angle;       // ASSOCIATE_RANGE_IMAGE_ANGLE
+    double inv_angle;   // 1 / angle (fast path of the cell computation; exactness restored by a guarded fallback)
+    double half_offset; // M_PI * 0.5 - ASSOCIATE_IMAGE_FOV * 0.5
+    double tan_value;   // ASSOCIATE_POINT_TAN_VALUE
+    double thr2;        // ASSOCIATE_NEAREST_SQUARE_DISTANCE_THRESHOLD
+    double nearest, farthest;
+    double plane_residual, range_spread;
+    double stack_interval;
+    int libm_mode;
+    int pad;
+};
+
+// per-keyframe state, device resident
+struct KfState {
+    unsigned long long pt_begin, pt_count;
+    unsigned long long ins_begin, ins_count;
+    unsigned long long q_begin, q_count;
+    double stamp;
+    unsigned long long table_begin; // this keyframe's slice of the interval-table pool (ins_count entries)
+    // written by k_prepare
+    unsigned long long proj_begin; // physical index of the first kept point (pt_begin + first, wrapped)
+    unsigned int first, n_proj;
+    int status; // LEVINS_OK / LEVINS_EMPTY
+    unsigned int m;
+    double ins_t0, ins_t_last, inv_mean_dt;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small algebra (column-major 3x3 like Eigen), mirrored summation order ((a0 b0 + a1 b1) + a2 b2)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void m3_mul_v(const double* R, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) y[i] = (R[i] * x[0] + R[3 + i] * x[1]) + R[6 + i] * x[2];
+}
+__device__ __forceinline__ void m3t_mul_v(const double* R, const double* x, double* y) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) y[i] = (R[3 * i] * x[0] + R[3 * i + 1] * x[1]) + R[3 * i + 2] * x[2];
+}
+__device__ __forceinline__ void m3_mul_m(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) C[3 * j + i] = (A[i] * B[3 * j] + A[3 + i] * B[3 * j + 1]) + A[6 + i] * B[3 * j + 2];
+}
+__device__ __forceinline__ void m3t_mul_m(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+            C[3 * j + i] = (A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1]) + A[3 * i + 2] * B[3 * j + 2];
+}
+__device__ __forceinline__ double v3_dot(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+
+__device__ __forceinline__ void quat_mul(const double* a, const double* b, double* r) {
+    const double ax = a[0], ay = a[1], az = a[2], aw = a[3];
+    const double bx = b[0], by = b[1], bz = b[2], bw = b[3];
+    r[3] = aw * bw - ax * bx - ay * by - az * bz;
+    r[0] = aw * bx + ax * bw + ay * bz - az * by;
+    r[1] = aw * by + ay * bw + az * bx - ax * bz;
+    r[2] = aw * bz + az * bw + ax * by - ay * bx;
+}
+__device__ __forceinline__ double quat_sqnorm(const double* q) { return ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]; }
+__device__ __forceinline__ void quat_inverse(const double* q, double* r) {
+    const double n2 = quat_sqnorm(q);
+    if (n2 > 0) {
+        r[0] = -q[0] / n2;
+        r[1] = -q[1] / n2;
+        r[2] = -q[2] / n2;
+        r[3] = q[3] / n2;
+    } else {
+        r[0] = r[1] = r[2] = r[3] = 0;
+    }
+}
+__device__ __forceinline__ void quat_normalize(double* q) {
+    const double z = quat_sqnorm(q);
+    if (z > 0) {
+        const double s = sqrt(z);
+        q[0] /= s;
+        q[1] /= s;
+        q[2] /= s;
+        q[3] /= s;
+    }
+}
+// Eigen toRotationMatrix, column-major output
+__device__ __forceinline__ void quat_to_matrix(const double* q, double* R) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz);
+    R[3] = txy - twz;
+    R[6] = txz + twy;
+    R[1] = txy + twz;
+    R[4] = 1 - (txx + tzz);
+    R[7] = tyz - twx;
+    R[2] = txz - twy;
+    R[5] = tyz + twx;
+    R[8] = 1 - (txx + tyy);
+}
+
+// Eigen::AngleAxisd(quaternion) (rotation.cc:65-68): angle and unit axis
+__device__ __forceinline__ void quat_to_angle_axis(const double* q, double& angle, double* axis) {
+    double n = sqrt(v3_dot(q, q));
+    if (n < DBL_EPSILON) {
+        const double m = fmax(fabs(q[0]), fmax(fabs(q[1]), fabs(q[2])));
+        if (m > 0) {
+            const double a = q[0] / m, b = q[1] / m, c = q[2] / m;
+            n = m * sqrt((a * a + b * b) + c * c);
+        } else {
+            n = 0;
+        }
+    }
+    if (n != 0) {
+        angle = 2 * atan2(n, fabs(q[3]));
+        if (q[3] < 0) n = -n;
+        axis[0] = q[0] / n;
+        axis[1] = q[1] / n;
+        axis[2] = q[2] / n;
+    } else {
+        angle = 0;
+        axis[0] = 1;
+        axis[1] = 0;
+        axis[2] = 0;
+    }
+}
+
+// rotation.cc:59-63
+__device__ __forceinline__ void rotvec_to_quat(const double* rvec, double* q) {
+    const double z = v3_dot(rvec, rvec);
+    const double angle = sqrt(z);
+    double vec[3] = {rvec[0], rvec[1], rvec[2]};
+    if (z > 0) {
+        const double s = sqrt(z);
+        vec[0] /= s;
+        vec[1] /= s;
+        vec[2] /= s;
+    }
+    const double ha = 0.5 * angle;
+    double sn, cs;
+    sincos(ha, &sn, &cs);
+    q[3] = cs;
+    q[0] = sn * vec[0];
+    q[1] = sn * vec[1];
+    q[2] = sn * vec[2];
+}
+
+// misc.cc:80-95 then 97-103, reference operation order (used once per keyframe for the pose at `stamp`)
+__device__ inline void interpolate_pose(const InsSample& s0, const InsSample& s1, double midtime, const double* Rbc,
+                                        const double* tbc, double* R, double* t) {
+    double dp[3] = {s1.p[0] - s0.p[0], s1.p[1] - s0.p[1], s1.p[2] - s0.p[2]};
+    double q1inv[4], dq[4], rvec[3], axis[3], angle;
+    quat_inverse(s1.q, q1inv);
+    quat_mul(q1inv, s0.q, dq);
+    quat_to_angle_axis(dq, angle, axis);
+    rvec[0] = angle * axis[0];
+    rvec[1] = angle * axis[1];
+    rvec[2] = angle * axis[2];
+    const double scale = (midtime - s0.state_time) / (s1.state_time - s0.state_time);
+    rvec[0] = rvec[0] * scale;
+    rvec[1] = rvec[1] * scale;
+    rvec[2] = rvec[2] * scale;
+    rotvec_to_quat(rvec, dq);
+    double p[3] = {s0.p[0] + dp[0] * scale, s0.p[1] + dp[1] * scale, s0.p[2] + dp[2] * scale};
+    double dqinv[4], q[4];
+    quat_inverse(dq, dqinv);
+    quat_mul(s0.q, dqinv, q);
+    quat_normalize(q);
+    double Rq[9], Rt[3];
+    quat_to_matrix(q, Rq);
+    m3_mul_v(Rq, tbc, Rt);
+    t[0] = p[0] + Rt[0];
+    t[1] = p[1] + Rt[1];
+    t[2] = p[2] + Rt[2];
+    m3_mul_m(Rq, Rbc, R);
+}
+__device__ inline void state_pose(const InsSample& s, const double* Rbc, const double* tbc, double* R, double* t) {
+    double Rq[9], Rt[3];
+    quat_to_matrix(s.q, Rq);
+    m3_mul_v(Rq, tbc, Rt);
+    t[0] = s.p[0] + Rt[0];
+    t[1] = s.p[1] + Rt[1];
+    t[2] = s.p[2] + Rt[2];
+    m3_mul_m(Rq, Rbc, R);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fdlibm-lineage atanf / atan2f: the float overloads the reference's unqualified atan2 calls resolve to on
+// glibc (tracking.cc:317-320).  Same operation sequence as oracle/levins_oracle.c; no contraction (-fmad=false),
+// IEEE division.  Bit-identical to glibc 2.39's atan2f on 2e8 inputs (tests/test_oracle_math.py).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float atanf_fd(float x) {
+    const float hi0 = 4.6364760399e-01f, hi1 = 7.8539812565e-01f, hi2 = 9.8279368877e-01f, hi3 = 1.5707962513e+00f;
+    const float lo0 = 5.0121582440e-09f, lo1 = 3.7748947079e-08f, lo2 = 3.4473217170e-08f, lo3 = 7.5497894159e-08f;
+    const float c0 = 3.3333334327e-01f, c1 = -2.0000000298e-01f, c2 = 1.4285714924e-01f, c3 = -1.1111110449e-01f,
+                c4 = 9.0908870101e-02f, c5 = -7.6918758452e-02f, c6 = 6.6610731184e-02f, c7 = -5.8335702866e-02f,
+                c8 = 4.9768779427e-02f, c9 = -3.6531571299e-02f, c10 = 1.6285819933e-02f;
+    const int hx = __float_as_int(x);
+    const int ix = hx & 0x7fffffff;
+    float hi = 0.f, lo = 0.f;
+    int id;
+    if (ix >= 0x4c000000) {
+        if (ix > 0x7f800000) return x + x;
+        if (hx > 0) return hi3 + lo3;
+        return -hi3 - lo3;
+    }
+    if (ix < 0x3ee00000) {
+        if (ix < 0x31000000) return x;
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) {
+                id = 0;
+                hi = hi0;
+                lo = lo0;
+                x = (2.0f * x - 1.0f) / (2.0f + x);
+            } else {
+                id = 1;
+                hi = hi1;
+                lo = lo1;
+                x = (x - 1.0f) / (x + 1.0f);
+            }
+        } else {
+            if (ix < 0x401c0000) {
+                id = 2;
+                hi = hi2;
+                lo = lo2;
+                x = (x - 1.5f) / (1.0f + 1.5f * x);
+            } else {
+                id = 3;
+                hi = hi3;
+                lo = lo3;
+                x = -1.0f / x;
+            }
+        }
+    }
+    const float z = x * x;
+    const float w = z * z;
+    const float s1 = z * (c0 + w * (c2 + w * (c4 + w * (c6 + w * (c8 + w * c10)))));
+    const float s2 = w * (c1 + w * (c3 + w * (c5 + w * (c7 + w * c9))));
+    if (id < 0) return x - x * (s1 + s2);
+    const float r = hi - ((x * (s1 + s2) - lo) - x);
+    return (hx < 0) ? -r : r;
+}
+
+__device__ __forceinline__ float atan2f_fd(float y, float x) {
+    const float tiny = 1.0e-30f, pi_o_4 = 7.8539818525e-01f, pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f,
+                pi_lo = -8.7422776573e-08f;
+    const int hx = __float_as_int(x), hy = __float_as_int(y);
+    const int ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
+    if (ix > 0x7f800000 || iy > 0x7f800000) return x + y;
+    if (hx == 0x3f800000) return atanf_fd(y);
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) {
+        switch (m) {
+        case 0:
+        case 1: return y;
+        case 2: return pi + tiny;
+        default: return -pi - tiny;
+        }
+    }
+    if (ix == 0) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    if (ix == 0x7f800000) {
+        if (iy == 0x7f800000) {
+            switch (m) {
+            case 0: return pi_o_4 + tiny;
+            case 1: return -pi_o_4 - tiny;
+            case 2: return 3.0f * pi_o_4 + tiny;
+            default: return -3.0f * pi_o_4 - tiny;
+            }
+        } else {
+            switch (m) {
+            case 0: return 0.0f;
+            case 1: return -0.0f;
+            case 2: return pi + tiny;
+            default: return -pi - tiny;
+            }
+        }
+    }
+    if (iy == 0x7f800000) return (hy < 0) ? -pi_o_2 - tiny : pi_o_2 + tiny;
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60)
+        z = pi_o_2 + 0.5f * pi_lo;
+    else if (hx < 0 && k < -60)
+        z = 0.0f;
+    else
+        z = atanf_fd(fabsf(y / x));
+    switch (m) {
+    case 0: return z;
+    case 1: return __int_as_float(__float_as_int(z) ^ (int) 0x80000000);
+    case 2: return pi - (z - pi_lo);
+    default: return (z - pi_lo) - pi;
+    }
+}
+
+// Eigen Vector3f redux order: e0 + (e1 + e2)
+__device__ __forceinline__ float v3f_sqnorm(float x, float y, float z) { return x * x + (y * y + z * z); }
+
+// ------------------------------------------------------------------------------------------------
+// stage 2: cell of a camera-frame point (tracking.cc:311-331).  Returns -1 when the point is rejected.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int angle_to_index(double a, const Consts& c) {
+    // (int) round(a / ANGLE) (tracking.cc:323-324).  Fast path: multiply by the reciprocal; whenever the product is
+    // close enough to a rounding boundary for the last-bit difference to matter, redo it with the true division.
+    const double qf = a * c.inv_angle;
+    const double r = round(qf);
+    if (fabs(fabs(qf - r) - 0.5) < 1e-9) return (int) round(a / c.angle);
+    return (int) r;
+}
+
+template <int LIBM_MODE>
+__device__ __forceinline__ int cell_of_point(float x, float y, float z, const Consts& c) {
+    if ((z < 0.f) || ((double) fabsf(x / z) > c.tan_value) || ((double) fabsf(y / z) > c.tan_value)) return -1;
+    const float s = x * x + z * z;
+    double row_angle, col_angle;
+    if (LIBM_MODE == 0) {
+        row_angle = (double) atan2f_fd(y, sqrtf(s)) + c.half_offset;
+        col_angle = (double) atan2f_fd(z, x) - c.half_offset;
+    } else {
+        row_angle = atan2((double) y, sqrt((double) s)) + c.half_offset;
+        col_angle = atan2((double) z, (double) x) - c.half_offset;
+    }
+    const int row = angle_to_index(row_angle, c);
+    const int col = angle_to_index(col_angle, c);
+    if ((row < 0) || (col < 0) || (row >= IMG) || (col >= IMG)) return -1;
+    return col + row * IMG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1: interval lookup (misc.cc:25-60 semantics) and per-point deskew
+// ------------------------------------------------------------------------------------------------
+// Returns the table entry index: i in [1, n-1] with time[i-1] <= t < time[i], or 0 (fallback) outside the window.
+__device__ __forceinline__ int find_interval(const Interval* __restrict__ tab, int n_ins, double t, double t0,
+                                             double t_last, double inv_mean_dt) {
+    if (n_ins < 2 || t0 > t || t_last <= t) return 0; // misc.cc:28-30 (n == 1: one of the two conditions always holds)
+    int lo = 1, hi = n_ins - 1;
+    int g = 1 + (int) ((t - t0) * inv_mean_dt);
+    g = min(max(g, lo), hi);
+#pragma unroll 1
+    for (int it = 0; it < 40; it++) {
+        const double a = __ldg(&tab[g].t_lo), b = __ldg(&tab[g].t_hi);
+        if (t < a) {
+            hi = g - 1;
+            g = (it < 2) ? g - 1 : (lo + hi) >> 1;
+        } else if (t >= b) {
+            lo = g + 1;
+            g = (it < 2) ? g + 1 : (lo + hi) >> 1;
+        } else {
+            return g;
+        }
+        if (lo > hi) return 0; // non-monotonic times: no bracketing interval (the reference would give up after 16 rounds)
+        g = min(max(g, lo), hi);
+    }
+    return 0;
+}
+
+// sin(phi) and 1 - cos(phi); Taylor to full double precision for the small angles of one INS interval
+__device__ __forceinline__ void sin_omc(double phi, double& sn, double& omc) {
+    const double p2 = phi * phi;
+    if (p2 < 0.0625) { // |phi| < 0.25 rad: truncation error < 3e-18 relative
+        double a = fma(p2, -1.0 / 156.0, 1.0);
+        a = fma(p2 * (-1.0 / 110.0), a, 1.0);
+        a = fma(p2 * (-1.0 / 72.0), a, 1.0);
+        a = fma(p2 * (-1.0 / 42.0), a, 1.0);
+        a = fma(p2 * (-1.0 / 20.0), a, 1.0);
+        a = fma(p2 * (-1.0 / 6.0), a, 1.0);
+        sn = phi * a;
+        double b = fma(p2, -1.0 / 182.0, 1.0);
+        b = fma(p2 * (-1.0 / 132.0), b, 1.0);
+        b = fma(p2 * (-1.0 / 90.0), b, 1.0);
+        b = fma(p2 * (-1.0 / 56.0), b, 1.0);
+        b = fma(p2 * (-1.0 / 30.0), b, 1.0);
+        b = fma(p2 * (-1.0 / 12.0), b, 1.0);
+        omc = 0.5 * p2 * b;
+    } else {
+        double s, cs, sh, ch;
+        sincos(phi, &s, &cs);
+        sincos(0.5 * phi, &sh, &ch);
+        sn = s;
+        omc = 2.0 * sh * sh;
+    }
+}
+
+struct KfView {
+    const Interval* tab;
+    int n_ins;
+    double t0, t_last, inv_mean_dt;
+};
+
+// Range gate (le_vins.cc:447-451) + deskew into the keyframe's camera frame (le_vins.cc:455-461).
+// Returns false for gated points.  The two f32 roundings of pointcloud.cc:68 are kept.
+__device__ __forceinline__ bool deskew_point(float x, float y, float z, double time, const KfView& kv,
+                                             const Extrinsics& e, const Consts& c, float& ox, float& oy, float& oz) {
+    const float norm = sqrtf(v3f_sqnorm(x, y, z));
+    if (((double) norm > c.farthest) || ((double) norm < c.nearest)) return false;
+    const double t = time + e.td_b_l;
+    const int idx = find_interval(kv.tab, kv.n_ins, t, kv.t0, kv.t_last, kv.inv_mean_dt);
+    const Interval* __restrict__ it = kv.tab + idx;
+
+    // p_c1 = f32(R_cl p + t_cl)   (pointcloud.cc:38 -> 68, first rounding)
+    const double xd = x, yd = y, zd = z;
+    const float p1x = (float) fma(e.Rcl[6], zd, fma(e.Rcl[3], yd, fma(e.Rcl[0], xd, e.tcl[0])));
+    const float p1y = (float) fma(e.Rcl[7], zd, fma(e.Rcl[4], yd, fma(e.Rcl[1], xd, e.tcl[1])));
+    const float p1z = (float) fma(e.Rcl[8], zd, fma(e.Rcl[5], yd, fma(e.Rcl[2], xd, e.tcl[2])));
+    const double ax = p1x, ay = p1y, az = p1z;
+    // u = R_bc p_c1 + t_bc
+    const double ux = fma(e.Rbc[6], az, fma(e.Rbc[3], ay, fma(e.Rbc[0], ax, e.tbc[0])));
+    const double uy = fma(e.Rbc[7], az, fma(e.Rbc[4], ay, fma(e.Rbc[1], ax, e.tbc[1])));
+    const double uz = fma(e.Rbc[8], az, fma(e.Rbc[5], ay, fma(e.Rbc[2], ax, e.tbc[2])));
+
+    // the entry as 11 x 16-byte read-only loads (uniform across a warp almost always => one L1 wavefront each)
+    const double2* __restrict__ e2 = reinterpret_cast<const double2*>(it);
+    const double2 v1 = __ldg(e2 + 1), v2 = __ldg(e2 + 2), v3 = __ldg(e2 + 3), v4 = __ldg(e2 + 4), v5 = __ldg(e2 + 5),
+                  v6 = __ldg(e2 + 6), v7 = __ldg(e2 + 7), v8 = __ldg(e2 + 8), v9 = __ldg(e2 + 9), v10 = __ldg(e2 + 10),
+                  v11 = __ldg(e2 + 11);
+    const double s = (t - v1.x) * v1.y;
+    const double kx = v6.y, ky = v7.x, kz = v7.y;
+    double sn, omc;
+    sin_omc(-s * v8.x, sn, omc);
+    // w = u + sin * (k x u) + (1 - cos) * k x (k x u)
+    const double cx = ky * uz - kz * uy, cy = kz * ux - kx * uz, cz = kx * uy - ky * ux;
+    const double dx = ky * cz - kz * cy, dy = kz * cx - kx * cz, dz = kx * cy - ky * cx;
+    const double wx = fma(omc, dx, fma(sn, cx, ux));
+    const double wy = fma(omc, dy, fma(sn, cy, uy));
+    const double wz = fma(omc, dz, fma(sn, cz, uz));
+    // p_c0 = A w + c0 + s c1   (second rounding, pointcloud.cc:45 -> 68)
+    const double rx = fma(v3.x, wz, fma(v2.y, wy, fma(v2.x, wx, fma(s, v10.x, v8.y))));
+    const double ry = fma(v4.y, wz, fma(v4.x, wy, fma(v3.y, wx, fma(s, v10.y, v9.x))));
+    const double rz = fma(v6.x, wz, fma(v5.y, wy, fma(v5.x, wx, fma(s, v11.x, v9.y))));
+    ox = (float) rx;
+    oy = (float) ry;
+    oz = (float) rz;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Eigen::ColPivHouseholderQR<Matrix<double,5,3>> compute + solve, same sequence as the oracle
+// ------------------------------------------------------------------------------------------------
+__device__ inline void colpiv_qr_solve_5x3(const double (*P)[3], double* x) {
+    constexpr int ROWS = 5, COLS = 3;
+    double q[COLS][ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++)
+#pragma unroll
+        for (int cI = 0; cI < COLS; cI++) q[cI][r] = P[r][cI];
+    double hcoef[COLS];
+    int perm[COLS] = {0, 1, 2};
+    double nu[COLS], nd[COLS];
+#pragma unroll
+    for (int k = 0; k < COLS; k++) {
+        double s = 0;
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) s += q[k][r] * q[k][r];
+        nd[k] = sqrt(s);
+        nu[k] = nd[k];
+    }
+    double maxn = nu[0];
+    if (nu[1] > maxn) maxn = nu[1];
+    if (nu[2] > maxn) maxn = nu[2];
+    const double th = maxn * DBL_EPSILON / (double) ROWS;
+    const double threshold_helper = th * th;
+    const double downdate = sqrt(DBL_EPSILON);
+    int nonzero = COLS;
+
+#pragma unroll
+    for (int k = 0; k < COLS; k++) {
+        int big = k;
+        double bigv = nu[k];
+#pragma unroll
+        for (int j = k + 1; j < COLS; j++)
+            if (nu[j] > bigv) {
+                bigv = nu[j];
+                big = j;
+            }
+        if (nonzero == COLS && bigv * bigv < threshold_helper * (double) (ROWS - k)) nonzero = k;
+        if (k != big) {
+#pragma unroll
+            for (int j = k + 1; j < COLS; j++) {
+                if (j == big) {
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        const double tmp = q[k][r];
+                        q[k][r] = q[j][r];
+                        q[j][r] = tmp;
+                    }
+                    double tmp = nu[k];
+                    nu[k] = nu[j];
+                    nu[j] = tmp;
+                    tmp = nd[k];
+                    nd[k] = nd[j];
+                    nd[j] = tmp;
+                    const int ti = perm[k];
+                    perm[k] = perm[j];
+                    perm[j] = ti;
+                }
+            }
+        }
+        const int len = ROWS - k;
+        double tail_sq = 0;
+#pragma unroll
+        for (int r = 1; r < ROWS; r++)
+            if (r < len) tail_sq += q[k][k + r] * q[k][k + r];
+        const double c0 = q[k][k];
+        double beta, tau;
+        if (tail_sq <= DBL_MIN) {
+            tau = 0;
+            beta = c0;
+#pragma unroll
+            for (int r = 1; r < ROWS; r++)
+                if (r < len) q[k][k + r] = 0;
+        } else {
+            beta = sqrt(c0 * c0 + tail_sq);
+            if (c0 >= 0) beta = -beta;
+#pragma unroll
+            for (int r = 1; r < ROWS; r++)
+                if (r < len) q[k][k + r] = q[k][k + r] / (c0 - beta);
+            tau = (beta - c0) / beta;
+        }
+        hcoef[k] = tau;
+        q[k][k] = beta;
+        if (tau != 0) {
+#pragma unroll
+            for (int j = k + 1; j < COLS; j++) {
+                double tmp = 0;
+#pragma unroll
+                for (int r = 1; r < ROWS; r++)
+                    if (r < len) tmp += q[k][k + r] * q[j][k + r];
+                tmp += q[j][k];
+                q[j][k] -= tau * tmp;
+#pragma unroll
+                for (int r = 1; r < ROWS; r++)
+                    if (r < len) q[j][k + r] -= (tau * q[k][k + r]) * tmp;
+            }
+        }
+#pragma unroll
+        for (int j = k + 1; j < COLS; j++) {
+            if (nu[j] != 0) {
+                double temp = fabs(q[j][k]) / nu[j];
+                temp = (1.0 + temp) * (1.0 - temp);
+                temp = temp < 0 ? 0 : temp;
+                const double ratio = nu[j] / nd[j];
+                const double temp2 = temp * (ratio * ratio);
+                if (temp2 <= downdate) {
+                    double s = 0;
+#pragma unroll
+                    for (int r = 1; r < ROWS; r++)
+                        if (r >= k + 1) s += q[j][r] * q[j][r];
+                    nd[j] = sqrt(s);
+                    nu[j] = nd[j];
+                } else {
+                    nu[j] *= sqrt(temp);
+                }
+            }
+        }
+    }
+
+    double c[ROWS] = {-1.0, -1.0, -1.0, -1.0, -1.0}; // mb = -Ones (tracking.cc:585)
+#pragma unroll
+    for (int k = 0; k < COLS; k++) {
+        if (k < nonzero) {
+            const double tau = hcoef[k];
+            const int len = ROWS - k;
+            if (tau != 0) {
+                double tmp = 0;
+#pragma unroll
+                for (int r = 1; r < ROWS; r++)
+                    if (r < len) tmp += q[k][k + r] * c[k + r];
+                tmp += c[k];
+                c[k] -= tau * tmp;
+#pragma unroll
+                for (int r = 1; r < ROWS; r++)
+                    if (r < len) c[k + r] -= (tau * q[k][k + r]) * tmp;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = COLS - 1; i >= 0; i--) {
+        if (i < nonzero) {
+            c[i] /= q[i][i];
+#pragma unroll
+            for (int r = 0; r < COLS; r++)
+                if (r < i) c[r] -= c[i] * q[i][r];
+        }
+    }
+    x[0] = x[1] = x[2] = 0;
+#pragma unroll
+    for (int i = 0; i < COLS; i++)
+        if (i < nonzero) {
+            // x[perm[i]] = c[i] without dynamic register indexing
+            if (perm[i] == 0) x[0] = c[i];
+            if (perm[i] == 1) x[1] = c[i];
+            if (perm[i] == 2) x[2] = c[i];
+        }
+}
+
+} // namespace lv

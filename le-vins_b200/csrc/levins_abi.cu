@@ -1,0 +1,908 @@
+// levins_abi.cu -- host side of liblevins_b200.so: context, device memory, launch sequencing, the C ABI.
+// No torch, no third-party libraries; CUDA runtime only.  There is no CPU fallback: every compute entry point
+// launches the sm_100a kernels of kernels.cuh and reports LEVINS_ERR_CUDA when that is impossible.
+#include "levins/abi.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace lv;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        size_t alloc = need + need / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, alloc);
+        if (e == cudaSuccess) bytes = alloc;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+} // namespace
+
+struct levins_ctx {
+    int device = 0;
+    levins_config cfg{};
+    Consts consts{};
+    Extrinsics ext{};
+    bool have_ext = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    std::mutex mu; // append_scan may come from another thread
+    uint64_t launches = 0;
+
+    // ---- streaming state ----
+    DevBuf ring;      // PointXYZIT x cfg.max_points
+    DevBuf ring_state; // RingState
+    uint64_t ring_tail = 0;     // physical index one past the newest point
+    uint64_t ring_count_ub = 0; // host's upper bound of the live point count
+    DevBuf s_ins, s_table, s_kf, s_queries;
+    DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2;
+    DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
+    DevBuf s_in_cloud; // explicit cloud uploaded by build_range_image
+    DevBuf s_zbuf, s_cells, s_c2c, s_unit, s_winner;
+    bool s_zbuf_init = false;
+    size_t s_cloud_n = 0;     // points in the resident cloud
+    bool s_cloud_valid = false;
+    bool s_image_valid = false;
+    bool s_image_from_raw = false; // cells were built from the ring (fused) rather than from a cloud
+    void* pinned = nullptr;        // small pinned staging area for results / state
+    size_t pinned_bytes = 0;
+
+    // ---- batch state ----
+    DevBuf b_pts, b_ins, b_table, b_queries, b_kfs;
+    DevBuf b_type, b_xyzd, b_flags;
+    DevBuf b_zbuf, b_cells;
+    std::vector<levins_keyframe_desc> b_descs;
+    size_t b_nq = 0, b_npts = 0, b_nins = 0;
+    int b_wave = 16;
+    int b_wave_alloc = 0;
+    bool b_valid = false;
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    struct EvSpan {
+        int kind;
+        size_t e0, e1;
+    };
+    std::vector<EvSpan> ev_spans;
+    float prof_ms[4] = {0, 0, 0, 0};
+    uint32_t prof_launches[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(levins_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+int cuda_fail(levins_ctx* c, cudaError_t e, const char* what) {
+    return fail(c, LEVINS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                    \
+    do {                                                            \
+        cudaError_t e__ = (call);                                   \
+        if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call);  \
+    } while (0)
+
+// tracking.h:119-135 evaluated with the reference's own double expressions, on the host's libm like the reference
+Consts make_consts(const levins_config& cfg) {
+    Consts c{};
+    const double ANGLE = 0.3 * M_PI / 180.0;
+    const double FOV = 90.0 * M_PI / 180.0;
+    c.angle = ANGLE;
+    c.inv_angle = 1.0 / ANGLE;
+    c.half_offset = M_PI * 0.5 - FOV * 0.5;
+    c.tan_value = tan(FOV * 0.5);
+    const double thr = sin(ANGLE) * cfg.nearest_distance_counts;
+    c.thr2 = pow(thr, 2);
+    c.nearest = cfg.nearest_depth;
+    c.farthest = cfg.farthest_depth;
+    c.plane_residual = cfg.plane_residual_threshold;
+    c.range_spread = cfg.range_spread_threshold;
+    c.stack_interval = cfg.stack_interval;
+    c.libm_mode = cfg.libm_mode;
+    return c;
+}
+
+int fill_zbuf(levins_ctx* ctx, unsigned long long* z, size_t n) {
+    k_fill_u64<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(z, n, EMPTY_KEY);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return LEVINS_OK;
+}
+
+int ensure_stream_buffers(levins_ctx* ctx, size_t n_ins, size_t n_feat) {
+    CU(ctx->s_ins.ensure(std::max<size_t>(n_ins, 1) * sizeof(InsSample)));
+    CU(ctx->s_table.ensure(std::max<size_t>(n_ins, 1) * sizeof(Interval)));
+    CU(ctx->s_kf.ensure(sizeof(KfState)));
+    CU(ctx->s_queries.ensure(std::max<size_t>(n_feat, 1) * 3 * sizeof(float)));
+    CU(ctx->s_type.ensure(std::max<size_t>(n_feat, 1)));
+    CU(ctx->s_xyzd.ensure(std::max<size_t>(n_feat, 1) * 16));
+    CU(ctx->s_flags.ensure(std::max<size_t>(n_feat, 1) * 4));
+    CU(ctx->s_knn_idx.ensure(std::max<size_t>(n_feat, 1) * 20));
+    CU(ctx->s_knn_d2.ensure(std::max<size_t>(n_feat, 1) * 20));
+    CU(ctx->s_cells.ensure((size_t) CELLS * sizeof(float4)));
+    CU(ctx->s_c2c.ensure((size_t) CELLS * 4));
+    CU(ctx->s_unit.ensure((size_t) CELLS * sizeof(PointXYZI)));
+    CU(ctx->s_winner.ensure((size_t) CELLS * 4));
+    if (!ctx->s_zbuf.p) {
+        CU(ctx->s_zbuf.ensure((size_t) CELLS * 8));
+        ctx->s_zbuf_init = false;
+    }
+    if (!ctx->s_zbuf_init) {
+        int r = fill_zbuf(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS);
+        if (r) return r;
+        ctx->s_zbuf_init = true;
+    }
+    return LEVINS_OK;
+}
+
+int ensure_ring(levins_ctx* ctx) {
+    if (ctx->ring.p) return LEVINS_OK;
+    CU(ctx->ring.ensure((size_t) ctx->cfg.max_points * sizeof(PointXYZIT)));
+    ctx->ring.bytes = (size_t) ctx->cfg.max_points * sizeof(PointXYZIT);
+    CU(ctx->ring_state.ensure(sizeof(RingState)));
+    CU(cudaMemsetAsync(ctx->ring_state.p, 0, sizeof(RingState), ctx->stream));
+    ctx->ring_tail = 0;
+    ctx->ring_count_ub = 0;
+    return LEVINS_OK;
+}
+
+void launch_deskew(levins_ctx* ctx, dim3 grid, const DeskewArgs& a, bool write_cloud) {
+    if (ctx->consts.libm_mode == 0) {
+        if (write_cloud)
+            k_deskew_bin<0, true><<<grid, DESKEW_THREADS, 0, ctx->stream>>>(a);
+        else
+            k_deskew_bin<0, false><<<grid, DESKEW_THREADS, 0, ctx->stream>>>(a);
+    } else {
+        if (write_cloud)
+            k_deskew_bin<1, true><<<grid, DESKEW_THREADS, 0, ctx->stream>>>(a);
+        else
+            k_deskew_bin<1, false><<<grid, DESKEW_THREADS, 0, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+}
+
+// read the ring state (synchronises)
+int read_ring_state(levins_ctx* ctx, RingState* out) {
+    CU(cudaMemcpyAsync(ctx->pinned, ctx->ring_state.p, sizeof(RingState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->pinned, sizeof(RingState));
+    ctx->ring_count_ub = out->count;
+    return LEVINS_OK;
+}
+
+// stage 1 on the ring: k_prepare (+ pops) then k_deskew_bin.  Leaves KfState in s_kf.
+int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins, bool write_cloud, bool bin) {
+    if (!ctx->have_ext) return fail(ctx, LEVINS_ERR_STATE, "levins_set_extrinsics has not been called");
+    if (!ins || n_ins == 0) return fail(ctx, LEVINS_ERR_ARG, "empty INS window");
+    if (n_ins > ctx->cfg.max_ins) return fail(ctx, LEVINS_ERR_CAPACITY, "INS window larger than config.max_ins");
+    if (!ctx->ring.p || ctx->ring_count_ub == 0) return LEVINS_EMPTY; // le_vins.cc:378: lidar_point_buffer_.empty()
+    CU(cudaMemcpyAsync(ctx->s_ins.p, ins, n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
+    KfState kf{};
+    kf.pt_begin = 0;
+    kf.pt_count = 0;
+    kf.ins_begin = 0;
+    kf.ins_count = n_ins;
+    kf.q_begin = 0;
+    kf.q_count = 0;
+    kf.stamp = stamp;
+    memcpy(ctx->pinned, &kf, sizeof(kf));
+    CU(cudaMemcpyAsync(ctx->s_kf.p, ctx->pinned, sizeof(kf), cudaMemcpyHostToDevice, ctx->stream));
+    PrepareArgs pa{};
+    pa.kfs = ctx->s_kf.as<KfState>();
+    pa.pts = ctx->ring.as<PointXYZIT>();
+    pa.pts_cap = ctx->cfg.max_points;
+    pa.ins = ctx->s_ins.as<InsSample>();
+    pa.table = ctx->s_table.as<Interval>();
+    pa.ring = ctx->ring_state.as<RingState>();
+    pa.ext = ctx->ext;
+    pa.c = ctx->consts;
+    k_prepare<<<1, 128, 0, ctx->stream>>>(pa);
+    ctx->launches++;
+    CU(cudaGetLastError());
+
+    const size_t n_ub = ctx->ring_count_ub;
+    if (write_cloud) CU(ctx->s_cloud.ensure(n_ub * sizeof(PointXYZI)));
+    DeskewArgs da{};
+    da.kfs = ctx->s_kf.as<KfState>();
+    da.pts = ctx->ring.as<PointXYZIT>();
+    da.pts_cap = ctx->cfg.max_points;
+    da.table = ctx->s_table.as<Interval>();
+    da.zbuf = ctx->s_zbuf.as<unsigned long long>();
+    da.cloud_out = write_cloud ? ctx->s_cloud.as<PointXYZI>() : nullptr;
+    da.ext = ctx->ext;
+    da.c = ctx->consts;
+    (void) bin;
+    dim3 grid((unsigned) ((n_ub + DESKEW_THREADS - 1) / DESKEW_THREADS), 1);
+    if (grid.x == 0) grid.x = 1;
+    launch_deskew(ctx, grid, da, write_cloud);
+    CU(cudaGetLastError());
+    return LEVINS_OK;
+}
+
+int run_finalize_stream(levins_ctx* ctx, bool from_cloud, const PointXYZI* cloud, bool want_winner) {
+    FinalizeArgs fa{};
+    fa.kfs = ctx->s_kf.as<KfState>();
+    fa.pts = ctx->ring.as<PointXYZIT>();
+    fa.pts_cap = ctx->cfg.max_points;
+    fa.table = ctx->s_table.as<Interval>();
+    fa.cloud = cloud;
+    fa.zbuf = ctx->s_zbuf.as<unsigned long long>();
+    fa.cells = ctx->s_cells.as<float4>();
+    fa.winner = want_winner ? ctx->s_winner.as<int32_t>() : nullptr;
+    fa.ext = ctx->ext;
+    fa.c = ctx->consts;
+    dim3 grid((CELLS + FINALIZE_THREADS - 1) / FINALIZE_THREADS, 1);
+    if (from_cloud)
+        k_finalize<true><<<grid, FINALIZE_THREADS, 0, ctx->stream>>>(fa);
+    else
+        k_finalize<false><<<grid, FINALIZE_THREADS, 0, ctx->stream>>>(fa);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return LEVINS_OK;
+}
+
+int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx) {
+    AssocArgs aa{};
+    aa.kfs = ctx->s_kf.as<KfState>();
+    aa.queries = ctx->s_queries.as<float>();
+    aa.cells = ctx->s_cells.as<float4>();
+    aa.c2c = with_idx ? ctx->s_c2c.as<int32_t>() : nullptr;
+    aa.type = ctx->s_type.as<int8_t>();
+    aa.xyz_depth = ctx->s_xyzd.as<float4>();
+    aa.flags = ctx->s_flags.as<int32_t>();
+    aa.knn_idx = with_idx ? ctx->s_knn_idx.as<int32_t>() : nullptr;
+    aa.knn_d2 = with_idx ? ctx->s_knn_d2.as<float>() : nullptr;
+    aa.c = ctx->consts;
+    dim3 grid((unsigned) ((nf + ASSOC_WARPS - 1) / ASSOC_WARPS), 1);
+    k_associate<<<grid, ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return LEVINS_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+// lifecycle
+// =================================================================================================
+extern "C" int levins_abi_version(void) { return LEVINS_ABI_VERSION; }
+
+extern "C" void levins_config_default(levins_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = sizeof(levins_config);
+    cfg->libm_mode = 0;
+    cfg->stack_interval = 0.5;          // le_vins.h:130
+    cfg->reserved_buffer_length = 10.0; // le_vins.h RESERVED_BUFFER_LENGTH
+    cfg->nearest_depth = 1.0;           // visual_mappoint.h:50
+    cfg->farthest_depth = 200.0;        // visual_mappoint.h:51
+    cfg->plane_residual_threshold = 0.1;
+    cfg->range_spread_threshold = 0.5;
+    cfg->nearest_distance_counts = 3;
+    cfg->max_points = 1ull << 24; // 16 Mi points = 512 MiB: 11 s of an OS1-128
+    cfg->max_ins = 4096;
+    cfg->max_features = 4096;
+}
+
+extern "C" const char* levins_status_string(int s) {
+    switch (s) {
+    case LEVINS_OK: return "ok";
+    case LEVINS_EMPTY: return "empty";
+    case LEVINS_ERR_ARG: return "invalid argument";
+    case LEVINS_ERR_CUDA: return "CUDA error";
+    case LEVINS_ERR_CAPACITY: return "capacity exceeded";
+    case LEVINS_ERR_STATE: return "invalid state";
+    default: return "unknown";
+    }
+}
+
+extern "C" int levins_create(int device, const levins_config* cfg, levins_ctx** out) {
+    if (!out) return LEVINS_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+        fprintf(stderr, "levins_create: no usable CUDA device %d (%s); this library has no CPU fallback\n", device,
+                e == cudaSuccess ? "device count is 0 or ordinal out of range" : cudaGetErrorString(e));
+        return LEVINS_ERR_CUDA;
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        fprintf(stderr, "levins_create: device %d is sm_%d%d; the kernels are built for sm_100a only\n", device, prop.major,
+                prop.minor);
+        return LEVINS_ERR_CUDA;
+    }
+    levins_ctx* ctx = new levins_ctx();
+    ctx->device = device;
+    levins_config_default(&ctx->cfg);
+    if (cfg) {
+        size_t n = std::min<size_t>(cfg->struct_size ? cfg->struct_size : sizeof(levins_config), sizeof(levins_config));
+        memcpy(&ctx->cfg, cfg, n);
+        ctx->cfg.struct_size = sizeof(levins_config);
+    }
+    if (ctx->cfg.max_points == 0 || ctx->cfg.max_ins == 0 || ctx->cfg.stack_interval <= 0) {
+        delete ctx;
+        return LEVINS_ERR_ARG;
+    }
+    ctx->consts = make_consts(ctx->cfg);
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost(&ctx->pinned, 1 << 20) != cudaSuccess) {
+        delete ctx;
+        return LEVINS_ERR_CUDA;
+    }
+    ctx->pinned_bytes = 1 << 20;
+    ctx->own_stream = true;
+    *out = ctx;
+    return LEVINS_OK;
+}
+
+extern "C" void levins_destroy(levins_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
+                      &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_cloud, &ctx->s_in_cloud,
+                      &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
+                      &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_type, &ctx->b_xyzd, &ctx->b_flags, &ctx->b_zbuf,
+                      &ctx->b_cells})
+        b->release();
+    for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* levins_last_error(const levins_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int levins_set_stream(levins_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+    return LEVINS_OK;
+}
+
+extern "C" int levins_synchronize(levins_ctx* ctx) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LEVINS_OK;
+}
+
+extern "C" int levins_set_extrinsics(levins_ctx* ctx, const levins_pose* pose_b_c, const levins_pose* pose_c_l, double td_b_l) {
+    if (!ctx || !pose_b_c || !pose_c_l) return fail(ctx, LEVINS_ERR_ARG, "null pose");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    memcpy(ctx->ext.Rbc, pose_b_c->R, sizeof(double) * 9);
+    memcpy(ctx->ext.tbc, pose_b_c->t, sizeof(double) * 3);
+    memcpy(ctx->ext.Rcl, pose_c_l->R, sizeof(double) * 9);
+    memcpy(ctx->ext.tcl, pose_c_l->t, sizeof(double) * 3);
+    ctx->ext.td_b_l = td_b_l;
+    ctx->have_ext = true;
+    return LEVINS_OK;
+}
+
+extern "C" int levins_set_profiling(levins_ctx* ctx, int enabled) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    ctx->profiling = enabled != 0;
+    return LEVINS_OK;
+}
+
+extern "C" uint64_t levins_launch_count(const levins_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// =================================================================================================
+// streaming API
+// =================================================================================================
+extern "C" int levins_append_scan(levins_ctx* ctx, const levins_point_xyzit* points, size_t n) {
+    if (!ctx || (!points && n)) return fail(ctx, LEVINS_ERR_ARG, "null points");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return LEVINS_OK;
+    int r = ensure_ring(ctx);
+    if (r) return r;
+    const uint64_t cap = ctx->cfg.max_points;
+    if (ctx->ring_count_ub + n > cap) { // learn the exact live count before refusing
+        RingState st;
+        r = read_ring_state(ctx, &st);
+        if (r) return r;
+        if (st.count + n > cap) return fail(ctx, LEVINS_ERR_CAPACITY, "ring buffer full: raise config.max_points");
+    }
+    const uint64_t tail = ctx->ring_tail;
+    const uint64_t first = std::min<uint64_t>(n, cap - tail);
+    PointXYZIT* base = ctx->ring.as<PointXYZIT>();
+    CU(cudaMemcpyAsync(base + tail, points, first * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
+    if (first < n)
+        CU(cudaMemcpyAsync(base, points + first, (n - first) * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->ring_tail = (tail + n) % cap;
+    ctx->ring_count_ub += n;
+    const double reserved = ctx->cfg.reserved_buffer_length + ctx->cfg.stack_interval * 2; // le_vins.cc:156
+    k_ring_append<<<1, 32, 0, ctx->stream>>>(ctx->ring_state.as<RingState>(), base, cap, n, reserved);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return LEVINS_OK;
+}
+
+extern "C" int levins_buffer_info(levins_ctx* ctx, size_t* n_points, double* t_front, double* t_back) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n_points) *n_points = 0;
+    if (t_front) *t_front = 0;
+    if (t_back) *t_back = 0;
+    if (!ctx->ring.p) return LEVINS_OK;
+    RingState st;
+    int r = read_ring_state(ctx, &st);
+    if (r) return r;
+    if (n_points) *n_points = st.count;
+    if (st.count) {
+        const uint64_t cap = ctx->cfg.max_points;
+        PointXYZIT a, b;
+        CU(cudaMemcpy(&a, ctx->ring.as<PointXYZIT>() + st.head, sizeof(a), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&b, ctx->ring.as<PointXYZIT>() + (st.head + st.count - 1) % cap, sizeof(b), cudaMemcpyDeviceToHost));
+        if (t_front) *t_front = a.time;
+        if (t_back) *t_back = b.time;
+    }
+    return LEVINS_OK;
+}
+
+extern "C" int levins_buffer_clear(levins_ctx* ctx) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->ring.p) CU(cudaMemsetAsync(ctx->ring_state.p, 0, sizeof(RingState), ctx->stream));
+    ctx->ring_tail = 0;
+    ctx->ring_count_ub = 0;
+    ctx->s_cloud_valid = false;
+    ctx->s_image_valid = false;
+    return LEVINS_OK;
+}
+
+// read KfState + ring state back (one small copy, synchronises)
+static int fetch_kf(levins_ctx* ctx, KfState* kf) {
+    char* pin = reinterpret_cast<char*>(ctx->pinned);
+    CU(cudaMemcpyAsync(pin, ctx->s_kf.p, sizeof(KfState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(pin + 256, ctx->ring_state.p, sizeof(RingState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(kf, pin, sizeof(KfState));
+    RingState st;
+    memcpy(&st, pin + 256, sizeof(st));
+    ctx->ring_count_ub = st.count;
+    return LEVINS_OK;
+}
+
+extern "C" int levins_stack_deskew(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins,
+                                   levins_point_xyzi* out_cloud, size_t out_capacity, size_t* n_out) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n_out) *n_out = 0;
+    ctx->s_cloud_valid = false;
+    ctx->s_image_valid = false;
+    int r = ensure_stream_buffers(ctx, n_ins, 1);
+    if (r) return r;
+    r = run_stage1(ctx, stamp, ins, n_ins, /*write_cloud=*/true, /*bin=*/true);
+    if (r) return r;
+    KfState kf;
+    r = fetch_kf(ctx, &kf);
+    if (r) return r;
+    ctx->s_cloud_n = kf.n_proj;
+    ctx->s_cloud_valid = true;
+    ctx->s_image_from_raw = true; // the z-buffer now holds this keyframe's winners (finalised lazily)
+    if (n_out) *n_out = kf.n_proj;
+    if (out_cloud && kf.n_proj) {
+        if (out_capacity < kf.n_proj) return fail(ctx, LEVINS_ERR_CAPACITY, "out_cloud too small");
+        CU(cudaMemcpyAsync(out_cloud, ctx->s_cloud.p, (size_t) kf.n_proj * sizeof(PointXYZI), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return kf.status ? LEVINS_EMPTY : LEVINS_OK;
+}
+
+extern "C" int levins_build_range_image(levins_ctx* ctx, const levins_point_xyzi* cloud, size_t n,
+                                        levins_point_xyzi* unit_sphere_out, size_t unit_capacity, int32_t* cell_winner_out,
+                                        size_t* m_out) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (m_out) *m_out = 0;
+    int r = ensure_stream_buffers(ctx, 1, 1);
+    if (r) return r;
+    ctx->s_image_valid = false;
+    const PointXYZI* dcloud = nullptr;
+    if (cloud) { // explicit cloud: re-bin from scratch
+        if (n > 0xffffffffull) return fail(ctx, LEVINS_ERR_ARG, "cloud too large");
+        if (ctx->s_image_from_raw) { // discard the pending fused z-buffer
+            r = fill_zbuf(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS);
+            if (r) return r;
+            ctx->s_image_from_raw = false;
+        }
+        CU(ctx->s_in_cloud.ensure(std::max<size_t>(n, 1) * sizeof(PointXYZI)));
+        if (n) CU(cudaMemcpyAsync(ctx->s_in_cloud.p, cloud, n * sizeof(PointXYZI), cudaMemcpyHostToDevice, ctx->stream));
+        dcloud = ctx->s_in_cloud.as<PointXYZI>();
+        if (n) {
+            const unsigned grid = (unsigned) ((n + 255) / 256);
+            if (ctx->consts.libm_mode == 0)
+                k_bin_cloud<0><<<grid, 256, 0, ctx->stream>>>(dcloud, (unsigned) n, ctx->s_zbuf.as<unsigned long long>(), ctx->consts);
+            else
+                k_bin_cloud<1><<<grid, 256, 0, ctx->stream>>>(dcloud, (unsigned) n, ctx->s_zbuf.as<unsigned long long>(), ctx->consts);
+            ctx->launches++;
+            CU(cudaGetLastError());
+        }
+        KfState kf{};
+        memcpy(ctx->pinned, &kf, sizeof(kf));
+        CU(cudaMemcpyAsync(ctx->s_kf.p, ctx->pinned, sizeof(kf), cudaMemcpyHostToDevice, ctx->stream));
+        r = run_finalize_stream(ctx, true, dcloud, true);
+        if (r) return r;
+    } else {
+        if (!ctx->s_cloud_valid || !ctx->s_image_from_raw)
+            return fail(ctx, LEVINS_ERR_STATE, "no resident cloud: call levins_stack_deskew first or pass a cloud");
+        // the z-buffer was filled by the fused deskew+bin kernel; winners index the resident cloud
+        r = run_finalize_stream(ctx, true, ctx->s_cloud.as<PointXYZI>(), true);
+        if (r) return r;
+        ctx->s_image_from_raw = false;
+    }
+    k_compact<<<1, 1024, 0, ctx->stream>>>(ctx->s_cells.as<float4>(), ctx->s_c2c.as<int32_t>(), ctx->s_unit.as<PointXYZI>());
+    ctx->launches++;
+    CU(cudaGetLastError());
+    KfState kf;
+    CU(cudaMemcpyAsync(ctx->pinned, ctx->s_kf.p, sizeof(KfState), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    memcpy(&kf, ctx->pinned, sizeof(kf));
+    const size_t m = kf.m;
+    if (m_out) *m_out = m;
+    if (unit_sphere_out && m) {
+        if (unit_capacity < m) return fail(ctx, LEVINS_ERR_CAPACITY, "unit_sphere_out too small");
+        CU(cudaMemcpyAsync(unit_sphere_out, ctx->s_unit.p, m * sizeof(PointXYZI), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (cell_winner_out)
+        CU(cudaMemcpyAsync(cell_winner_out, ctx->s_winner.p, (size_t) CELLS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->s_image_valid = m > 0;
+    return m ? LEVINS_OK : LEVINS_EMPTY;
+}
+
+extern "C" int levins_associate(levins_ctx* ctx, const float* query_xyz, size_t nf, int8_t* type, float* xyz_depth,
+                                int32_t* knn_idx, float* knn_d2, int32_t* flags) {
+    if (!ctx || (!query_xyz && nf)) return fail(ctx, LEVINS_ERR_ARG, "null queries");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (nf > ctx->cfg.max_features) return fail(ctx, LEVINS_ERR_CAPACITY, "more features than config.max_features");
+    if (!ctx->s_image_valid) return fail(ctx, LEVINS_ERR_STATE, "no range image: call levins_build_range_image first");
+    if (nf == 0) return LEVINS_OK;
+    int r = ensure_stream_buffers(ctx, 1, nf);
+    if (r) return r;
+    CU(cudaMemcpyAsync(ctx->s_queries.p, query_xyz, nf * 12, cudaMemcpyHostToDevice, ctx->stream));
+    // q_count lives in the device KfState
+    unsigned long long qc[2] = {0, nf};
+    memcpy(ctx->pinned, qc, sizeof(qc));
+    CU(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->s_kf.p) + offsetof(KfState, q_begin), ctx->pinned, sizeof(qc),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    r = run_associate_stream(ctx, nf, true);
+    if (r) return r;
+    if (type) CU(cudaMemcpyAsync(type, ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz_depth) CU(cudaMemcpyAsync(xyz_depth, ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (flags) CU(cudaMemcpyAsync(flags, ctx->s_flags.p, nf * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (knn_idx) CU(cudaMemcpyAsync(knn_idx, ctx->s_knn_idx.p, nf * 20, cudaMemcpyDeviceToHost, ctx->stream));
+    if (knn_d2) CU(cudaMemcpyAsync(knn_d2, ctx->s_knn_d2.p, nf * 20, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LEVINS_OK;
+}
+
+extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins,
+                               const float* query_xyz, size_t nf, int8_t* type, float* xyz_depth, size_t* n_projected_out,
+                               size_t* m_out) {
+    if (!ctx || (!query_xyz && nf)) return fail(ctx, LEVINS_ERR_ARG, "null queries");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (nf > ctx->cfg.max_features) return fail(ctx, LEVINS_ERR_CAPACITY, "more features than config.max_features");
+    if (n_projected_out) *n_projected_out = 0;
+    if (m_out) *m_out = 0;
+    ctx->s_cloud_valid = false;
+    ctx->s_image_valid = false;
+    int r = ensure_stream_buffers(ctx, n_ins, nf);
+    if (r) return r;
+    if (ctx->s_image_from_raw) { // a stack_deskew result was never consumed: clear its z-buffer
+        r = fill_zbuf(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS);
+        if (r) return r;
+        ctx->s_image_from_raw = false;
+    }
+    r = run_stage1(ctx, stamp, ins, n_ins, /*write_cloud=*/false, /*bin=*/true);
+    if (r == LEVINS_EMPTY) {
+        for (size_t k = 0; k < nf; k++) {
+            if (type) type[k] = LEVINS_MAPPOINT_NONE;
+            if (xyz_depth) {
+                memcpy(xyz_depth + 4 * k, query_xyz + 3 * k, 12);
+                xyz_depth[4 * k + 3] = 0;
+            }
+        }
+        return LEVINS_EMPTY;
+    }
+    if (r) return r;
+    if (nf) {
+        CU(cudaMemcpyAsync(ctx->s_queries.p, query_xyz, nf * 12, cudaMemcpyHostToDevice, ctx->stream));
+        unsigned long long qc[2] = {0, nf};
+        memcpy(reinterpret_cast<char*>(ctx->pinned) + 512, qc, sizeof(qc));
+        CU(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->s_kf.p) + offsetof(KfState, q_begin),
+                           reinterpret_cast<char*>(ctx->pinned) + 512, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    r = run_finalize_stream(ctx, false, nullptr, false);
+    if (r) return r;
+    if (nf) {
+        r = run_associate_stream(ctx, nf, false);
+        if (r) return r;
+        if (type) CU(cudaMemcpyAsync(type, ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
+        if (xyz_depth) CU(cudaMemcpyAsync(xyz_depth, ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    KfState kf;
+    r = fetch_kf(ctx, &kf);
+    if (r) return r;
+    if (n_projected_out) *n_projected_out = kf.n_proj;
+    if (m_out) *m_out = kf.m;
+    ctx->s_image_valid = kf.m > 0;
+    // no compact-index map was built for this image; levins_associate needs one
+    if (ctx->s_image_valid) {
+        k_compact<<<1, 1024, 0, ctx->stream>>>(ctx->s_cells.as<float4>(), ctx->s_c2c.as<int32_t>(), nullptr);
+        ctx->launches++;
+    }
+    return (kf.status || kf.m == 0) ? LEVINS_EMPTY : LEVINS_OK;
+}
+
+extern "C" int levins_point_cloud_projection(levins_ctx* ctx, const levins_pose* pose, const levins_point_xyzi* src,
+                                             levins_point_xyzi* dst, size_t n) {
+    if (!ctx || !pose || (n && (!src || !dst))) return fail(ctx, LEVINS_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return LEVINS_OK;
+    if (n > 0xffffffffull) return fail(ctx, LEVINS_ERR_ARG, "cloud too large");
+    CU(ctx->s_in_cloud.ensure(2 * n * sizeof(PointXYZI)));
+    PointXYZI* d_src = ctx->s_in_cloud.as<PointXYZI>();
+    PointXYZI* d_dst = d_src + n;
+    CU(cudaMemcpyAsync(d_src, src, n * sizeof(PointXYZI), cudaMemcpyHostToDevice, ctx->stream));
+    Extrinsics e{};
+    memcpy(e.Rcl, pose->R, sizeof(double) * 9);
+    memcpy(e.tcl, pose->t, sizeof(double) * 3);
+    k_project<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(d_src, d_dst, (unsigned) n, e);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(dst, d_dst, n * sizeof(PointXYZI), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LEVINS_OK;
+}
+
+// =================================================================================================
+// batch API
+// =================================================================================================
+extern "C" int levins_batch_set_wave(levins_ctx* ctx, int w) {
+    if (!ctx || w < 0 || w > 4096) return LEVINS_ERR_ARG;
+    ctx->b_wave = w ? w : 16;
+    return LEVINS_OK;
+}
+
+extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* points, size_t n_points,
+                                   const levins_ins_sample* ins, size_t n_ins, const float* query_xyz, size_t n_queries,
+                                   const levins_keyframe_desc* descs, size_t n_kf) {
+    if (!ctx || !points || !ins || !descs || (!query_xyz && n_queries)) return fail(ctx, LEVINS_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    ctx->b_valid = false;
+    if (n_kf == 0) return fail(ctx, LEVINS_ERR_ARG, "no keyframes");
+    std::vector<KfState> kfs(n_kf);
+    size_t table_entries = 0; // the table depends on the keyframe pose, so INS slices shared by keyframes get separate tables
+    for (size_t k = 0; k < n_kf; k++) {
+        const levins_keyframe_desc& d = descs[k];
+        if (d.pt_begin + d.pt_count > n_points || d.ins_begin + d.ins_count > n_ins || d.q_begin + d.q_count > n_queries ||
+            d.ins_count == 0 || d.pt_count > 0xffffffffull)
+            return fail(ctx, LEVINS_ERR_ARG, "keyframe descriptor out of range");
+        KfState s{};
+        s.pt_begin = d.pt_begin;
+        s.pt_count = d.pt_count;
+        s.ins_begin = d.ins_begin;
+        s.ins_count = d.ins_count;
+        s.q_begin = d.q_begin;
+        s.q_count = d.q_count;
+        s.stamp = d.stamp;
+        s.table_begin = table_entries;
+        table_entries += d.ins_count;
+        kfs[k] = s;
+    }
+    CU(ctx->b_pts.ensure(std::max<size_t>(n_points, 1) * sizeof(PointXYZIT)));
+    CU(ctx->b_ins.ensure(n_ins * sizeof(InsSample)));
+    CU(ctx->b_table.ensure(table_entries * sizeof(Interval)));
+    CU(ctx->b_queries.ensure(std::max<size_t>(n_queries, 1) * 12));
+    CU(ctx->b_kfs.ensure(n_kf * sizeof(KfState)));
+    CU(ctx->b_type.ensure(std::max<size_t>(n_queries, 1)));
+    CU(ctx->b_xyzd.ensure(std::max<size_t>(n_queries, 1) * 16));
+    CU(ctx->b_flags.ensure(std::max<size_t>(n_queries, 1) * 4));
+    CU(cudaMemcpyAsync(ctx->b_pts.p, points, n_points * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->b_ins.p, ins, n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
+    if (n_queries) CU(cudaMemcpyAsync(ctx->b_queries.p, query_xyz, n_queries * 12, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->b_kfs.p, kfs.data(), n_kf * sizeof(KfState), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream)); // kfs is a stack vector
+    ctx->b_descs.assign(descs, descs + n_kf);
+    ctx->b_nq = n_queries;
+    ctx->b_npts = n_points;
+    ctx->b_nins = n_ins;
+    ctx->b_valid = true;
+    return LEVINS_OK;
+}
+
+static cudaEvent_t get_event(levins_ctx* ctx, size_t i) {
+    while (ctx->ev_pool.size() <= i) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        ctx->ev_pool.push_back(ev);
+    }
+    return ctx->ev_pool[i];
+}
+
+extern "C" int levins_batch_run(levins_ctx* ctx) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->b_valid) return fail(ctx, LEVINS_ERR_STATE, "levins_batch_upload has not been called");
+    if (!ctx->have_ext) return fail(ctx, LEVINS_ERR_STATE, "levins_set_extrinsics has not been called");
+    const size_t n_kf = ctx->b_descs.size();
+    const int wave = (int) std::min<size_t>(ctx->b_wave, n_kf);
+    if (ctx->b_wave_alloc < wave) {
+        CU(ctx->b_zbuf.ensure((size_t) wave * CELLS * 8));
+        CU(ctx->b_cells.ensure((size_t) wave * CELLS * sizeof(float4)));
+        int r = fill_zbuf(ctx, ctx->b_zbuf.as<unsigned long long>(), (size_t) wave * CELLS);
+        if (r) return r;
+        ctx->b_wave_alloc = wave;
+    }
+    size_t ev = 0;
+    ctx->ev_spans.clear();
+    auto mark = [&](int kind, bool begin) {
+        if (!ctx->profiling) return;
+        cudaEvent_t e = get_event(ctx, ev);
+        cudaEventRecord(e, ctx->stream);
+        if (begin)
+            ctx->ev_spans.push_back({kind, ev, 0});
+        else
+            ctx->ev_spans.back().e1 = ev;
+        ev++;
+    };
+
+    PrepareArgs pa{};
+    pa.kfs = ctx->b_kfs.as<KfState>();
+    pa.pts = ctx->b_pts.as<PointXYZIT>();
+    pa.pts_cap = ~0ull;
+    pa.ins = ctx->b_ins.as<InsSample>();
+    pa.table = ctx->b_table.as<Interval>();
+    pa.ring = nullptr;
+    pa.ext = ctx->ext;
+    pa.c = ctx->consts;
+    mark(0, true);
+    k_prepare<<<(unsigned) n_kf, 128, 0, ctx->stream>>>(pa);
+    mark(0, false);
+    ctx->launches++;
+    CU(cudaGetLastError());
+
+    for (size_t k0 = 0; k0 < n_kf; k0 += wave) {
+        const int nw = (int) std::min<size_t>(wave, n_kf - k0);
+        uint64_t max_pts = 0, max_q = 0;
+        for (int i = 0; i < nw; i++) {
+            max_pts = std::max<uint64_t>(max_pts, ctx->b_descs[k0 + i].pt_count);
+            max_q = std::max<uint64_t>(max_q, ctx->b_descs[k0 + i].q_count);
+        }
+        DeskewArgs da{};
+        da.kfs = ctx->b_kfs.as<KfState>() + k0;
+        da.pts = ctx->b_pts.as<PointXYZIT>();
+        da.pts_cap = ~0ull;
+        da.table = ctx->b_table.as<Interval>();
+        da.zbuf = ctx->b_zbuf.as<unsigned long long>();
+        da.cloud_out = nullptr;
+        da.ext = ctx->ext;
+        da.c = ctx->consts;
+        if (max_pts) {
+            dim3 grid((unsigned) ((max_pts + DESKEW_THREADS - 1) / DESKEW_THREADS), nw);
+            mark(1, true);
+            launch_deskew(ctx, grid, da, false);
+            mark(1, false);
+            CU(cudaGetLastError());
+        }
+        FinalizeArgs fa{};
+        fa.kfs = ctx->b_kfs.as<KfState>() + k0;
+        fa.pts = ctx->b_pts.as<PointXYZIT>();
+        fa.pts_cap = ~0ull;
+        fa.table = ctx->b_table.as<Interval>();
+        fa.cloud = nullptr;
+        fa.zbuf = ctx->b_zbuf.as<unsigned long long>();
+        fa.cells = ctx->b_cells.as<float4>();
+        fa.winner = nullptr;
+        fa.ext = ctx->ext;
+        fa.c = ctx->consts;
+        mark(2, true);
+        k_finalize<false><<<dim3((CELLS + FINALIZE_THREADS - 1) / FINALIZE_THREADS, nw), FINALIZE_THREADS, 0, ctx->stream>>>(fa);
+        mark(2, false);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        if (max_q) {
+            AssocArgs aa{};
+            aa.kfs = ctx->b_kfs.as<KfState>() + k0;
+            aa.queries = ctx->b_queries.as<float>();
+            aa.cells = ctx->b_cells.as<float4>();
+            aa.c2c = nullptr;
+            aa.type = ctx->b_type.as<int8_t>();
+            aa.xyz_depth = ctx->b_xyzd.as<float4>();
+            aa.flags = ctx->b_flags.as<int32_t>();
+            aa.knn_idx = nullptr;
+            aa.knn_d2 = nullptr;
+            aa.c = ctx->consts;
+            mark(3, true);
+            k_associate<<<dim3((unsigned) ((max_q + ASSOC_WARPS - 1) / ASSOC_WARPS), nw), ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
+            mark(3, false);
+            ctx->launches++;
+            CU(cudaGetLastError());
+        }
+    }
+    return LEVINS_OK;
+}
+
+extern "C" int levins_batch_kernel_ms(levins_ctx* ctx, float ms[4], uint32_t launches[4]) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < 4; i++) {
+        ctx->prof_ms[i] = 0;
+        ctx->prof_launches[i] = 0;
+    }
+    for (const auto& s : ctx->ev_spans) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, ctx->ev_pool[s.e0], ctx->ev_pool[s.e1]));
+        ctx->prof_ms[s.kind] += t;
+        ctx->prof_launches[s.kind]++;
+    }
+    if (ms) memcpy(ms, ctx->prof_ms, sizeof(ctx->prof_ms));
+    if (launches) memcpy(launches, ctx->prof_launches, sizeof(ctx->prof_launches));
+    return LEVINS_OK;
+}
+
+extern "C" int levins_batch_download(levins_ctx* ctx, int8_t* type, float* xyz_depth, int32_t* flags, uint32_t* n_projected,
+                                     uint32_t* m) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->b_valid) return fail(ctx, LEVINS_ERR_STATE, "no batch");
+    const size_t nq = ctx->b_nq, n_kf = ctx->b_descs.size();
+    if (type && nq) CU(cudaMemcpyAsync(type, ctx->b_type.p, nq, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz_depth && nq) CU(cudaMemcpyAsync(xyz_depth, ctx->b_xyzd.p, nq * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (flags && nq) CU(cudaMemcpyAsync(flags, ctx->b_flags.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<KfState> kfs;
+    if (n_projected || m) {
+        kfs.resize(n_kf);
+        CU(cudaMemcpyAsync(kfs.data(), ctx->b_kfs.p, n_kf * sizeof(KfState), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < kfs.size(); k++) {
+        if (n_projected) n_projected[k] = kfs[k].n_proj;
+        if (m) m[k] = kfs[k].m;
+    }
+    return LEVINS_OK;
+}

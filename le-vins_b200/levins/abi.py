@@ -1,0 +1,263 @@
+"""ctypes binding of liblevins_b200.so (include/levins/abi.h) -- the harness-side view of the C ABI.
+
+This is plumbing for tests and bench.py, not the product: the product is the shared library and its C++ host
+headers (le-vins_b200/host).  There is no fallback: if the library is missing or no sm_100 GPU is present,
+construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .synth import INS, XYZI, XYZIT
+
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(PKG_DIR, "liblevins_b200.so")
+
+OK, EMPTY = 0, 1
+ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = -1, -2, -3, -4
+CELLS = 300 * 300
+
+EXPORTS = [
+    "levins_abi_version", "levins_config_default", "levins_create", "levins_destroy", "levins_last_error",
+    "levins_status_string", "levins_set_stream", "levins_synchronize", "levins_set_extrinsics", "levins_append_scan",
+    "levins_buffer_info", "levins_buffer_clear", "levins_stack_deskew", "levins_build_range_image", "levins_associate",
+    "levins_keyframe", "levins_point_cloud_projection", "levins_batch_upload", "levins_batch_run",
+    "levins_batch_download", "levins_batch_set_wave", "levins_set_profiling", "levins_batch_kernel_ms",
+    "levins_launch_count",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("libm_mode", C.c_int32), ("stack_interval", C.c_double),
+        ("reserved_buffer_length", C.c_double), ("nearest_depth", C.c_double), ("farthest_depth", C.c_double),
+        ("plane_residual_threshold", C.c_double), ("range_spread_threshold", C.c_double),
+        ("nearest_distance_counts", C.c_int32), ("reserved0", C.c_int32), ("max_points", C.c_uint64),
+        ("max_ins", C.c_uint64), ("max_features", C.c_uint64),
+    ]
+
+
+KF_DESC = np.dtype([("pt_begin", "<u8"), ("pt_count", "<u8"), ("ins_begin", "<u8"), ("ins_count", "<u8"),
+                    ("q_begin", "<u8"), ("q_count", "<u8"), ("stamp", "<f8")])
+assert KF_DESC.itemsize == 56
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, sz, dbl, i32 = C.c_void_p, C.c_size_t, C.c_double, C.c_int
+        L.levins_abi_version.restype = i32
+        L.levins_config_default.argtypes = [C.POINTER(Config)]
+        L.levins_create.restype = i32
+        L.levins_create.argtypes = [i32, C.POINTER(Config), C.POINTER(vp)]
+        L.levins_destroy.argtypes = [vp]
+        L.levins_last_error.restype = C.c_char_p
+        L.levins_last_error.argtypes = [vp]
+        L.levins_status_string.restype = C.c_char_p
+        L.levins_status_string.argtypes = [i32]
+        for name, args in {
+            "levins_set_stream": [vp, vp],
+            "levins_synchronize": [vp],
+            "levins_set_extrinsics": [vp, vp, vp, dbl],
+            "levins_append_scan": [vp, vp, sz],
+            "levins_buffer_info": [vp, vp, vp, vp],
+            "levins_buffer_clear": [vp],
+            "levins_stack_deskew": [vp, dbl, vp, sz, vp, sz, vp],
+            "levins_build_range_image": [vp, vp, sz, vp, sz, vp, vp],
+            "levins_associate": [vp, vp, sz, vp, vp, vp, vp, vp],
+            "levins_keyframe": [vp, dbl, vp, sz, vp, sz, vp, vp, vp, vp],
+            "levins_point_cloud_projection": [vp, vp, vp, vp, sz],
+            "levins_batch_upload": [vp, vp, sz, vp, sz, vp, sz, vp, sz],
+            "levins_batch_run": [vp],
+            "levins_batch_download": [vp, vp, vp, vp, vp, vp],
+            "levins_batch_set_wave": [vp, i32],
+            "levins_set_profiling": [vp, i32],
+            "levins_batch_kernel_ms": [vp, vp, vp],
+        }.items():
+            fn = getattr(L, name)
+            fn.restype = i32
+            fn.argtypes = args
+        L.levins_launch_count.restype = C.c_uint64
+        L.levins_launch_count.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_config() -> Config:
+    cfg = Config()
+    lib().levins_config_default(C.byref(cfg))
+    return cfg
+
+
+class LevinsError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"levins status {status} ({lib().levins_status_string(status).decode()}): {msg}")
+        self.status = status
+
+
+class Context:
+    """One levins_ctx on one GPU."""
+
+    def __init__(self, device: int = 0, cfg: Config | None = None, **overrides):
+        L = lib()
+        cfg = cfg or default_config()
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        h = C.c_void_p()
+        st = L.levins_create(int(device), C.byref(cfg), C.byref(h))
+        if st != OK:
+            raise LevinsError(st, "levins_create failed (no sm_100 GPU? the library has no CPU fallback)")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().levins_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st, allow_empty=True):
+        if st < 0 or (st == EMPTY and not allow_empty):
+            raise LevinsError(st, lib().levins_last_error(self._h).decode())
+        return st
+
+    # ---- configuration ----
+    def set_stream(self, cuda_stream: int):
+        self._check(lib().levins_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(lib().levins_synchronize(self._h))
+
+    def set_extrinsics(self, pose_b_c, pose_c_l, td_b_l):
+        pb = np.ascontiguousarray(pose_b_c, np.float64)
+        pc = np.ascontiguousarray(pose_c_l, np.float64)
+        assert pb.size == 12 and pc.size == 12
+        self._check(lib().levins_set_extrinsics(self._h, _p(pb), _p(pc), float(td_b_l)))
+
+    def set_profiling(self, on: bool):
+        self._check(lib().levins_set_profiling(self._h, int(on)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().levins_launch_count(self._h))
+
+    # ---- streaming ----
+    def append_scan(self, points):
+        pts = np.ascontiguousarray(points, XYZIT)
+        self._check(lib().levins_append_scan(self._h, _p(pts), len(pts)))
+
+    def buffer_info(self):
+        n, a, b = C.c_size_t(0), C.c_double(0), C.c_double(0)
+        self._check(lib().levins_buffer_info(self._h, C.byref(n), C.byref(a), C.byref(b)))
+        return n.value, a.value, b.value
+
+    def buffer_clear(self):
+        self._check(lib().levins_buffer_clear(self._h))
+
+    def stack_deskew(self, stamp, ins, want_cloud=True, capacity=None):
+        ins = np.ascontiguousarray(ins, INS)
+        n = C.c_size_t(0)
+        cap = int(capacity if capacity is not None else self.buffer_info()[0])
+        out = np.zeros(max(cap, 1), XYZI) if want_cloud else None
+        st = self._check(lib().levins_stack_deskew(self._h, float(stamp), _p(ins), len(ins), _p(out), cap, C.byref(n)))
+        return st, n.value, (out[: n.value] if want_cloud else None)
+
+    def build_range_image(self, cloud=None, want_unit=True, want_winner=True):
+        cl = None if cloud is None else np.ascontiguousarray(cloud, XYZI)
+        unit = np.zeros(CELLS, XYZI) if want_unit else None
+        win = np.full(CELLS, -2, np.int32) if want_winner else None
+        m = C.c_size_t(0)
+        st = self._check(lib().levins_build_range_image(self._h, _p(cl), 0 if cl is None else len(cl), _p(unit), CELLS,
+                                                        _p(win), C.byref(m)))
+        return st, m.value, (unit[: m.value] if want_unit else None), win
+
+    def associate(self, queries):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+        f = len(q)
+        ty = np.zeros(f, np.int8)
+        xd = np.zeros((f, 4), np.float32)
+        ki = np.full((f, 5), -7, np.int32)
+        kd = np.zeros((f, 5), np.float32)
+        fl = np.zeros(f, np.int32)
+        self._check(lib().levins_associate(self._h, _p(q), f, _p(ty), _p(xd), _p(ki), _p(kd), _p(fl)))
+        return {"type": ty, "xyz_depth": xd, "knn_idx": ki, "knn_d2": kd, "flags": fl}
+
+    def keyframe(self, stamp, ins, queries):
+        ins = np.ascontiguousarray(ins, INS)
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+        f = len(q)
+        ty = np.zeros(f, np.int8)
+        xd = np.zeros((f, 4), np.float32)
+        npj, m = C.c_size_t(0), C.c_size_t(0)
+        st = self._check(lib().levins_keyframe(self._h, float(stamp), _p(ins), len(ins), _p(q), f, _p(ty), _p(xd),
+                                               C.byref(npj), C.byref(m)))
+        return {"status": st, "type": ty, "xyz_depth": xd, "n_projected": npj.value, "m": m.value}
+
+    def point_cloud_projection(self, pose, cloud):
+        pose = np.ascontiguousarray(pose, np.float64)
+        src = np.ascontiguousarray(cloud, XYZI)
+        dst = np.zeros(len(src), XYZI)
+        self._check(lib().levins_point_cloud_projection(self._h, _p(pose), _p(src), _p(dst), len(src)))
+        return dst
+
+    # ---- batch ----
+    def batch_upload(self, points, ins, queries, descs):
+        self._b_points = np.ascontiguousarray(points, XYZIT)
+        self._b_ins = np.ascontiguousarray(ins, INS)
+        self._b_q = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+        self._b_descs = np.ascontiguousarray(descs, KF_DESC)
+        self._check(lib().levins_batch_upload(self._h, _p(self._b_points), len(self._b_points), _p(self._b_ins),
+                                              len(self._b_ins), _p(self._b_q), len(self._b_q), _p(self._b_descs),
+                                              len(self._b_descs)))
+
+    def batch_run(self):
+        self._check(lib().levins_batch_run(self._h))
+
+    def batch_set_wave(self, w: int):
+        self._check(lib().levins_batch_set_wave(self._h, int(w)))
+
+    def batch_download(self, out=None):
+        nq, nk = len(self._b_q), len(self._b_descs)
+        if out is None:
+            out = {"type": np.zeros(nq, np.int8), "xyz_depth": np.zeros((nq, 4), np.float32),
+                   "flags": np.zeros(nq, np.int32), "n_projected": np.zeros(nk, np.uint32), "m": np.zeros(nk, np.uint32)}
+        self._check(lib().levins_batch_download(self._h, _p(out.get("type")), _p(out.get("xyz_depth")), _p(out.get("flags")),
+                                                _p(out.get("n_projected")), _p(out.get("m"))))
+        return out
+
+    def batch_kernel_ms(self):
+        ms = np.zeros(4, np.float32)
+        n = np.zeros(4, np.uint32)
+        self._check(lib().levins_batch_kernel_ms(self._h, _p(ms), _p(n)))
+        return ms, n
+
+
+def batch_descs(b) -> np.ndarray:
+    """levins_keyframe_desc array for a synth.Batch (queries laid out keyframe-major)."""
+    k = b.n_keyframes
+    f = b.queries.shape[1]
+    d = np.zeros(k, KF_DESC)
+    d["pt_begin"], d["pt_count"] = b.pt_begin, b.pt_count
+    d["ins_begin"], d["ins_count"] = b.ins_begin, b.ins_count
+    d["q_begin"] = np.arange(k) * f
+    d["q_count"] = f
+    d["stamp"] = b.stamps
+    return d
