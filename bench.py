@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- LiDAR depth-enhancement hot path on B200: features depth-associated / s, LiDAR pts / s, p50 keyframe ms.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" is one pass of the whole hot path (window search + INS table, per-point deskew fused with range-image
+binning, cell finalisation, per-feature 5-NN + plane fit) over one batch of independent synthetic keyframes of
+BASELINE.json configs[1] (R3LIVE handheld shape: Livox-Avia-like 24 000 pts/scan at 10 Hz, 0.5 s stack window,
+1280x1024 camera, 300 features per keyframe).  Every rank processes its own batch (weak scaling); keyframes are
+independent, so the only exchange step is the final NCCL all-gather of the per-feature results.
+
+Printed JSON (one line, rank 0):
+  value      whole-job features/s with the batch already resident in HBM (CUDA events on the launching stream)
+  e2e        the same metric through the C ABI with HOST buffers: host->device copies of points / INS / queries and
+             the device->host read of the results are inside the timed region
+  roofline   dominant kernel (k_deskew_bin): algorithmic bytes (32 B per projected point) / its mean launch time
+             measured live with CUDA events, against MEASURED_PEAKS.json's hbm_gbs
+  cpu_baseline  the CPU oracle (a port of the reference's algorithm with its parallel structure) on a bounded sample
+`--impl reference` times that CPU port alone on the box's host cores (the reference itself cannot be built here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "le-vins_b200"), os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "features_depth_associated_per_s"
+UNIT = "features/s"
+CFG = 2  # BASELINE.json configs[1]
+DEFAULT_KEYFRAMES = 256
+UNIQUE_SCANS = 48
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def workload_name(n_kf):
+    return f"cfg2_r3live_avia_24kpts_x5scans_1280x1024_F300_batch{n_kf}_independent_keyframes"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+        0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+        0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU legs (oracle port)
+# ------------------------------------------------------------------------------------------------------------
+def cpu_keyframes(batch, ks, nthreads):
+    import oracle_py as orc
+    from levins import synth
+
+    t0 = time.perf_counter()
+    nf = 0
+    npts = 0
+    for k in ks:
+        kf = synth.batch_keyframe(batch, k)
+        r = orc.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries,
+                         kf.shape.stack_interval, nthreads=nthreads)
+        nf += len(kf.queries)
+        npts += r["n_projected"]
+    return time.perf_counter() - t0, nf, npts
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: stage 1 parallel over all host threads, stages
+    2-3 serial with a KD-tree, as in le_vins.cc:464 / tracking.cc:307-362,399-413) on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_py as orc
+    from levins import synth
+
+    orc.build()
+    n_sample = 8
+    batch = synth.make_batch(CFG, n_sample, n_unique_scans=UNIQUE_SCANS)
+    cores = orc.max_threads()
+    for _ in range(args.warmup):
+        cpu_keyframes(batch, range(n_sample), cores)
+    t_total, nf_total, np_total = 0.0, 0, 0
+    for _ in range(args.steps):
+        t, nf, npts = cpu_keyframes(batch, range(n_sample), cores)
+        t_total += t
+        nf_total += nf
+        np_total += npts
+    value = nf_total / t_total
+    sample = f"{n_sample} keyframes of the workload per step ({n_sample * 300} features, {np_total // args.steps} points)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(DEFAULT_KEYFRAMES), "sample_keyframes_per_step": n_sample},
+        "lidar_pts_per_s": np_total / t_total, "keyframes_per_s": n_sample * args.steps / t_total,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle port of the reference's CPU path; the reference itself needs Eigen/PCL/FLANN/TBB/OpenCV (absent)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def pinned_copy(torch, arr):
+    """numpy array -> pinned host memory (numpy view over a pinned torch tensor)."""
+    raw = arr.view(np.uint8).reshape(-1)
+    t = torch.empty(raw.shape[0], dtype=torch.uint8, pin_memory=True)
+    v = t.numpy()
+    v[:] = raw
+    return t, v.view(arr.dtype).reshape(arr.shape)
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from levins import abi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    n_kf = args.keyframes
+    batch = synth.make_batch(CFG, n_kf, seed=synth.BASE_SEED + 5 + 1000 * rank, n_unique_scans=UNIQUE_SCANS)
+    descs = abi.batch_descs(batch)
+    F = batch.queries.shape[1]
+    q_flat = np.ascontiguousarray(batch.queries.reshape(-1, 3))
+    keep = []
+    t_pts, pts = pinned_copy(torch, batch.points)
+    t_ins, ins = pinned_copy(torch, batch.ins)
+    t_q, q = pinned_copy(torch, q_flat)
+    keep += [t_pts, t_ins, t_q]
+
+    ctx = abi.Context(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_extrinsics(batch.shape.rig.pose_b_c, batch.shape.rig.pose_c_l, batch.shape.rig.td_b_l)
+    ctx.batch_set_wave(args.wave)
+    ctx.batch_upload(pts, ins, q, descs)
+
+    # results gathered across ranks at the end of every step (the path's only exchange step)
+    nq = n_kf * F
+    res_host = {"type": np.zeros(nq, np.int8), "xyz_depth": np.zeros((nq, 4), np.float32)}
+    gather_buf = None
+    if world > 1:
+        dptr = ctx.batch_result_pointers()
+        local_xyzd = abi.device_tensor(torch, dptr["xyz_depth"], (nq, 4), torch.float32, local_rank)
+        local_type = abi.device_tensor(torch, dptr["type"], (nq,), torch.int8, local_rank)
+        gather_xyzd = torch.empty((world * nq, 4), dtype=torch.float32, device=dev)
+        gather_type = torch.empty((world * nq,), dtype=torch.int8, device=dev)
+        gather_buf = (local_xyzd, local_type, gather_xyzd, gather_type)
+
+    def gather():
+        if gather_buf is not None:
+            dist.all_gather_into_tensor(gather_buf[2], gather_buf[0])
+            dist.all_gather_into_tensor(gather_buf[3], gather_buf[1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.batch_run()
+        gather()
+
+    def step_e2e():
+        ctx.batch_upload(pts, ins, q, descs)
+        ctx.batch_run()
+        gather()
+        ctx.batch_download(res_host)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), ctx.launch_count - l0
+
+    # ---- device-resident throughput ----
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    with ClockSampler(local_rank) as clocks:
+        ms_total, launches = timed(step_resident, args.steps)
+        # keep the sampler alive over the e2e region too so that short runs still collect samples
+        e2e_steps = max(3, min(args.steps, args.e2e_steps))
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, _ = timed(step_e2e, e2e_steps)
+    ms_per_step = ms_total / args.steps
+    total_features = world * nq
+    value = total_features * args.steps / (ms_total * 1e-3)
+    out = ctx.batch_download()
+    n_proj_total = int(out["n_projected"].astype(np.int64).sum())
+    pts_per_step = n_proj_total  # per rank
+    e2e_value = total_features * e2e_steps / (ms_e2e * 1e-3)
+    h2d = int(pts.nbytes + ins.nbytes + q.nbytes + descs.nbytes)
+    d2h = int(res_host["type"].nbytes + res_host["xyz_depth"].nbytes)
+
+    # ---- per-kernel time, live, with CUDA events on the launching stream ----
+    ctx.set_profiling(True)
+    prof_ms = np.zeros(4)
+    prof_n = np.zeros(4)
+    for _ in range(3):
+        ctx.batch_run()
+        m, n = ctx.batch_kernel_ms()
+        prof_ms += m
+        prof_n += n
+    ctx.set_profiling(False)
+    peak, peak_src = load_peaks()
+    deskew_launch_ms = prof_ms[1] / max(prof_n[1], 1)
+    launches_per_step = prof_n[1] / 3
+    alg_bytes_per_launch = 32.0 * n_proj_total / max(launches_per_step, 1)
+    achieved = alg_bytes_per_launch / (deskew_launch_ms * 1e-3) / 1e9
+    share = prof_ms / max(prof_ms.sum(), 1e-9)
+
+    # ---- streaming latency: append scans + fused keyframe through the ABI, wall clock per keyframe ----
+    p50 = None
+    if rank == 0 and not args.no_stream:
+        p50 = stream_latency(abi, synth, local_rank)
+
+    # ---- CPU baseline on a bounded sample (rank 0 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_py as orc
+
+        orc.build()
+        cores = orc.max_threads()
+        ks = list(range(min(args.cpu_keyframes, n_kf)))
+        cpu_keyframes(batch, ks[:2], cores)
+        t, nf, npts = cpu_keyframes(batch, ks, cores)
+        cpu = {"value": nf / t, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{len(ks)} keyframes of the workload ({nf} features, {npts} points) in {t:.1f} s; stage 1 on "
+                         f"{cores} threads, stages 2-3 serial + KD-tree like the reference",
+               "lidar_pts_per_s": npts / t}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(n_kf), "keyframes_per_gpu": n_kf, "points_per_keyframe": int(n_proj_total / n_kf),
+                       "features_per_keyframe": F, "wave": args.wave,
+                       "l2": f"inputs larger than L2: {pts.nbytes / 1e6:.0f} MB of points per GPU per step"},
+            "lidar_pts_per_s": world * pts_per_step * args.steps / (ms_total * 1e-3),
+            "keyframes_per_s": world * n_kf * args.steps / (ms_total * 1e-3),
+            "p50_keyframe_ms": p50,
+            "clocks": clocks.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_deskew_bin", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": load_traffic(),
+                         "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launch_ms": deskew_launch_ms,
+                         "peak_source": peak_src,
+                         "kernel_time_share": {"k_prepare": share[0], "k_deskew_bin": share[1], "k_finalize": share[2],
+                                               "k_associate": share[3]},
+                         "whole_step_frac": (32.0 * n_proj_total / (ms_per_step * 1e-3) / 1e9) / peak},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            with open(path) as f:
+                return json.load(f).get("k_deskew_bin_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def stream_latency(abi, synth, device, n_keyframes=40):
+    """Config-2 streaming: one scan appended per 0.1 s of sensor time, one keyframe every 0.4 s.  Wall time from the
+    first append of a keyframe's new scans to its results on the host; p50 over the keyframes."""
+    shp = synth.shape(CFG)
+    b = synth.make_batch(CFG, n_keyframes, n_unique_scans=12, seed=synth.BASE_SEED + 77)
+    per = shp.pts_per_scan
+    ctx = abi.Context(device)
+    ctx.set_extrinsics(shp.rig.pose_b_c, shp.rig.pose_c_l, shp.rig.td_b_l)
+    n_scans = len(b.points) // per
+    times = []
+    scan = 0
+    stamps = b.stamps[::1]
+    # keyframes every 0.4 s of sensor time = every 4th scan boundary; b.stamps are 0.5 s apart, use them directly
+    for k, stamp in enumerate(stamps):
+        kf_ins = b.ins[b.ins_begin[k]: b.ins_begin[k] + b.ins_count[k]]
+        t0 = time.perf_counter()
+        while scan < n_scans and b.points["time"][scan * per] <= stamp + 1e-9:  # everything that started before the stamp
+            ctx.append_scan(b.points[scan * per:(scan + 1) * per])
+            scan += 1
+        ctx.keyframe(float(stamp), kf_ins, b.queries[k])
+        times.append(1e3 * (time.perf_counter() - t0))
+    ctx.close()
+    return float(np.median(times[3:])) if len(times) > 3 else None
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--keyframes", type=int, default=DEFAULT_KEYFRAMES, help="keyframes per GPU per step")
+    ap.add_argument("--wave", type=int, default=16)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-keyframes", type=int, default=96)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-stream", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

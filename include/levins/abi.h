@@ -193,6 +193,10 @@ int levins_batch_run(levins_ctx *ctx);
  * laid out by descriptor q_begin (i.e. parallel to the query pool); n_projected[K], m[K] per keyframe. */
 int levins_batch_download(levins_ctx *ctx, int8_t *type, float *xyz_depth, int32_t *flags, uint32_t *n_projected,
                           uint32_t *m);
+/* Device addresses of the result arrays of the resident batch (type: int8[n_queries], xyz_depth: float[4*n_queries],
+ * flags: int32[n_queries]), valid until the next levins_batch_upload.  For exchange steps that stay on the device
+ * (e.g. an NCCL all-gather of the depths issued on the same stream). */
+int levins_batch_result_pointers(levins_ctx *ctx, void **type, void **xyz_depth, void **flags);
 /* Waves: how many keyframes share one set of launches (their z-buffers stay L2-resident). 0 = default. */
 int levins_batch_set_wave(levins_ctx *ctx, int keyframes_per_wave);
 /* Per-kernel device time of the last levins_batch_run, measured with CUDA events on the launching stream when

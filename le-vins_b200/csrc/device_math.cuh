@@ -67,6 +67,11 @@ struct Consts {
     double stack_interval;
     int libm_mode;
     int pad;
+    // exact f32 restatements of the range gate on the squared norm (sqrtf is monotone and correctly rounded):
+    //   (double) sqrtf(n2) > farthest  <=>  n2 > n2_far        (double) sqrtf(n2) < nearest  <=>  n2 < n2_near
+    float n2_far, n2_near;
+    float inv_angle_f; // (float) (1 / ANGLE)
+    float cell_guard;  // fast-path cell ids closer than this (in cells) to a rounding boundary are recomputed exactly
 };
 
 // per-keyframe state, device resident
@@ -388,51 +393,169 @@ __device__ __forceinline__ int cell_of_point(float x, float y, float z, const Co
 }
 
 // ------------------------------------------------------------------------------------------------
+// z-buffer key: [gen:8][range bits:31][point index:25].  atomicMin keeps, per cell, the nearest point and on
+// equal range the first index (tracking.cc:332: strictly smaller range replaces).  `gen` counts DOWN from 254 once
+// per use of a z-buffer, so keys left by earlier keyframes (larger gen) lose against any new key and read as
+// "empty": the buffer never has to be cleared between keyframes (only every 254 uses).
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned KEY_IDX_BITS = 25;
+constexpr unsigned KEY_IDX_MASK = (1u << KEY_IDX_BITS) - 1;
+constexpr unsigned long long MAX_POINTS_PER_KEYFRAME = 1ull << KEY_IDX_BITS;
+__device__ __forceinline__ unsigned long long key_make(unsigned gen, float range, unsigned idx) {
+    return ((unsigned long long) gen << 56) | ((unsigned long long) __float_as_uint(range) << KEY_IDX_BITS) | idx;
+}
+__device__ __forceinline__ bool key_live(unsigned long long key, unsigned gen) { return (unsigned) (key >> 56) == gen; }
+__device__ __forceinline__ unsigned key_index(unsigned long long key) { return (unsigned) key & KEY_IDX_MASK; }
+
+// ------------------------------------------------------------------------------------------------
+// stage 2 fast path.  The cell id only needs the angles to ~1e-4 cell except next to a rounding boundary, so the
+// common case uses a 9-term odd minimax polynomial for atan on [-1, 1] (|error| < 6e-9 + f32 rounding) on
+// t = x/z resp. t = y/sqrt(x^2+z^2) (inside the FOV gate both lie in [-1, 1]), and every id that falls within
+// `cell_guard` of a boundary is recomputed with the exact, mirrored cell_of_point<>().  Result: bit-identical cell ids.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float atan_poly(float t) {
+    const float u = t * t;
+    float p = 0.0024566929787397385f;
+    p = fmaf(p, u, -0.014401225373148918f);
+    p = fmaf(p, u, 0.03978099301457405f);
+    p = fmaf(p, u, -0.07234836369752884f);
+    p = fmaf(p, u, 0.10498934984207153f);
+    p = fmaf(p, u, -0.14161226153373718f);
+    p = fmaf(p, u, 0.19985906779766083f);
+    p = fmaf(p, u, -0.33332598209381104f);
+    p = fmaf(p, u, 0.9999998807907104f);
+    return t * p;
+}
+
+// FOV gate of tracking.cc:311-314 without the two IEEE divisions:
+//   fl32(|x| / |z|) > TAN (TAN = 1 - 2^-53)  <=>  fl32(|x| / |z|) >= 1  <=>  |x| / |z| >= 1 - 2^-25  (round to nearest even)
+//   <=>  |x| - |z| >= -|z| 2^-25, where the left side is exact in f32 by Sterbenz's lemma whenever it matters.
+// z == 0 rejects too (x/0 = inf; 0/0 = NaN passes the reference's gate but such a point then fails the col >= 0 test).
+__device__ __forceinline__ bool outside_fov(float x, float y, float z) {
+    const float az = fabsf(z);
+    const float lim = -az * 2.98023223876953125e-8f; // 2^-25
+    return (z < 0.f) || (fabsf(x) - az >= lim) || (fabsf(y) - az >= lim);
+}
+
+// returns the cell id or -1; sets `ambiguous` when the exact path must decide
+__device__ __forceinline__ int cell_of_point_fast(float x, float y, float z, const Consts& c, bool& ambiguous) {
+    ambiguous = false;
+    if (z < 0.f) return -1;
+    if (!(z > 1e-30f)) { // zero / denormal-range z: |z| 2^-25 may be inexact, leave it to the exact path
+        ambiguous = true;
+        return -1;
+    }
+    if (outside_fov(x, y, z)) return -1;
+    // col_angle / ANGLE = (atan2(z, x) - pi/4) / ANGLE = 150 - atan(x / z) / ANGLE
+    float rz = __frcp_rn(z);
+    const float tc = x * rz;
+    const float qc = fmaf(-atan_poly(tc), c.inv_angle_f, 150.0f);
+    // row_angle / ANGLE = (atan2(y, sqrt(x^2 + z^2)) + pi/4) / ANGLE = 150 + atan(y / sqrt(x^2 + z^2)) / ANGLE
+    const float s = fmaf(x, x, z * z);
+    const float tr = y * rsqrtf(s);
+    const float qr = fmaf(atan_poly(tr), c.inv_angle_f, 150.0f);
+    const float rc = rintf(qc), rr = rintf(qr);
+    const float edge = 0.5f - c.cell_guard;
+    if (fabsf(qc - rc) > edge || fabsf(qr - rr) > edge) {
+        ambiguous = true;
+        return -1;
+    }
+    const int col = (int) rc, row = (int) rr;
+    if ((row < 0) || (col < 0) || (row >= IMG) || (col >= IMG)) return -1;
+    return col + row * IMG;
+}
+
+// ------------------------------------------------------------------------------------------------
 // stage 1: interval lookup (misc.cc:25-60 semantics) and per-point deskew
 // ------------------------------------------------------------------------------------------------
 // Returns the table entry index: i in [1, n-1] with time[i-1] <= t < time[i], or 0 (fallback) outside the window.
-__device__ __forceinline__ int find_interval(const Interval* __restrict__ tab, int n_ins, double t, double t0,
-                                             double t_last, double inv_mean_dt) {
-    if (n_ins < 2 || t0 > t || t_last <= t) return 0; // misc.cc:28-30 (n == 1: one of the two conditions always holds)
-    int lo = 1, hi = n_ins - 1;
-    int g = 1 + (int) ((t - t0) * inv_mean_dt);
-    g = min(max(g, lo), hi);
+struct KfView {
+    const Interval* tab;
+    int n_ins;
+    double t0, t_last, inv_mean_dt;
+};
+
+__device__ __noinline__ int find_interval_slow(const Interval* __restrict__ tab, int n_ins, double t, int g, int lo, int hi) {
 #pragma unroll 1
-    for (int it = 0; it < 40; it++) {
-        const double a = __ldg(&tab[g].t_lo), b = __ldg(&tab[g].t_hi);
-        if (t < a) {
+    for (int it = 0; it < 48; it++) {
+        const double2 ab = __ldg(reinterpret_cast<const double2*>(tab + g));
+        if (t < ab.x) {
             hi = g - 1;
             g = (it < 2) ? g - 1 : (lo + hi) >> 1;
-        } else if (t >= b) {
+        } else if (t >= ab.y) {
             lo = g + 1;
             g = (it < 2) ? g + 1 : (lo + hi) >> 1;
         } else {
             return g;
         }
-        if (lo > hi) return 0; // non-monotonic times: no bracketing interval (the reference would give up after 16 rounds)
+        if (lo > hi) return 0; // non-monotonic times: no bracketing interval (the reference gives up after 16 rounds)
         g = min(max(g, lo), hi);
     }
     return 0;
 }
 
-// sin(phi) and 1 - cos(phi); Taylor to full double precision for the small angles of one INS interval
+// The interval entry held in registers; consecutive points almost always share it (points are time-sorted and an
+// INS interval spans ~1 000-6 000 of them), which is checked per point, not assumed.
+struct EntryRegs {
+    double t_lo, t_hi, ts0, inv_dts;
+    double A0, A1, A2, A3, A4, A5, A6, A7, A8;
+    double kx, ky, kz, theta;
+    double c0x, c0y, c0z, c1x, c1y, c1z;
+};
+
+__device__ __forceinline__ void load_entry(const Interval* __restrict__ it, EntryRegs& e) {
+    const double2* __restrict__ p = reinterpret_cast<const double2*>(it);
+    const double2 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2), v3 = __ldg(p + 3), v4 = __ldg(p + 4), v5 = __ldg(p + 5),
+                  v6 = __ldg(p + 6), v7 = __ldg(p + 7), v8 = __ldg(p + 8), v9 = __ldg(p + 9), v10 = __ldg(p + 10),
+                  v11 = __ldg(p + 11);
+    e.t_lo = v0.x; e.t_hi = v0.y; e.ts0 = v1.x; e.inv_dts = v1.y;
+    e.A0 = v2.x; e.A1 = v2.y; e.A2 = v3.x; e.A3 = v3.y; e.A4 = v4.x; e.A5 = v4.y; e.A6 = v5.x; e.A7 = v5.y; e.A8 = v6.x;
+    e.kx = v6.y; e.ky = v7.x; e.kz = v7.y; e.theta = v8.x;
+    e.c0x = v8.y; e.c0y = v9.x; e.c0z = v9.y; e.c1x = v10.x; e.c1y = v10.y; e.c1z = v11.x;
+}
+
+// Make `e` the entry for time t (misc.cc:25-60 semantics).  Fast when e already brackets t.
+__device__ __forceinline__ void seek_entry(const KfView& kv, double t, EntryRegs& e, int& cur) {
+    if (cur > 0 && e.t_lo <= t && t < e.t_hi) return;
+    int idx = 0;
+    if (!(kv.n_ins < 2 || kv.t0 > t || kv.t_last <= t)) { // misc.cc:28-30
+        const int lo = 1, hi = kv.n_ins - 1;
+        int g = 1 + (int) ((t - kv.t0) * kv.inv_mean_dt);
+        g = min(max(g, lo), hi);
+        const double2 ab = __ldg(reinterpret_cast<const double2*>(kv.tab + g));
+        idx = (ab.x <= t && t < ab.y) ? g : find_interval_slow(kv.tab, kv.n_ins, t, g, lo, hi);
+    }
+    if (idx != cur || cur < 0) {
+        load_entry(kv.tab + idx, e);
+        cur = idx;
+    }
+}
+
+// sin(phi) and 1 - cos(phi) to full double precision for the small angles of one INS interval
 __device__ __forceinline__ void sin_omc(double phi, double& sn, double& omc) {
     const double p2 = phi * phi;
-    if (p2 < 0.0625) { // |phi| < 0.25 rad: truncation error < 3e-18 relative
-        double a = fma(p2, -1.0 / 156.0, 1.0);
-        a = fma(p2 * (-1.0 / 110.0), a, 1.0);
-        a = fma(p2 * (-1.0 / 72.0), a, 1.0);
-        a = fma(p2 * (-1.0 / 42.0), a, 1.0);
-        a = fma(p2 * (-1.0 / 20.0), a, 1.0);
-        a = fma(p2 * (-1.0 / 6.0), a, 1.0);
-        sn = phi * a;
-        double b = fma(p2, -1.0 / 182.0, 1.0);
-        b = fma(p2 * (-1.0 / 132.0), b, 1.0);
-        b = fma(p2 * (-1.0 / 90.0), b, 1.0);
-        b = fma(p2 * (-1.0 / 56.0), b, 1.0);
-        b = fma(p2 * (-1.0 / 30.0), b, 1.0);
-        b = fma(p2 * (-1.0 / 12.0), b, 1.0);
-        omc = 0.5 * p2 * b;
+    if (p2 < 2.44140625e-4) { // |phi| < 2^-6: truncation error < 1e-21 relative
+        double a = fma(p2, -1.0 / 5040.0, 1.0 / 120.0);
+        a = fma(p2, a, -1.0 / 6.0);
+        sn = fma(phi * p2, a, phi);
+        double b = fma(p2, -1.0 / 40320.0, 1.0 / 720.0);
+        b = fma(p2, b, -1.0 / 24.0);
+        b = fma(p2, b, 0.5);
+        omc = p2 * b;
+    } else if (p2 < 0.0625) { // |phi| < 0.25 rad: truncation error < 3e-18 relative
+        double a = fma(p2, 1.0 / 6227020800.0, -1.0 / 39916800.0);
+        a = fma(p2, a, 1.0 / 362880.0);
+        a = fma(p2, a, -1.0 / 5040.0);
+        a = fma(p2, a, 1.0 / 120.0);
+        a = fma(p2, a, -1.0 / 6.0);
+        sn = fma(phi * p2, a, phi);
+        double b = fma(p2, 1.0 / 87178291200.0, -1.0 / 479001600.0);
+        b = fma(p2, b, 1.0 / 3628800.0);
+        b = fma(p2, b, -1.0 / 40320.0);
+        b = fma(p2, b, 1.0 / 720.0);
+        b = fma(p2, b, -1.0 / 24.0);
+        b = fma(p2, b, 0.5);
+        omc = p2 * b;
     } else {
         double s, cs, sh, ch;
         sincos(phi, &s, &cs);
@@ -442,55 +565,43 @@ __device__ __forceinline__ void sin_omc(double phi, double& sn, double& omc) {
     }
 }
 
-struct KfView {
-    const Interval* tab;
-    int n_ins;
-    double t0, t_last, inv_mean_dt;
-};
-
-// Range gate (le_vins.cc:447-451) + deskew into the keyframe's camera frame (le_vins.cc:455-461).
-// Returns false for gated points.  The two f32 roundings of pointcloud.cc:68 are kept.
-__device__ __forceinline__ bool deskew_point(float x, float y, float z, double time, const KfView& kv,
-                                             const Extrinsics& e, const Consts& c, float& ox, float& oy, float& oz) {
-    const float norm = sqrtf(v3f_sqnorm(x, y, z));
-    if (((double) norm > c.farthest) || ((double) norm < c.nearest)) return false;
-    const double t = time + e.td_b_l;
-    const int idx = find_interval(kv.tab, kv.n_ins, t, kv.t0, kv.t_last, kv.inv_mean_dt);
-    const Interval* __restrict__ it = kv.tab + idx;
-
+// Deskew one raw point into the keyframe's camera frame (le_vins.cc:455-461) with the entry in registers.
+// The two f32 roundings of pointcloud.cc:68 are kept.
+__device__ __forceinline__ void deskew_core(float x, float y, float z, double t, const EntryRegs& e, const Extrinsics& ex,
+                                            float& ox, float& oy, float& oz) {
     // p_c1 = f32(R_cl p + t_cl)   (pointcloud.cc:38 -> 68, first rounding)
     const double xd = x, yd = y, zd = z;
-    const float p1x = (float) fma(e.Rcl[6], zd, fma(e.Rcl[3], yd, fma(e.Rcl[0], xd, e.tcl[0])));
-    const float p1y = (float) fma(e.Rcl[7], zd, fma(e.Rcl[4], yd, fma(e.Rcl[1], xd, e.tcl[1])));
-    const float p1z = (float) fma(e.Rcl[8], zd, fma(e.Rcl[5], yd, fma(e.Rcl[2], xd, e.tcl[2])));
+    const float p1x = (float) fma(ex.Rcl[6], zd, fma(ex.Rcl[3], yd, fma(ex.Rcl[0], xd, ex.tcl[0])));
+    const float p1y = (float) fma(ex.Rcl[7], zd, fma(ex.Rcl[4], yd, fma(ex.Rcl[1], xd, ex.tcl[1])));
+    const float p1z = (float) fma(ex.Rcl[8], zd, fma(ex.Rcl[5], yd, fma(ex.Rcl[2], xd, ex.tcl[2])));
     const double ax = p1x, ay = p1y, az = p1z;
     // u = R_bc p_c1 + t_bc
-    const double ux = fma(e.Rbc[6], az, fma(e.Rbc[3], ay, fma(e.Rbc[0], ax, e.tbc[0])));
-    const double uy = fma(e.Rbc[7], az, fma(e.Rbc[4], ay, fma(e.Rbc[1], ax, e.tbc[1])));
-    const double uz = fma(e.Rbc[8], az, fma(e.Rbc[5], ay, fma(e.Rbc[2], ax, e.tbc[2])));
-
-    // the entry as 11 x 16-byte read-only loads (uniform across a warp almost always => one L1 wavefront each)
-    const double2* __restrict__ e2 = reinterpret_cast<const double2*>(it);
-    const double2 v1 = __ldg(e2 + 1), v2 = __ldg(e2 + 2), v3 = __ldg(e2 + 3), v4 = __ldg(e2 + 4), v5 = __ldg(e2 + 5),
-                  v6 = __ldg(e2 + 6), v7 = __ldg(e2 + 7), v8 = __ldg(e2 + 8), v9 = __ldg(e2 + 9), v10 = __ldg(e2 + 10),
-                  v11 = __ldg(e2 + 11);
-    const double s = (t - v1.x) * v1.y;
-    const double kx = v6.y, ky = v7.x, kz = v7.y;
+    const double ux = fma(ex.Rbc[6], az, fma(ex.Rbc[3], ay, fma(ex.Rbc[0], ax, ex.tbc[0])));
+    const double uy = fma(ex.Rbc[7], az, fma(ex.Rbc[4], ay, fma(ex.Rbc[1], ax, ex.tbc[1])));
+    const double uz = fma(ex.Rbc[8], az, fma(ex.Rbc[5], ay, fma(ex.Rbc[2], ax, ex.tbc[2])));
+    const double s = (t - e.ts0) * e.inv_dts;
     double sn, omc;
-    sin_omc(-s * v8.x, sn, omc);
+    sin_omc(-s * e.theta, sn, omc);
     // w = u + sin * (k x u) + (1 - cos) * k x (k x u)
-    const double cx = ky * uz - kz * uy, cy = kz * ux - kx * uz, cz = kx * uy - ky * ux;
-    const double dx = ky * cz - kz * cy, dy = kz * cx - kx * cz, dz = kx * cy - ky * cx;
+    const double cx = fma(e.ky, uz, -(e.kz * uy)), cy = fma(e.kz, ux, -(e.kx * uz)), cz = fma(e.kx, uy, -(e.ky * ux));
+    const double dx = fma(e.ky, cz, -(e.kz * cy)), dy = fma(e.kz, cx, -(e.kx * cz)), dz = fma(e.kx, cy, -(e.ky * cx));
     const double wx = fma(omc, dx, fma(sn, cx, ux));
     const double wy = fma(omc, dy, fma(sn, cy, uy));
     const double wz = fma(omc, dz, fma(sn, cz, uz));
     // p_c0 = A w + c0 + s c1   (second rounding, pointcloud.cc:45 -> 68)
-    const double rx = fma(v3.x, wz, fma(v2.y, wy, fma(v2.x, wx, fma(s, v10.x, v8.y))));
-    const double ry = fma(v4.y, wz, fma(v4.x, wy, fma(v3.y, wx, fma(s, v10.y, v9.x))));
-    const double rz = fma(v6.x, wz, fma(v5.y, wy, fma(v5.x, wx, fma(s, v11.x, v9.y))));
-    ox = (float) rx;
-    oy = (float) ry;
-    oz = (float) rz;
+    ox = (float) fma(e.A2, wz, fma(e.A1, wy, fma(e.A0, wx, fma(s, e.c1x, e.c0x))));
+    oy = (float) fma(e.A5, wz, fma(e.A4, wy, fma(e.A3, wx, fma(s, e.c1y, e.c0y))));
+    oz = (float) fma(e.A8, wz, fma(e.A7, wy, fma(e.A6, wx, fma(s, e.c1z, e.c0z))));
+}
+
+// Range gate (le_vins.cc:447-451) on the squared norm (see Consts) + entry lookup + deskew.  false for gated points.
+__device__ __forceinline__ bool deskew_point(float x, float y, float z, double time, const KfView& kv, const Extrinsics& ex,
+                                             const Consts& c, EntryRegs& e, int& cur, float& ox, float& oy, float& oz) {
+    const float n2 = v3f_sqnorm(x, y, z);
+    if ((n2 > c.n2_far) || (n2 < c.n2_near)) return false;
+    const double t = time + ex.td_b_l;
+    seek_entry(kv, t, e, cur);
+    deskew_core(x, y, z, t, e, ex, ox, oy, oz);
     return true;
 }
 

@@ -4,8 +4,10 @@
 //                  per-INS-interval table that replaces the per-point pose interpolation (misc.cc:62-103)
 //   k_deskew_bin   per point: range gate + deskew (le_vins.cc:445-464) fused with range-image binning
 //                  (tracking.cc:307-336) through a 64-bit atomicMin key (range bits | point index)
-//   k_finalize     per cell: winner -> unit vector + range (tracking.cc:340-354), z-buffer reset
-//   k_associate    per feature (one warp): exact windowed 5-NN + QR plane fit + validity + depth (tracking.cc:564-634)
+//   k_associate    per feature (one warp): exact windowed 5-NN + QR plane fit + validity + depth (tracking.cc:564-634);
+//                  in the fused path it also turns the z-buffer winners of its window into unit vectors + ranges
+//                  (tracking.cc:340-354) on the fly
+//   k_finalize     stage-wise API only: per cell winner -> unit vector + range
 // plus k_bin_cloud / k_compact / k_project / k_ring_append for the stage-wise ABI entry points.
 #pragma once
 
@@ -213,137 +215,294 @@ __global__ void __launch_bounds__(128) k_prepare(const __grid_constant__ Prepare
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_deskew_bin: one thread per point
+// k_deskew_bin: persistent CTAs, each walking a contiguous range of 1 024-point tiles.  The raw points (32 B each)
+// are streamed HBM -> shared memory by the TMA unit (cp.async.bulk, 1-D, completion on an mbarrier) through a
+// 3-stage ring, so that the memory system always has ~64 KB per CTA in flight while all 8 warps do arithmetic; the
+// per-point math never waits on an HBM load.  Each thread handles 4 points of a tile (lane-strided), keeps the INS
+// interval entry in registers across points and tiles, and issues its z-buffer probes for the 4 points together.
 // ------------------------------------------------------------------------------------------------
+constexpr int DESKEW_PPT = 4;
+constexpr int TILE_PTS = DESKEW_THREADS * DESKEW_PPT; // 1024 points = 32 KB
+constexpr int TILE_BYTES = TILE_PTS * 32;
+constexpr int DESKEW_STAGES = 3;
+constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 64;
+constexpr int DESKEW_PTS_PER_BLOCK = TILE_PTS;
+
 struct DeskewArgs {
-    const KfState* kfs; // first keyframe of this launch (blockIdx.y indexes from here)
+    KfState* kfs; // first keyframe of this launch
+    unsigned n_kf;         // keyframes in this launch
+    unsigned tiles_per_kf; // ceil(max points per keyframe / TILE_PTS)
     const PointXYZIT* pts;
     unsigned long long pts_cap;
     const Interval* table;
-    unsigned long long* zbuf; // [gridDim.y][CELLS]
-    PointXYZI* cloud_out;     // streaming only (gridDim.y == 1), nullable
+    unsigned long long* zbuf; // [n_kf][CELLS]
+    PointXYZI* cloud_out;     // streaming only (n_kf == 1), nullable
+    unsigned gen;             // z-buffer generation of this launch
     Extrinsics ext;
     Consts c;
 };
 
-__device__ __forceinline__ void zbuf_min(unsigned long long* cell, unsigned long long key) {
-    // most points lose: filter with a plain L2 read first (a stale value is only ever larger, so no update is missed)
-    if (key < __ldcg(cell)) atomicMin(cell, key);
+// ---- mbarrier / TMA bulk-copy primitives (PTX) ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completing `bytes` on the mbarrier (size and addresses multiples of 16 B)
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
-template <int LIBM_MODE, bool WRITE_CLOUD>
-__global__ void __launch_bounds__(DESKEW_THREADS) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
-    const KfState* __restrict__ kf = a.kfs + blockIdx.y;
-    const unsigned n = kf->n_proj;
-    const unsigned k = blockIdx.x * DESKEW_THREADS + threadIdx.x;
-    if (blockIdx.x * DESKEW_THREADS >= n) return;
-    if (k >= n) return;
+__device__ __forceinline__ KfView kf_view(const KfState* __restrict__ kf, const Interval* table) {
     KfView kv;
-    kv.tab = a.table + kf->table_begin;
+    kv.tab = table + kf->table_begin;
     kv.n_ins = (int) kf->ins_count;
     kv.t0 = kf->ins_t0;
     kv.t_last = kf->ins_t_last;
     kv.inv_mean_dt = kf->inv_mean_dt;
+    return kv;
+}
 
-    const unsigned long long pi = wrap(kf->proj_begin + k, a.pts_cap);
-    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(a.pts + pi);
-    const float4 xyz = __ldg(p4);
-    const double2 it = __ldg(reinterpret_cast<const double2*>(p4 + 1));
-
-    float ox, oy, oz;
-    const bool kept = deskew_point(xyz.x, xyz.y, xyz.z, it.y, kv, a.ext, a.c, ox, oy, oz);
-    if (WRITE_CLOUD) {
-        float4* out = reinterpret_cast<float4*>(a.cloud_out + k);
-        out[0] = kept ? make_float4(ox, oy, oz, 1.0f) : make_float4(0.f, 0.f, 0.f, 1.0f); // resize() default (le_vins.cc:438)
-        out[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+// Returns true when this key is the first of the current generation in its cell (exactly one thread per cell sees that).
+__device__ __forceinline__ bool zbuf_min(unsigned long long* cell, unsigned long long key, unsigned gen) {
+    // most points lose: filter with a plain L2 read first (a stale value is only ever larger, so no update is missed)
+    if (key < __ldcg(cell)) {
+        const unsigned long long old = atomicMin(cell, key);
+        return !key_live(old, gen);
     }
-    if (!kept) return; // a default point lands at col = -150 and is dropped at tracking.cc:326-328
-    const int cell = cell_of_point<LIBM_MODE>(ox, oy, oz, a.c);
-    if (cell < 0) return;
-    const float range = sqrtf(v3f_sqnorm(ox, oy, oz)); // tracking.cc:330
-    if (!(range < FLT_MAX)) return;                    // tracking.cc:332 against the FLT_MAX initial value
-    const unsigned long long key = ((unsigned long long) __float_as_uint(range) << 32) | k;
-    zbuf_min(a.zbuf + (size_t) blockIdx.y * CELLS + cell, key);
+    return false;
+}
+
+template <int LIBM_MODE>
+__device__ __noinline__ int cell_of_point_exact(float x, float y, float z, const Consts& c) {
+    return cell_of_point<LIBM_MODE>(x, y, z, c);
+}
+
+// cell id: polynomial fast path, exact mirrored path next to rounding boundaries (bit-identical by construction)
+template <int LIBM_MODE>
+__device__ __forceinline__ int cell_id(float x, float y, float z, const Consts& c) {
+    bool amb;
+    int cell = cell_of_point_fast(x, y, z, c, amb);
+    if (amb) cell = cell_of_point_exact<LIBM_MODE>(x, y, z, c);
+    return cell;
+}
+
+template <int LIBM_MODE, bool WRITE_CLOUD>
+__global__ void __launch_bounds__(DESKEW_THREADS, 2) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + DESKEW_STAGES * TILE_BYTES);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const unsigned total = a.n_kf * a.tiles_per_kf;
+    const unsigned per = (total + gridDim.x - 1) / gridDim.x;
+    const unsigned t_begin = blockIdx.x * per;
+    const unsigned t_end = min(t_begin + per, total);
+    if (t_begin >= t_end) return;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < DESKEW_STAGES; s++) mbar_init(full + s, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // producer (thread 0): start the copy of tile t into stage s
+    auto issue = [&](unsigned t, int s) {
+        const KfState* kf = a.kfs + t / a.tiles_per_kf;
+        const unsigned off = (t % a.tiles_per_kf) * TILE_PTS;
+        const unsigned n = kf->n_proj;
+        const unsigned cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
+        mbar_arrive_expect_tx(full + s, cnt * 32u);
+        if (cnt) {
+            unsigned char* dst = smem_raw + s * TILE_BYTES;
+            const unsigned long long phys = wrap(kf->proj_begin + off, a.pts_cap);
+            const unsigned long long room = a.pts_cap - phys; // ring: the tile may wrap around the end
+            const unsigned first = room < cnt ? (unsigned) room : cnt;
+            tma_bulk_g2s(dst, a.pts + phys, first * 32u, full + s);
+            if (first < cnt) tma_bulk_g2s(dst + first * 32u, a.pts, (cnt - first) * 32u, full + s);
+        }
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < DESKEW_STAGES - 1; i++)
+            if (t_begin + i < t_end) issue(t_begin + i, i);
+    }
+
+    EntryRegs e;
+    int cur = -1;
+    unsigned cur_kf = 0xffffffffu;
+    KfView kv{};
+    unsigned n = 0;
+    unsigned first_fills = 0;
+
+    unsigned it = 0;
+    for (unsigned t = t_begin; t < t_end; ++t, ++it) {
+        const int s = it % DESKEW_STAGES;
+        if (tid == 0 && t + DESKEW_STAGES - 1 < t_end) issue(t + DESKEW_STAGES - 1, (it + DESKEW_STAGES - 1) % DESKEW_STAGES);
+
+        const unsigned kfi = t / a.tiles_per_kf;
+        KfState* __restrict__ kf = a.kfs + kfi;
+        if (kfi != cur_kf) { // new keyframe: flush the fill count, reload the view, drop the cached interval
+            if (cur_kf != 0xffffffffu) {
+                first_fills = __reduce_add_sync(0xffffffffu, first_fills);
+                if (lane == 0 && first_fills) atomicAdd(&a.kfs[cur_kf].m, first_fills);
+                first_fills = 0;
+            }
+            cur_kf = kfi;
+            kv = kf_view(kf, a.table);
+            n = kf->n_proj;
+            cur = -1;
+        }
+        const unsigned off = (t % a.tiles_per_kf) * TILE_PTS;
+        const unsigned cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
+
+        mbar_wait(full + s, (it / DESKEW_STAGES) & 1);
+
+        if (cnt) {
+            const float4* __restrict__ sp = reinterpret_cast<const float4*>(smem_raw + s * TILE_BYTES);
+            unsigned long long key[DESKEW_PPT];
+            int cell[DESKEW_PPT];
+#pragma unroll
+            for (int j = 0; j < DESKEW_PPT; j++) {
+                const unsigned i = warp * (DESKEW_PPT * 32) + j * 32 + lane;
+                cell[j] = -1;
+                key[j] = 0;
+                if (i < cnt) {
+                    const float4 xyz = sp[2 * i];
+                    const double tm = reinterpret_cast<const double2*>(sp)[2 * i + 1].y;
+                    const unsigned k = off + i;
+                    float ox, oy, oz;
+                    const bool kept = deskew_point(xyz.x, xyz.y, xyz.z, tm, kv, a.ext, a.c, e, cur, ox, oy, oz);
+                    if (WRITE_CLOUD) {
+                        float4* out = reinterpret_cast<float4*>(a.cloud_out + k);
+                        out[0] = kept ? make_float4(ox, oy, oz, 1.0f) : make_float4(0.f, 0.f, 0.f, 1.0f); // resize() default (le_vins.cc:438)
+                        out[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    if (kept) { // a default point lands at col = -150 and is dropped at tracking.cc:326-328
+                        const int cid = cell_id<LIBM_MODE>(ox, oy, oz, a.c);
+                        if (cid >= 0) {
+                            const float range = sqrtf(v3f_sqnorm(ox, oy, oz)); // tracking.cc:330
+                            if (range < FLT_MAX) {                             // tracking.cc:332 against the FLT_MAX initial value
+                                cell[j] = cid;
+                                key[j] = key_make(a.gen, range, k);
+                            }
+                        }
+                    }
+                }
+            }
+            // z-buffer: probe the 4 cells together (independent L2 reads), then the few atomics that can still win
+            unsigned long long* __restrict__ zb = a.zbuf + (size_t) kfi * CELLS;
+            unsigned long long seen[DESKEW_PPT];
+#pragma unroll
+            for (int j = 0; j < DESKEW_PPT; j++) seen[j] = cell[j] >= 0 ? __ldcg(zb + cell[j]) : 0ull;
+#pragma unroll
+            for (int j = 0; j < DESKEW_PPT; j++)
+                if (cell[j] >= 0 && key[j] < seen[j]) {
+                    const unsigned long long old = atomicMin(zb + cell[j], key[j]);
+                    first_fills += !key_live(old, a.gen);
+                }
+        }
+        __syncthreads(); // every thread is done with stage s before it is refilled (next iteration's issue)
+    }
+    first_fills = __reduce_add_sync(0xffffffffu, first_fills);
+    if (lane == 0 && first_fills) atomicAdd(&a.kfs[cur_kf].m, first_fills);
 }
 
 // explicit-cloud binning for levins_build_range_image(cloud != NULL)
 template <int LIBM_MODE>
 __global__ void __launch_bounds__(256) k_bin_cloud(const PointXYZI* __restrict__ cloud, unsigned n, unsigned long long* zbuf,
-                                                   const __grid_constant__ Consts c) {
+                                                   unsigned gen, KfState* kf, const __grid_constant__ Consts c) {
     const unsigned k = blockIdx.x * 256 + threadIdx.x;
-    if (k >= n) return;
-    const float4 p = __ldg(reinterpret_cast<const float4*>(cloud + k));
-    const int cell = cell_of_point<LIBM_MODE>(p.x, p.y, p.z, c);
-    if (cell < 0) return;
-    const float range = sqrtf(v3f_sqnorm(p.x, p.y, p.z));
-    if (!(range < FLT_MAX)) return;
-    zbuf_min(zbuf + cell, ((unsigned long long) __float_as_uint(range) << 32) | k);
+    unsigned ff = 0;
+    if (k < n) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(cloud + k));
+        const int cell = cell_id<LIBM_MODE>(p.x, p.y, p.z, c);
+        if (cell >= 0) {
+            const float range = sqrtf(v3f_sqnorm(p.x, p.y, p.z));
+            if (range < FLT_MAX) ff = zbuf_min(zbuf + cell, key_make(gen, range, k), gen);
+        }
+    }
+    ff = __reduce_add_sync(0xffffffffu, ff);
+    if ((threadIdx.x & 31) == 0 && ff) atomicAdd(&kf->m, ff);
+}
+
+// unit vector + range of a camera-frame point (tracking.cc:346-351)
+__device__ __forceinline__ float4 unit_and_range(float x, float y, float z) {
+    const float n2 = v3f_sqnorm(x, y, z);
+    const float r = sqrtf(n2);
+    if (n2 > 0.f) {
+        const float nn = sqrtf(n2);
+        return make_float4(x / nn, y / nn, z / nn, r);
+    }
+    return make_float4(x, y, z, r);
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_finalize: one thread per cell.  cells[] = (unit x, unit y, unit z, range), range = -1 marks an empty cell.
+// k_finalize (stage-wise entry points only): one thread per cell.
+// cells[] = (unit x, unit y, unit z, range), range = -1 marks an empty cell.
 // ------------------------------------------------------------------------------------------------
 struct FinalizeArgs {
-    KfState* kfs;
+    const KfState* kfs;
     const PointXYZIT* pts;
     unsigned long long pts_cap;
     const Interval* table;
     const PointXYZI* cloud; // FROM_CLOUD source
-    unsigned long long* zbuf;
+    const unsigned long long* zbuf;
     float4* cells;   // [gridDim.y][CELLS]
     int32_t* winner; // nullable, [CELLS] (single keyframe)
+    unsigned gen;
     Extrinsics ext;
     Consts c;
 };
 
 template <bool FROM_CLOUD>
 __global__ void __launch_bounds__(FINALIZE_THREADS) k_finalize(const __grid_constant__ FinalizeArgs a) {
-    KfState* kf = a.kfs + blockIdx.y;
+    const KfState* __restrict__ kf = a.kfs + blockIdx.y;
     const int cell = blockIdx.x * FINALIZE_THREADS + threadIdx.x;
-    bool filled = false;
-    if (cell < CELLS) {
-        unsigned long long* zp = a.zbuf + (size_t) blockIdx.y * CELLS + cell;
-        const unsigned long long key = *zp;
-        float4 out = make_float4(0.f, 0.f, 0.f, -1.0f);
-        int win = -1;
-        if (key != EMPTY_KEY) {
-            const unsigned k = (unsigned) (key & 0xffffffffu);
-            float x, y, z;
-            if (FROM_CLOUD) {
-                const float4 p = __ldg(reinterpret_cast<const float4*>(a.cloud + k));
-                x = p.x;
-                y = p.y;
-                z = p.z;
-            } else { // recompute the winner's deskew: same function, same bits as in k_deskew_bin
-                KfView kv;
-                kv.tab = a.table + kf->table_begin;
-                kv.n_ins = (int) kf->ins_count;
-                kv.t0 = kf->ins_t0;
-                kv.t_last = kf->ins_t_last;
-                kv.inv_mean_dt = kf->inv_mean_dt;
-                const unsigned long long pi = wrap(kf->proj_begin + k, a.pts_cap);
-                const float4* __restrict__ p4 = reinterpret_cast<const float4*>(a.pts + pi);
-                const float4 xyz = __ldg(p4);
-                const double2 it = __ldg(reinterpret_cast<const double2*>(p4 + 1));
-                deskew_point(xyz.x, xyz.y, xyz.z, it.y, kv, a.ext, a.c, x, y, z);
-            }
-            const float n2 = v3f_sqnorm(x, y, z); // tracking.cc:348-349
-            const float r = sqrtf(n2);
-            if (n2 > 0.f) {
-                const float nn = sqrtf(n2);
-                out = make_float4(x / nn, y / nn, z / nn, r);
-            } else {
-                out = make_float4(x, y, z, r);
-            }
-            win = (int) k;
-            filled = true;
-            *zp = EMPTY_KEY; // leave the z-buffer ready for the next keyframe that uses this slot
+    if (cell >= CELLS) return;
+    const unsigned long long key = a.zbuf[(size_t) blockIdx.y * CELLS + cell];
+    float4 out = make_float4(0.f, 0.f, 0.f, -1.0f);
+    int win = -1;
+    if (key_live(key, a.gen)) {
+        const unsigned k = key_index(key);
+        float x, y, z;
+        if (FROM_CLOUD) {
+            const float4 p = __ldg(reinterpret_cast<const float4*>(a.cloud + k));
+            x = p.x;
+            y = p.y;
+            z = p.z;
+        } else { // recompute the winner's deskew: same function, same bits as in k_deskew_bin
+            const KfView kv = kf_view(kf, a.table);
+            const float4* __restrict__ p4 = reinterpret_cast<const float4*>(a.pts + wrap(kf->proj_begin + k, a.pts_cap));
+            const float4 xyz = __ldg(p4);
+            const double tm = __ldg(reinterpret_cast<const double2*>(p4 + 1)).y;
+            EntryRegs e;
+            int cur = -1;
+            deskew_point(xyz.x, xyz.y, xyz.z, tm, kv, a.ext, a.c, e, cur, x, y, z);
         }
-        a.cells[(size_t) blockIdx.y * CELLS + cell] = out;
-        if (a.winner) a.winner[cell] = win;
+        out = unit_and_range(x, y, z);
+        win = (int) k;
     }
-    const unsigned cnt = __syncthreads_count(filled);
-    if (threadIdx.x == 0 && cnt) atomicAdd(&kf->m, cnt);
+    a.cells[(size_t) blockIdx.y * CELLS + cell] = out;
+    if (a.winner) a.winner[cell] = win;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -402,13 +561,25 @@ __global__ void __launch_bounds__(1024) k_compact(const float4* __restrict__ cel
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_associate: one warp per feature
+// k_associate: one warp per feature.
+//   FUSED = false: candidates come from the finalised cell array (stage-wise API).
+//   FUSED = true : candidates come straight from the z-buffer: the winner of each window cell is deskewed on the fly
+//                  (same function, same bits as in k_deskew_bin), so the batch / keyframe path needs no k_finalize,
+//                  no 1.44 MB cell array per keyframe and only deskews the cells some feature actually looks at.
 // ------------------------------------------------------------------------------------------------
 struct AssocArgs {
     const KfState* kfs;
     const float* queries; // pool, 3 floats per query
-    const float4* cells;  // [gridDim.y][CELLS]
+    const float4* cells;  // !FUSED: [gridDim.y][CELLS]
     const int32_t* c2c;   // nullable (single keyframe): cell -> compact index
+    // FUSED sources
+    const unsigned long long* zbuf; // [gridDim.y][CELLS]
+    const PointXYZIT* pts;
+    unsigned long long pts_cap;
+    const Interval* table;
+    unsigned gen;
+    Extrinsics ext;
+    // outputs
     int8_t* type;
     float4* xyz_depth;
     int32_t* flags;
@@ -417,6 +588,7 @@ struct AssocArgs {
     Consts c;
 };
 
+template <bool FUSED>
 __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_constant__ AssocArgs a) {
     const KfState* __restrict__ kf = a.kfs + blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -424,60 +596,133 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_con
     if (f >= kf->q_count) return;
     const size_t qi = kf->q_begin + f;
     const float qx = __ldg(a.queries + 3 * qi), qy = __ldg(a.queries + 3 * qi + 1), qz = __ldg(a.queries + 3 * qi + 2);
-    const float4* __restrict__ cells = a.cells + (size_t) blockIdx.y * CELLS;
 
-    // the query's own cell; precision is irrelevant here, the window has a full cell of slack
+    // The query's position in cell units.  Precision is irrelevant: the window and the mask below carry half a cell
+    // of slack, and every candidate they keep is measured with the reference's exact f32 arithmetic afterwards.
     const float el = atan2f(qy, sqrtf(qx * qx + qz * qz));
     const float az = atan2f(qz, qx);
-    const float inv_ang = (float) a.c.inv_angle, off = (float) a.c.half_offset;
-    const int rowq = (int) rintf((el + off) * inv_ang);
-    const int colq = (int) rintf((az - off) * inv_ang);
+    const float inv_ang = a.c.inv_angle_f, off = (float) a.c.half_offset;
+    const float rq = (el + off) * inv_ang, cq = (az - off) * inv_ang;
+    const int rowq = (int) rintf(rq), colq = (int) rintf(cq);
+    // Only points within the acceptance radius T = 3 sin(0.3 deg) (chord; 3.00002 cells of arc) can influence a result
+    // (tracking.cc:573).  A point of cell (r, c) lies within +-0.5 cell of (r, c) in (row, col) angle, and by the
+    // haversine formula its arc distance g to the query obeys  g^2 >= (1 - 3e-4) (dEl^2 + cos(el_q) cos(el_p) dAz^2),
+    // |el_p| <= |el_q| + 0.91 deg.  Cells that cannot contain such a point are skipped (about 60 % of the window).
+    const float ael = fabsf(el);
+    const float cmin = fmaxf(0.f, __cosf(ael) * __cosf(fminf(ael + 0.016f, 1.5707963f))) * 0.999f;
 
-    unsigned dbits[4];
-    int cid[4];
+    // ---- candidates: scan the 9 x 13 window, keep live cells inside the mask, compact them across the warp ----
+    __shared__ unsigned long long s_key[ASSOC_WARPS][128];
+    __shared__ int s_cid[ASSOC_WARPS][128];
+    const int wib = threadIdx.x >> 5;
+    const unsigned long long* __restrict__ zb = FUSED ? a.zbuf + (size_t) blockIdx.y * CELLS : nullptr;
+    const float4* __restrict__ cells = FUSED ? nullptr : a.cells + (size_t) blockIdx.y * CELLS;
+    int count = 0;
 #pragma unroll
     for (int itc = 0; itc < 4; itc++) {
-        dbits[itc] = 0x7f800000u; // +inf
-        cid[itc] = 0x7fffffff;
         const int j = lane + 32 * itc;
-        if (j < WIN_CELLS) {
-            const int r = rowq - WIN_ROWS + j / WIN_W;
-            const int cc = colq - WIN_COLS + j % WIN_W;
-            if (r >= 0 && r < IMG && cc >= 0 && cc < IMG) {
-                const float4 v = __ldg(cells + r * IMG + cc);
-                if (v.w >= 0.f) {
+        const int r = rowq - WIN_ROWS + j / WIN_W;
+        const int cc = colq - WIN_COLS + j % WIN_W;
+        bool live = false;
+        unsigned long long key = 0;
+        if (j < WIN_CELLS && r >= 0 && r < IMG && cc >= 0 && cc < IMG) {
+            const float dr = fmaxf(0.f, fabsf((float) r - rq) - 0.51f);
+            const float dc = fmaxf(0.f, fabsf((float) cc - cq) - 0.51f);
+            if (dr * dr + cmin * dc * dc <= 9.0601f) { // 3.01^2
+                if (FUSED) {
+                    key = __ldg(zb + r * IMG + cc);
+                    live = key_live(key, a.gen);
+                } else {
+                    live = __ldg(&cells[r * IMG + cc].w) >= 0.f;
+                }
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const int pos = count + __popc(bal & ((1u << lane) - 1));
+            s_key[wib][pos] = key;
+            s_cid[wib][pos] = r * IMG + cc;
+        }
+        count += __popc(bal);
+    }
+    __syncwarp();
+
+    float4 cand[4];
+    int cid[4];
+    unsigned dbits[4];
+#pragma unroll
+    for (int itc = 0; itc < 4; itc++) {
+        cand[itc] = make_float4(0.f, 0.f, 0.f, -1.0f);
+        cid[itc] = 0x7fffffff;
+        dbits[itc] = 0x7f800000u; // +inf
+    }
+    {
+        KfView kv{};
+        unsigned long long pbegin = 0;
+        if (FUSED) {
+            kv = kf_view(kf, a.table);
+            pbegin = kf->proj_begin;
+        }
+        EntryRegs e;
+        int cur = -1;
+#pragma unroll
+        for (int itc = 0; itc < 4; itc++) {
+            if (32 * itc < count) { // warp-uniform: rounds beyond the candidate count cost nothing
+                const int ci = lane + 32 * itc;
+                if (ci < count) {
+                    cid[itc] = s_cid[wib][ci];
+                    if (FUSED) {
+                        // the winner of this cell, deskewed on the fly: same function, same bits as in k_deskew_bin
+                        const float4* __restrict__ p4 =
+                            reinterpret_cast<const float4*>(a.pts + wrap(pbegin + key_index(s_key[wib][ci]), a.pts_cap));
+                        const float4 xyz = __ldg(p4);
+                        const double tm = __ldg(reinterpret_cast<const double2*>(p4 + 1)).y;
+                        float x, y, z;
+                        deskew_point(xyz.x, xyz.y, xyz.z, tm, kv, a.ext, a.c, e, cur, x, y, z);
+                        cand[itc] = unit_and_range(x, y, z); // tracking.cc:346-351
+                    } else {
+                        cand[itc] = __ldg(cells + cid[itc]);
+                    }
                     // FLANN L2_Simple<float>: result = 0; result += diff*diff, x then y then z
-                    const float dx = qx - v.x, dy = qy - v.y, dz = qz - v.z;
+                    const float dx = qx - cand[itc].x, dy = qy - cand[itc].y, dz = qz - cand[itc].z;
                     float d = dx * dx;
                     d = d + dy * dy;
                     d = d + dz * dz;
                     dbits[itc] = __float_as_uint(d);
-                    cid[itc] = r * IMG + cc;
                 }
             }
         }
     }
 
-    // top-5 by (d2, cell id): cell ids are row-major, i.e. the order of the reference's compacted indices
+    // ---- top-5 by (d2, cell id): cell ids are row-major, i.e. the order of the reference's compacted indices ----
     unsigned nn_d[5];
     int nn_c[5];
+    float4 nn_p[5];
     int found = 0;
 #pragma unroll
     for (int r = 0; r < 5; r++) {
         unsigned bd = dbits[0];
         int bc = cid[0];
+        float4 bp = cand[0];
 #pragma unroll
         for (int itc = 1; itc < 4; itc++)
             if (dbits[itc] < bd || (dbits[itc] == bd && cid[itc] < bc)) {
                 bd = dbits[itc];
                 bc = cid[itc];
+                bp = cand[itc];
             }
         const unsigned m1 = __reduce_min_sync(0xffffffffu, bd);
         const unsigned m2 = __reduce_min_sync(0xffffffffu, bd == m1 ? (unsigned) bc : 0xffffffffu);
+        const bool mine = (bd == m1) && ((unsigned) bc == m2);
+        const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
         nn_d[r] = m1;
         nn_c[r] = (int) m2;
+        nn_p[r].x = __shfl_sync(0xffffffffu, bp.x, owner);
+        nn_p[r].y = __shfl_sync(0xffffffffu, bp.y, owner);
+        nn_p[r].z = __shfl_sync(0xffffffffu, bp.z, owner);
+        nn_p[r].w = __shfl_sync(0xffffffffu, bp.w, owner);
         if (m1 != 0x7f800000u) found++;
-        if (bd == m1 && (unsigned) bc == m2) { // this lane owns the winner: retire it
+        if (mine) { // this lane owns the winner: retire it
 #pragma unroll
             for (int itc = 0; itc < 4; itc++)
                 if (dbits[itc] == m1 && cid[itc] == (int) m2) {
@@ -495,16 +740,12 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_con
         flags = 2;
     } else {
         double P[5][3];
-        float rng0 = 0.f, rng4 = 0.f;
 #pragma unroll
         for (int k = 0; k < 5; k++) { // tracking.cc:577-581
-            const float4 v = __ldg(cells + nn_c[k]);
-            const double rr = (double) v.w;
-            P[k][0] = (double) v.x * rr;
-            P[k][1] = (double) v.y * rr;
-            P[k][2] = (double) v.z * rr;
-            if (k == 0) rng0 = v.w;
-            if (k == 4) rng4 = v.w;
+            const double rr = (double) nn_p[k].w;
+            P[k][0] = (double) nn_p[k].x * rr;
+            P[k][1] = (double) nn_p[k].y * rr;
+            P[k][2] = (double) nn_p[k].z * rr;
         }
         double mx[3];
         colpiv_qr_solve_5x3(P, mx);                            // tracking.cc:584-589
@@ -527,7 +768,7 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_con
                 flags |= 4;
             }
         }
-        const float depth_diff = fabsf(rng0 - rng4); // :607-608
+        const float depth_diff = fabsf(nn_p[0].w - nn_p[4].w); // :607-608
         if ((double) depth_diff > a.c.range_spread) {
             isvalid = false;
             flags |= 8;
@@ -585,9 +826,5 @@ __global__ void __launch_bounds__(256) k_project(const PointXYZI* __restrict__ s
     d4[1] = q;
 }
 
-__global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
-    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = v;
-}
 
 } // namespace lv

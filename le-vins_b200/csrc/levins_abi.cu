@@ -52,6 +52,8 @@ struct levins_ctx {
     std::string err;
     std::mutex mu; // append_scan may come from another thread
     uint64_t launches = 0;
+    int num_sms = 148;
+    bool deskew_attr_set = false;
 
     // ---- streaming state ----
     DevBuf ring;      // PointXYZIT x cfg.max_points
@@ -63,7 +65,8 @@ struct levins_ctx {
     DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
     DevBuf s_in_cloud; // explicit cloud uploaded by build_range_image
     DevBuf s_zbuf, s_cells, s_c2c, s_unit, s_winner;
-    bool s_zbuf_init = false;
+    unsigned s_gen = 255; // z-buffer generation of the streaming slot (255 = never initialised)
+    unsigned s_img_gen = 0; // generation whose winners are in s_zbuf / s_cells
     size_t s_cloud_n = 0;     // points in the resident cloud
     bool s_cloud_valid = false;
     bool s_image_valid = false;
@@ -79,6 +82,7 @@ struct levins_ctx {
     size_t b_nq = 0, b_npts = 0, b_nins = 0;
     int b_wave = 16;
     int b_wave_alloc = 0;
+    unsigned b_gen = 255;
     bool b_valid = false;
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -123,13 +127,46 @@ Consts make_consts(const levins_config& cfg) {
     c.range_spread = cfg.range_spread_threshold;
     c.stack_interval = cfg.stack_interval;
     c.libm_mode = cfg.libm_mode;
+    // Range gate restated on the squared norm: sqrtf is monotone and correctly rounded on host and device alike, so
+    // "(double) sqrtf(n2) > farthest" flips at one float; find it by bisection over the (ordered) positive float patterns.
+    auto as_f = [](uint32_t b) { float f; memcpy(&f, &b, 4); return f; };
+    {
+        uint32_t lo = 0, hi = 0x7f7fffffu; // largest n2 that is NOT gated as "too far"
+        if ((double) sqrtf(as_f(hi)) > c.farthest) {
+            while (hi - lo > 1) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if ((double) sqrtf(as_f(mid)) > c.farthest) hi = mid; else lo = mid;
+            }
+            c.n2_far = (double) sqrtf(as_f(lo)) > c.farthest ? -1.0f : as_f(lo);
+        } else {
+            c.n2_far = as_f(hi);
+        }
+    }
+    {
+        uint32_t lo = 0, hi = 0x7f7fffffu; // smallest n2 that is NOT gated as "too near"
+        if ((double) sqrtf(as_f(lo)) < c.nearest) {
+            while (hi - lo > 1) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if ((double) sqrtf(as_f(mid)) < c.nearest) lo = mid; else hi = mid;
+            }
+            c.n2_near = as_f(hi);
+        } else {
+            c.n2_near = 0.0f;
+        }
+    }
+    c.inv_angle_f = (float) (1.0 / ANGLE);
+    c.cell_guard = 4e-4f; // >= 4x the worst-case error of the polynomial cell path
     return c;
 }
 
-int fill_zbuf(levins_ctx* ctx, unsigned long long* z, size_t n) {
-    k_fill_u64<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(z, n, EMPTY_KEY);
-    ctx->launches++;
-    CU(cudaGetLastError());
+// Start a new z-buffer generation for `n` cells (see key_make): a real clear only every 254 uses.
+int next_gen(levins_ctx* ctx, unsigned long long* z, size_t n, unsigned* gen) {
+    if (*gen <= 1 || *gen > 254) {
+        CU(cudaMemsetAsync(z, 0xFF, n * sizeof(unsigned long long), ctx->stream));
+        *gen = 254;
+    } else {
+        *gen -= 1;
+    }
     return LEVINS_OK;
 }
 
@@ -149,12 +186,7 @@ int ensure_stream_buffers(levins_ctx* ctx, size_t n_ins, size_t n_feat) {
     CU(ctx->s_winner.ensure((size_t) CELLS * 4));
     if (!ctx->s_zbuf.p) {
         CU(ctx->s_zbuf.ensure((size_t) CELLS * 8));
-        ctx->s_zbuf_init = false;
-    }
-    if (!ctx->s_zbuf_init) {
-        int r = fill_zbuf(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS);
-        if (r) return r;
-        ctx->s_zbuf_init = true;
+        ctx->s_gen = 255;
     }
     return LEVINS_OK;
 }
@@ -170,19 +202,34 @@ int ensure_ring(levins_ctx* ctx) {
     return LEVINS_OK;
 }
 
-void launch_deskew(levins_ctx* ctx, dim3 grid, const DeskewArgs& a, bool write_cloud) {
+// k_deskew_bin is persistent: at most two CTAs per SM (96 KB of TMA staging each), each walking a contiguous tile range.
+int launch_deskew(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf, bool write_cloud) {
+    a.n_kf = n_kf;
+    a.tiles_per_kf = (unsigned) ((max_pts + TILE_PTS - 1) / TILE_PTS);
+    const unsigned total = a.n_kf * a.tiles_per_kf;
+    if (total == 0) return LEVINS_OK;
+    if (!ctx->deskew_attr_set) {
+        CU(cudaFuncSetAttribute(k_deskew_bin<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
+        CU(cudaFuncSetAttribute(k_deskew_bin<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
+        CU(cudaFuncSetAttribute(k_deskew_bin<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
+        CU(cudaFuncSetAttribute(k_deskew_bin<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
+        ctx->deskew_attr_set = true;
+    }
+    const unsigned grid = std::min<unsigned>(total, 2u * (unsigned) ctx->num_sms);
     if (ctx->consts.libm_mode == 0) {
         if (write_cloud)
-            k_deskew_bin<0, true><<<grid, DESKEW_THREADS, 0, ctx->stream>>>(a);
+            k_deskew_bin<0, true><<<grid, DESKEW_THREADS, DESKEW_SMEM, ctx->stream>>>(a);
         else
-            k_deskew_bin<0, false><<<grid, DESKEW_THREADS, 0, ctx->stream>>>(a);
+            k_deskew_bin<0, false><<<grid, DESKEW_THREADS, DESKEW_SMEM, ctx->stream>>>(a);
     } else {
         if (write_cloud)
-            k_deskew_bin<1, true><<<grid, DESKEW_THREADS, 0, ctx->stream>>>(a);
+            k_deskew_bin<1, true><<<grid, DESKEW_THREADS, DESKEW_SMEM, ctx->stream>>>(a);
         else
-            k_deskew_bin<1, false><<<grid, DESKEW_THREADS, 0, ctx->stream>>>(a);
+            k_deskew_bin<1, false><<<grid, DESKEW_THREADS, DESKEW_SMEM, ctx->stream>>>(a);
     }
     ctx->launches++;
+    CU(cudaGetLastError());
+    return LEVINS_OK;
 }
 
 // read the ring state (synchronises)
@@ -225,7 +272,12 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     CU(cudaGetLastError());
 
     const size_t n_ub = ctx->ring_count_ub;
+    if (n_ub >= MAX_POINTS_PER_KEYFRAME) return fail(ctx, LEVINS_ERR_CAPACITY, "more than 2^25 points in one keyframe window");
     if (write_cloud) CU(ctx->s_cloud.ensure(n_ub * sizeof(PointXYZI)));
+    {
+        int r = next_gen(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS, &ctx->s_gen);
+        if (r) return r;
+    }
     DeskewArgs da{};
     da.kfs = ctx->s_kf.as<KfState>();
     da.pts = ctx->ring.as<PointXYZIT>();
@@ -233,14 +285,11 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     da.table = ctx->s_table.as<Interval>();
     da.zbuf = ctx->s_zbuf.as<unsigned long long>();
     da.cloud_out = write_cloud ? ctx->s_cloud.as<PointXYZI>() : nullptr;
+    da.gen = ctx->s_gen;
     da.ext = ctx->ext;
     da.c = ctx->consts;
     (void) bin;
-    dim3 grid((unsigned) ((n_ub + DESKEW_THREADS - 1) / DESKEW_THREADS), 1);
-    if (grid.x == 0) grid.x = 1;
-    launch_deskew(ctx, grid, da, write_cloud);
-    CU(cudaGetLastError());
-    return LEVINS_OK;
+    return launch_deskew(ctx, da, n_ub, 1, write_cloud);
 }
 
 int run_finalize_stream(levins_ctx* ctx, bool from_cloud, const PointXYZI* cloud, bool want_winner) {
@@ -253,6 +302,7 @@ int run_finalize_stream(levins_ctx* ctx, bool from_cloud, const PointXYZI* cloud
     fa.zbuf = ctx->s_zbuf.as<unsigned long long>();
     fa.cells = ctx->s_cells.as<float4>();
     fa.winner = want_winner ? ctx->s_winner.as<int32_t>() : nullptr;
+    fa.gen = ctx->s_gen;
     fa.ext = ctx->ext;
     fa.c = ctx->consts;
     dim3 grid((CELLS + FINALIZE_THREADS - 1) / FINALIZE_THREADS, 1);
@@ -265,12 +315,18 @@ int run_finalize_stream(levins_ctx* ctx, bool from_cloud, const PointXYZI* cloud
     return LEVINS_OK;
 }
 
-int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx) {
+int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused) {
     AssocArgs aa{};
     aa.kfs = ctx->s_kf.as<KfState>();
     aa.queries = ctx->s_queries.as<float>();
     aa.cells = ctx->s_cells.as<float4>();
     aa.c2c = with_idx ? ctx->s_c2c.as<int32_t>() : nullptr;
+    aa.zbuf = ctx->s_zbuf.as<unsigned long long>();
+    aa.pts = ctx->ring.as<PointXYZIT>();
+    aa.pts_cap = ctx->cfg.max_points;
+    aa.table = ctx->s_table.as<Interval>();
+    aa.gen = ctx->s_gen;
+    aa.ext = ctx->ext;
     aa.type = ctx->s_type.as<int8_t>();
     aa.xyz_depth = ctx->s_xyzd.as<float4>();
     aa.flags = ctx->s_flags.as<int32_t>();
@@ -278,7 +334,10 @@ int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx) {
     aa.knn_d2 = with_idx ? ctx->s_knn_d2.as<float>() : nullptr;
     aa.c = ctx->consts;
     dim3 grid((unsigned) ((nf + ASSOC_WARPS - 1) / ASSOC_WARPS), 1);
-    k_associate<<<grid, ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
+    if (fused)
+        k_associate<true><<<grid, ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
+    else
+        k_associate<false><<<grid, ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
     ctx->launches++;
     CU(cudaGetLastError());
     return LEVINS_OK;
@@ -349,6 +408,7 @@ extern "C" int levins_create(int device, const levins_config* cfg, levins_ctx** 
         return LEVINS_ERR_ARG;
     }
     ctx->consts = make_consts(ctx->cfg);
+    ctx->num_sms = prop.multiProcessorCount;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(&ctx->pinned, 1 << 20) != cudaSuccess) {
         delete ctx;
@@ -536,26 +596,27 @@ extern "C" int levins_build_range_image(levins_ctx* ctx, const levins_point_xyzi
     const PointXYZI* dcloud = nullptr;
     if (cloud) { // explicit cloud: re-bin from scratch
         if (n > 0xffffffffull) return fail(ctx, LEVINS_ERR_ARG, "cloud too large");
-        if (ctx->s_image_from_raw) { // discard the pending fused z-buffer
-            r = fill_zbuf(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS);
-            if (r) return r;
-            ctx->s_image_from_raw = false;
-        }
+        if (n >= MAX_POINTS_PER_KEYFRAME) return fail(ctx, LEVINS_ERR_CAPACITY, "more than 2^25 points in one cloud");
+        ctx->s_image_from_raw = false;
+        r = next_gen(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS, &ctx->s_gen); // a new, empty image
+        if (r) return r;
         CU(ctx->s_in_cloud.ensure(std::max<size_t>(n, 1) * sizeof(PointXYZI)));
         if (n) CU(cudaMemcpyAsync(ctx->s_in_cloud.p, cloud, n * sizeof(PointXYZI), cudaMemcpyHostToDevice, ctx->stream));
         dcloud = ctx->s_in_cloud.as<PointXYZI>();
-        if (n) {
-            const unsigned grid = (unsigned) ((n + 255) / 256);
-            if (ctx->consts.libm_mode == 0)
-                k_bin_cloud<0><<<grid, 256, 0, ctx->stream>>>(dcloud, (unsigned) n, ctx->s_zbuf.as<unsigned long long>(), ctx->consts);
-            else
-                k_bin_cloud<1><<<grid, 256, 0, ctx->stream>>>(dcloud, (unsigned) n, ctx->s_zbuf.as<unsigned long long>(), ctx->consts);
-            ctx->launches++;
-            CU(cudaGetLastError());
-        }
         KfState kf{};
         memcpy(ctx->pinned, &kf, sizeof(kf));
         CU(cudaMemcpyAsync(ctx->s_kf.p, ctx->pinned, sizeof(kf), cudaMemcpyHostToDevice, ctx->stream));
+        if (n) {
+            const unsigned grid = (unsigned) ((n + 255) / 256);
+            if (ctx->consts.libm_mode == 0)
+                k_bin_cloud<0><<<grid, 256, 0, ctx->stream>>>(dcloud, (unsigned) n, ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen,
+                                                                 ctx->s_kf.as<KfState>(), ctx->consts);
+            else
+                k_bin_cloud<1><<<grid, 256, 0, ctx->stream>>>(dcloud, (unsigned) n, ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen,
+                                                                 ctx->s_kf.as<KfState>(), ctx->consts);
+            ctx->launches++;
+            CU(cudaGetLastError());
+        }
         r = run_finalize_stream(ctx, true, dcloud, true);
         if (r) return r;
     } else {
@@ -602,7 +663,7 @@ extern "C" int levins_associate(levins_ctx* ctx, const float* query_xyz, size_t 
     memcpy(ctx->pinned, qc, sizeof(qc));
     CU(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->s_kf.p) + offsetof(KfState, q_begin), ctx->pinned, sizeof(qc),
                        cudaMemcpyHostToDevice, ctx->stream));
-    r = run_associate_stream(ctx, nf, true);
+    r = run_associate_stream(ctx, nf, true, false);
     if (r) return r;
     if (type) CU(cudaMemcpyAsync(type, ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
     if (xyz_depth) CU(cudaMemcpyAsync(xyz_depth, ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -626,11 +687,7 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
     ctx->s_image_valid = false;
     int r = ensure_stream_buffers(ctx, n_ins, nf);
     if (r) return r;
-    if (ctx->s_image_from_raw) { // a stack_deskew result was never consumed: clear its z-buffer
-        r = fill_zbuf(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS);
-        if (r) return r;
-        ctx->s_image_from_raw = false;
-    }
+    ctx->s_image_from_raw = false;
     r = run_stage1(ctx, stamp, ins, n_ins, /*write_cloud=*/false, /*bin=*/true);
     if (r == LEVINS_EMPTY) {
         for (size_t k = 0; k < nf; k++) {
@@ -650,10 +707,8 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
         CU(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->s_kf.p) + offsetof(KfState, q_begin),
                            reinterpret_cast<char*>(ctx->pinned) + 512, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
     }
-    r = run_finalize_stream(ctx, false, nullptr, false);
-    if (r) return r;
     if (nf) {
-        r = run_associate_stream(ctx, nf, false);
+        r = run_associate_stream(ctx, nf, false, true);
         if (r) return r;
         if (type) CU(cudaMemcpyAsync(type, ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
         if (xyz_depth) CU(cudaMemcpyAsync(xyz_depth, ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -663,12 +718,8 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
     if (r) return r;
     if (n_projected_out) *n_projected_out = kf.n_proj;
     if (m_out) *m_out = kf.m;
-    ctx->s_image_valid = kf.m > 0;
-    // no compact-index map was built for this image; levins_associate needs one
-    if (ctx->s_image_valid) {
-        k_compact<<<1, 1024, 0, ctx->stream>>>(ctx->s_cells.as<float4>(), ctx->s_c2c.as<int32_t>(), nullptr);
-        ctx->launches++;
-    }
+    // the fused path keeps no cell array: a later levins_associate() needs levins_build_range_image() first
+    ctx->s_image_valid = false;
     return (kf.status || kf.m == 0) ? LEVINS_EMPTY : LEVINS_OK;
 }
 
@@ -716,7 +767,7 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
     for (size_t k = 0; k < n_kf; k++) {
         const levins_keyframe_desc& d = descs[k];
         if (d.pt_begin + d.pt_count > n_points || d.ins_begin + d.ins_count > n_ins || d.q_begin + d.q_count > n_queries ||
-            d.ins_count == 0 || d.pt_count > 0xffffffffull)
+            d.ins_count == 0 || d.pt_count >= MAX_POINTS_PER_KEYFRAME)
             return fail(ctx, LEVINS_ERR_ARG, "keyframe descriptor out of range");
         KfState s{};
         s.pt_begin = d.pt_begin;
@@ -770,9 +821,7 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
     const int wave = (int) std::min<size_t>(ctx->b_wave, n_kf);
     if (ctx->b_wave_alloc < wave) {
         CU(ctx->b_zbuf.ensure((size_t) wave * CELLS * 8));
-        CU(ctx->b_cells.ensure((size_t) wave * CELLS * sizeof(float4)));
-        int r = fill_zbuf(ctx, ctx->b_zbuf.as<unsigned long long>(), (size_t) wave * CELLS);
-        if (r) return r;
+        ctx->b_gen = 255; // fresh memory: force a clear at the first generation
         ctx->b_wave_alloc = wave;
     }
     size_t ev = 0;
@@ -810,6 +859,9 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             max_pts = std::max<uint64_t>(max_pts, ctx->b_descs[k0 + i].pt_count);
             max_q = std::max<uint64_t>(max_q, ctx->b_descs[k0 + i].q_count);
         }
+        // every wave is a new z-buffer generation: the slots are reused without being cleared
+        int r = next_gen(ctx, ctx->b_zbuf.as<unsigned long long>(), (size_t) ctx->b_wave_alloc * CELLS, &ctx->b_gen);
+        if (r) return r;
         DeskewArgs da{};
         da.kfs = ctx->b_kfs.as<KfState>() + k0;
         da.pts = ctx->b_pts.as<PointXYZIT>();
@@ -817,37 +869,27 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         da.table = ctx->b_table.as<Interval>();
         da.zbuf = ctx->b_zbuf.as<unsigned long long>();
         da.cloud_out = nullptr;
+        da.gen = ctx->b_gen;
         da.ext = ctx->ext;
         da.c = ctx->consts;
         if (max_pts) {
-            dim3 grid((unsigned) ((max_pts + DESKEW_THREADS - 1) / DESKEW_THREADS), nw);
             mark(1, true);
-            launch_deskew(ctx, grid, da, false);
+            r = launch_deskew(ctx, da, max_pts, (unsigned) nw, false);
             mark(1, false);
-            CU(cudaGetLastError());
+            if (r) return r;
         }
-        FinalizeArgs fa{};
-        fa.kfs = ctx->b_kfs.as<KfState>() + k0;
-        fa.pts = ctx->b_pts.as<PointXYZIT>();
-        fa.pts_cap = ~0ull;
-        fa.table = ctx->b_table.as<Interval>();
-        fa.cloud = nullptr;
-        fa.zbuf = ctx->b_zbuf.as<unsigned long long>();
-        fa.cells = ctx->b_cells.as<float4>();
-        fa.winner = nullptr;
-        fa.ext = ctx->ext;
-        fa.c = ctx->consts;
-        mark(2, true);
-        k_finalize<false><<<dim3((CELLS + FINALIZE_THREADS - 1) / FINALIZE_THREADS, nw), FINALIZE_THREADS, 0, ctx->stream>>>(fa);
-        mark(2, false);
-        ctx->launches++;
-        CU(cudaGetLastError());
         if (max_q) {
             AssocArgs aa{};
             aa.kfs = ctx->b_kfs.as<KfState>() + k0;
             aa.queries = ctx->b_queries.as<float>();
-            aa.cells = ctx->b_cells.as<float4>();
+            aa.cells = nullptr;
             aa.c2c = nullptr;
+            aa.zbuf = ctx->b_zbuf.as<unsigned long long>();
+            aa.pts = ctx->b_pts.as<PointXYZIT>();
+            aa.pts_cap = ~0ull;
+            aa.table = ctx->b_table.as<Interval>();
+            aa.gen = ctx->b_gen;
+            aa.ext = ctx->ext;
             aa.type = ctx->b_type.as<int8_t>();
             aa.xyz_depth = ctx->b_xyzd.as<float4>();
             aa.flags = ctx->b_flags.as<int32_t>();
@@ -855,12 +897,21 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             aa.knn_d2 = nullptr;
             aa.c = ctx->consts;
             mark(3, true);
-            k_associate<<<dim3((unsigned) ((max_q + ASSOC_WARPS - 1) / ASSOC_WARPS), nw), ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
+            k_associate<true><<<dim3((unsigned) ((max_q + ASSOC_WARPS - 1) / ASSOC_WARPS), nw), ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
             mark(3, false);
             ctx->launches++;
             CU(cudaGetLastError());
         }
     }
+    return LEVINS_OK;
+}
+
+extern "C" int levins_batch_result_pointers(levins_ctx* ctx, void** type, void** xyz_depth, void** flags) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    if (!ctx->b_valid) return fail(ctx, LEVINS_ERR_STATE, "no batch");
+    if (type) *type = ctx->b_type.p;
+    if (xyz_depth) *xyz_depth = ctx->b_xyzd.p;
+    if (flags) *flags = ctx->b_flags.p;
     return LEVINS_OK;
 }
 

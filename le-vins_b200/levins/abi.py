@@ -26,7 +26,7 @@ EXPORTS = [
     "levins_buffer_info", "levins_buffer_clear", "levins_stack_deskew", "levins_build_range_image", "levins_associate",
     "levins_keyframe", "levins_point_cloud_projection", "levins_batch_upload", "levins_batch_run",
     "levins_batch_download", "levins_batch_set_wave", "levins_set_profiling", "levins_batch_kernel_ms",
-    "levins_launch_count",
+    "levins_launch_count", "levins_batch_result_pointers",
 ]
 
 
@@ -80,6 +80,7 @@ def lib():
             "levins_batch_run": [vp],
             "levins_batch_download": [vp, vp, vp, vp, vp, vp],
             "levins_batch_set_wave": [vp, i32],
+            "levins_batch_result_pointers": [vp, vp, vp, vp],
             "levins_set_profiling": [vp, i32],
             "levins_batch_kernel_ms": [vp, vp, vp],
         }.items():
@@ -243,6 +244,11 @@ class Context:
                                                 _p(out.get("n_projected")), _p(out.get("m"))))
         return out
 
+    def batch_result_pointers(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(lib().levins_batch_result_pointers(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"type": a.value, "xyz_depth": b.value, "flags": c.value}
+
     def batch_kernel_ms(self):
         ms = np.zeros(4, np.float32)
         n = np.zeros(4, np.uint32)
@@ -261,3 +267,15 @@ def batch_descs(b) -> np.ndarray:
     d["q_count"] = f
     d["stamp"] = b.stamps
     return d
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ holder so that torch can view library-owned device memory (no copy)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(torch, ptr, shape, dtype, device_index):
+    typestr = {torch.float32: "<f4", torch.int8: "|i1", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_CudaArray(ptr, shape, typestr), device=torch.device("cuda", device_index))

@@ -213,3 +213,42 @@ def test_point_cloud_projection(ctx, oracle):
     got = ctx.point_cloud_projection(rig.pose_c_l, cloud)
     ref = oracle.point_cloud_projection(rig.pose_c_l, cloud)
     assert got.tobytes() == ref.tobytes()
+
+
+def _boundary_cloud(n, seed):
+    """Points whose row / col angles sit on (or within 1e-9 .. 1e-3 cell of) a cell rounding boundary."""
+    rng = np.random.default_rng(seed)
+    ang = 0.3 * np.pi / 180.0
+    row = rng.integers(-2, 302, n)
+    col = rng.integers(-2, 302, n)
+    mag = 10.0 ** rng.uniform(-9, -3, n) * rng.choice([-1.0, 0.0, 1.0], n)
+    mag2 = 10.0 ** rng.uniform(-9, -3, n) * rng.choice([-1.0, 0.0, 1.0], n)
+    on_row = rng.random(n) < 0.7
+    on_col = rng.random(n) < 0.7
+    el = (row + np.where(on_row, 0.5 + mag, rng.uniform(-0.5, 0.5, n))) * ang - np.pi / 4
+    az = (col + np.where(on_col, 0.5 + mag2, rng.uniform(-0.5, 0.5, n))) * ang + np.pi / 4
+    r = rng.uniform(1.0, 80.0, n)
+    cloud = np.zeros(n, synth.XYZI)
+    cloud["x"] = (r * np.cos(el) * np.cos(az)).astype(np.float32)
+    cloud["z"] = (r * np.cos(el) * np.sin(az)).astype(np.float32)
+    cloud["y"] = (r * np.sin(el)).astype(np.float32)
+    cloud["w"] = 1.0
+    return cloud
+
+
+@pytest.mark.parametrize("libm_mode", [0, 1])
+def test_cell_ids_on_rounding_boundaries(oracle, built_lib, libm_mode):
+    """The polynomial cell fast path + guarded exact path must give the oracle's cell for points that sit on the
+    rounding boundaries (where a 1e-7 rad error would flip the id), on the FOV edge and at the grid edge."""
+    c = abi.Context(0, libm_mode=libm_mode)
+    for seed in range(3):
+        cloud = _boundary_cloud(400_000, seed)
+        ref = oracle.range_image(cloud, libm_mode=libm_mode)
+        st, m, unit, winner = c.build_range_image(cloud)
+        diff = int(np.sum(winner != ref["winner"]))
+        if libm_mode == 0:
+            assert m == ref["m"] and diff == 0, f"{diff} cells differ"
+            assert unit.tobytes() == ref["unit_sphere"].tobytes()
+        else:  # CUDA's double atan2 is not glibc's; on-boundary points may legitimately fall either way
+            assert diff < 0.02 * ref["m"]
+    c.close()
