@@ -250,8 +250,9 @@ __device__ inline void state_pose(const InsSample& s, const double* Rbc, const d
 
 // ------------------------------------------------------------------------------------------------
 // fdlibm-lineage atanf / atan2f: the float overloads the reference's unqualified atan2 calls resolve to on
-// glibc (tracking.cc:317-320).  Same operation sequence as oracle/levins_oracle.c; no contraction (-fmad=false),
-// IEEE division.  Bit-identical to glibc 2.39's atan2f on 2e8 inputs (tests/test_oracle_math.py).
+// glibc (tracking.cc:317-320): glibc's sysdeps/ieee754/flt-32 algorithm, operation for operation; no contraction
+// (-fmad=false), IEEE division.  The CPU checker's copy of the same sequence is verified bit-identical to glibc 2.39's
+// atan2f on 2e7 inputs in tests/test_oracle.py, and this device copy against the checker in the GPU parity tests.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float atanf_fd(float x) {
     const float hi0 = 4.6364760399e-01f, hi1 = 7.8539812565e-01f, hi2 = 9.8279368877e-01f, hi3 = 1.5707962513e+00f;
@@ -606,7 +607,7 @@ __device__ __forceinline__ bool deskew_point(float x, float y, float z, double t
 }
 
 // ------------------------------------------------------------------------------------------------
-// Eigen::ColPivHouseholderQR<Matrix<double,5,3>> compute + solve, same sequence as the oracle
+// Eigen::ColPivHouseholderQR<Matrix<double,5,3>> compute + solve (Eigen >= 3.3 algorithm, LAPACK-style norm down-dating)
 // ------------------------------------------------------------------------------------------------
 __device__ inline void colpiv_qr_solve_5x3(const double (*P)[3], double* x) {
     constexpr int ROWS = 5, COLS = 3;

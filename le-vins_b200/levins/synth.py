@@ -181,6 +181,8 @@ def make_scene(rng, kind="hall"):
         if np.hypot(c[0], c[1]) < 4.0:  # keep the start area free
             c += 6.0 * np.sign(c + 1e-3)
         sx, sy, sz = rng.uniform(size[0], size[1], size=3)
+        if kind != "hall" and abs(c[1]) - sy / 2 < 3.0:  # street: keep the driving corridor |y| < 3 m free
+            c[1] = np.sign(c[1] + 1e-3) * (3.0 + sy / 2 + rng.uniform(0.0, 6.0))
         boxes.append(np.array([[c[0] - sx / 2, c[1] - sy / 2, hall[1, 2] - sz], [c[0] + sx / 2, c[1] + sy / 2, hall[1, 2]]]))
     return np.stack(boxes)  # (B, 2, 3)
 

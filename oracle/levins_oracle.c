@@ -522,6 +522,26 @@ float orc_atan2f_fdlibm(float y, float x) {
     }
 }
 
+/* compares the restatement with this machine's libm atan2f on n pseudo-random inputs (finite coordinates and raw
+ * bit patterns); returns the number of mismatching results (NaN == NaN). */
+long orc_atan2f_selfcheck(long n, unsigned long long seed) {
+    unsigned long long s = seed ? seed : 88172645463325252ULL;
+    long bad = 0;
+    for (long i = 0; i < n; i++) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        float y = (float) ((long long) (s & 0xffffff) - 0x800000) * (200.0f / 0x800000);
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        float x = (float) ((long long) (s & 0xffffff) - 0x800000) * (200.0f / 0x800000);
+        if (i % 7 == 0) {
+            x = i2f((int32_t) (s >> 20));
+            y = i2f((int32_t) (s >> 3));
+        }
+        float a = atan2f(y, x), b = orc_atan2f_fdlibm(y, x);
+        if (f2i(a) != f2i(b) && !(a != a && b != b)) bad++;
+    }
+    return bad;
+}
+
 /* ------------------------------------------------------------------------------------------
  * tracking.cc:298-358  Tracking::depthAssociationProjection  (binning + compaction)
  * ------------------------------------------------------------------------------------------ */

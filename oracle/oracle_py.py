@@ -94,6 +94,8 @@ def lib():
         L.orc_is_good_depth.argtypes = [dbl, dbl]
         L.orc_atan2f_fdlibm.restype = C.c_float
         L.orc_atan2f_fdlibm.argtypes = [C.c_float, C.c_float]
+        L.orc_atan2f_selfcheck.restype = C.c_long
+        L.orc_atan2f_selfcheck.argtypes = [C.c_long, C.c_ulonglong]
         L.orc_keyframe.restype = sz
         L.orc_keyframe.argtypes = [vp, sz, dbl, dbl, vp, sz, vp, vp, dbl, vp, sz, i32, i32, vp, vp, vp]
         L.orc_max_threads.restype = i32
@@ -341,6 +343,10 @@ def is_good_depth(depth, scale=1.0) -> bool:
 
 def atan2f_fdlibm(y, x) -> float:
     return float(lib().orc_atan2f_fdlibm(float(y), float(x)))
+
+
+def atan2f_selfcheck(n, seed=0) -> int:
+    return int(lib().orc_atan2f_selfcheck(int(n), int(seed)))
 
 
 def keyframe(points, stamp, ins, pose_b_c, pose_c_l, td_b_l, queries, stack_interval=0.5, libm_mode=LIBM_FLOAT,

@@ -1,0 +1,74 @@
+"""Golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle).
+
+CPU: the oracle still reproduces every stage output bit for bit (pins the restatement; the reference ships no
+golden vectors of its own).  GPU: the CUDA path reproduces the fixture without the oracle in the loop.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from levins import synth
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+assert GOLDEN, "golden fixtures missing"
+
+
+def _load(path):
+    d = np.load(path)
+    return {k: d[k] for k in d.files}
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_golden(oracle, path):
+    g = _load(path)
+    s1 = oracle.stack_deskew(g["points"], float(g["stamp"]), g["ins"], g["pose_b_c"], g["pose_c_l"], float(g["td_b_l"]),
+                             float(g["stack_interval"]), details=True)
+    assert s1["first"] == int(g["first"]) and s1["n"] == int(g["n"])
+    assert s1["cloud"].tobytes() == g["cloud"].tobytes()
+    assert np.array_equal(s1["kept"], g["kept"]) and np.array_equal(s1["ins_index"], g["ins_index"])
+    s2 = oracle.range_image(s1["cloud"])
+    assert s2["m"] == int(g["m"]) and np.array_equal(s2["winner"], g["winner"])
+    assert s2["unit_sphere"].tobytes() == g["unit_sphere"].tobytes()
+    s3 = oracle.associate(s2["unit_sphere"], g["queries"], use_kdtree=True)
+    for k in ("type", "xyz_depth", "knn_idx", "knn_d2", "flags"):
+        assert np.array_equal(s3[k], g[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_gpu_reproduces_golden(built_lib, path):
+    from levins import abi
+
+    g = _load(path)
+    c = abi.Context(0, stack_interval=float(g["stack_interval"]))
+    c.set_extrinsics(g["pose_b_c"], g["pose_c_l"], float(g["td_b_l"]))
+    c.append_scan(g["points"])
+    st, n, cloud = c.stack_deskew(float(g["stamp"]), g["ins"])
+    assert n == int(g["n"]) and c.buffer_info()[0] == len(g["points"]) - int(g["first"])
+    kept = g["kept"].astype(bool)
+    a = np.stack([cloud["x"], cloud["y"], cloud["z"]], -1)
+    b = np.stack([g["cloud"]["x"], g["cloud"]["y"], g["cloud"]["z"]], -1)
+    assert np.array_equal(np.any(a != 0, axis=1), kept)
+    err = np.linalg.norm(a[kept].astype(np.float64) - b[kept], axis=1) / np.linalg.norm(b[kept].astype(np.float64), axis=1)
+    assert err.max() <= 1e-4  # north_star tolerance for deskewed coordinates
+    st, m, unit, winner = c.build_range_image(g["cloud"])  # stage 2 on the fixture's cloud: bit-exact
+    assert m == int(g["m"]) and np.array_equal(winner, g["winner"]) and unit.tobytes() == g["unit_sphere"].tobytes()
+    got = c.associate(g["queries"])  # stage 3 on the fixture's image: decisions and depths bit-exact
+    assert np.array_equal(got["type"], g["type"])
+    assert got["xyz_depth"].tobytes() == g["xyz_depth"].tobytes()
+    ok = (g["flags"] & 3) == 0
+    assert np.array_equal(got["knn_idx"][ok], g["knn_idx"][ok]) and np.array_equal(got["knn_d2"][ok], g["knn_d2"][ok])
+    # fused keyframe end to end
+    c2 = abi.Context(0, stack_interval=float(g["stack_interval"]))
+    c2.set_extrinsics(g["pose_b_c"], g["pose_c_l"], float(g["td_b_l"]))
+    c2.append_scan(g["points"])
+    f = c2.keyframe(float(g["stamp"]), g["ins"], g["queries"])
+    assert f["n_projected"] == int(g["n"]) and f["m"] == int(g["m"])
+    assert np.mean(f["type"] == g["type"]) >= 0.95
+    both = (f["type"] == 1) & (g["type"] == 1)
+    if both.any():
+        assert np.max(np.abs(f["xyz_depth"][both, 3] - g["xyz_depth"][both, 3]) / g["xyz_depth"][both, 3]) <= 1e-4
+    c.close()
+    c2.close()
