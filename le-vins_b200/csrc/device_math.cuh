@@ -438,32 +438,29 @@ __device__ __forceinline__ bool outside_fov(float x, float y, float z) {
     return (z < 0.f) || (fabsf(x) - az >= lim) || (fabsf(y) - az >= lim);
 }
 
-// returns the cell id or -1; sets `ambiguous` when the exact path must decide
+// returns the cell id or -1; sets `ambiguous` when the exact path must decide.  Straight-line code (no early exits) so
+// that several points per thread interleave; rounding uses the 1.5 * 2^23 magic constant instead of FRND / F2I.
 __device__ __forceinline__ int cell_of_point_fast(float x, float y, float z, const Consts& c, bool& ambiguous) {
-    ambiguous = false;
-    if (z < 0.f) return -1;
-    if (!(z > 1e-30f)) { // zero / denormal-range z: |z| 2^-25 may be inexact, leave it to the exact path
-        ambiguous = true;
-        return -1;
-    }
-    if (outside_fov(x, y, z)) return -1;
+    const bool behind = z < 0.f;
+    const bool tiny = !(z > 1e-30f); // zero / denormal-range z: |z| 2^-25 may be inexact, leave it to the exact path
+    const bool outside = outside_fov(x, y, z);
     // col_angle / ANGLE = (atan2(z, x) - pi/4) / ANGLE = 150 - atan(x / z) / ANGLE
-    float rz = __frcp_rn(z);
+    const float rz = __frcp_rn(z);
     const float tc = x * rz;
     const float qc = fmaf(-atan_poly(tc), c.inv_angle_f, 150.0f);
     // row_angle / ANGLE = (atan2(y, sqrt(x^2 + z^2)) + pi/4) / ANGLE = 150 + atan(y / sqrt(x^2 + z^2)) / ANGLE
     const float s = fmaf(x, x, z * z);
     const float tr = y * rsqrtf(s);
     const float qr = fmaf(atan_poly(tr), c.inv_angle_f, 150.0f);
-    const float rc = rintf(qc), rr = rintf(qr);
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23: (q + MAGIC) - MAGIC = rint(q) for |q| < 2^22
+    const float mc = qc + MAGIC, mr = qr + MAGIC;
+    const float rc = mc - MAGIC, rr = mr - MAGIC;
+    const int col = __float_as_int(mc) - 0x4B400000, row = __float_as_int(mr) - 0x4B400000;
     const float edge = 0.5f - c.cell_guard;
-    if (fabsf(qc - rc) > edge || fabsf(qr - rr) > edge) {
-        ambiguous = true;
-        return -1;
-    }
-    const int col = (int) rc, row = (int) rr;
-    if ((row < 0) || (col < 0) || (row >= IMG) || (col >= IMG)) return -1;
-    return col + row * IMG;
+    const bool near_edge = (fabsf(qc - rc) > edge) || (fabsf(qr - rr) > edge);
+    const bool in_grid = ((unsigned) row < (unsigned) IMG) && ((unsigned) col < (unsigned) IMG);
+    ambiguous = !behind && (tiny || (!outside && near_edge));
+    return (behind || tiny || outside || near_edge || !in_grid) ? -1 : col + row * IMG;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,6 +510,18 @@ __device__ __forceinline__ void load_entry(const Interval* __restrict__ it, Entr
     e.A0 = v2.x; e.A1 = v2.y; e.A2 = v3.x; e.A3 = v3.y; e.A4 = v4.x; e.A5 = v4.y; e.A6 = v5.x; e.A7 = v5.y; e.A8 = v6.x;
     e.kx = v6.y; e.ky = v7.x; e.kz = v7.y; e.theta = v8.x;
     e.c0x = v8.y; e.c0y = v9.x; e.c0z = v9.y; e.c1x = v10.x; e.c1y = v10.y; e.c1z = v11.x;
+}
+
+// does the cached entry `cur` serve time t?  (entry 0 = out-of-window fallback, misc.cc:28-30, 74-77)
+__device__ __forceinline__ bool entry_serves(const KfView& kv, const EntryRegs& e, int cur, double t) {
+    if (cur > 0) {
+        // GPS seconds of week are positive: IEEE doubles then order like their bit patterns (integer compares run on
+        // the ALU pipe instead of the busier FP64 pipe); negative or NaN times simply miss and take the slow path
+        const long long ti = __double_as_longlong(t);
+        return (__double_as_longlong(e.t_lo) <= ti) && (ti < __double_as_longlong(e.t_hi)) && (ti > 0);
+    }
+    const bool out_of_window = (kv.n_ins < 2) || (kv.t0 > t) || (kv.t_last <= t);
+    return cur == 0 && out_of_window;
 }
 
 // Make `e` the entry for time t (misc.cc:25-60 semantics).  Fast when e already brackets t.
@@ -566,8 +575,21 @@ __device__ __forceinline__ void sin_omc(double phi, double& sn, double& omc) {
     }
 }
 
+// tier-1 polynomials only (|phi| < 2^-6), straight-line: the caller checks theta of the interval once
+__device__ __forceinline__ void sin_omc_small(double phi, double& sn, double& omc) {
+    const double p2 = phi * phi;
+    double a = fma(p2, -1.0 / 5040.0, 1.0 / 120.0);
+    a = fma(p2, a, -1.0 / 6.0);
+    sn = fma(phi * p2, a, phi);
+    double b = fma(p2, -1.0 / 40320.0, 1.0 / 720.0);
+    b = fma(p2, b, -1.0 / 24.0);
+    b = fma(p2, b, 0.5);
+    omc = p2 * b;
+}
+
 // Deskew one raw point into the keyframe's camera frame (le_vins.cc:455-461) with the entry in registers.
 // The two f32 roundings of pointcloud.cc:68 are kept.
+template <bool SMALL_ANGLE = false>
 __device__ __forceinline__ void deskew_core(float x, float y, float z, double t, const EntryRegs& e, const Extrinsics& ex,
                                             float& ox, float& oy, float& oz) {
     // p_c1 = f32(R_cl p + t_cl)   (pointcloud.cc:38 -> 68, first rounding)
@@ -582,7 +604,10 @@ __device__ __forceinline__ void deskew_core(float x, float y, float z, double t,
     const double uz = fma(ex.Rbc[8], az, fma(ex.Rbc[5], ay, fma(ex.Rbc[2], ax, ex.tbc[2])));
     const double s = (t - e.ts0) * e.inv_dts;
     double sn, omc;
-    sin_omc(-s * e.theta, sn, omc);
+    if (SMALL_ANGLE)
+        sin_omc_small(-s * e.theta, sn, omc);
+    else
+        sin_omc(-s * e.theta, sn, omc);
     // w = u + sin * (k x u) + (1 - cos) * k x (k x u)
     const double cx = fma(e.ky, uz, -(e.kz * uy)), cy = fma(e.kz, ux, -(e.kx * uz)), cz = fma(e.kx, uy, -(e.ky * ux));
     const double dx = fma(e.ky, cz, -(e.kz * cy)), dy = fma(e.kz, cx, -(e.kx * cz)), dz = fma(e.kx, cy, -(e.ky * cx));
@@ -602,7 +627,7 @@ __device__ __forceinline__ bool deskew_point(float x, float y, float z, double t
     if ((n2 > c.n2_far) || (n2 < c.n2_near)) return false;
     const double t = time + ex.td_b_l;
     seek_entry(kv, t, e, cur);
-    deskew_core(x, y, z, t, e, ex, ox, oy, oz);
+    deskew_core<false>(x, y, z, t, e, ex, ox, oy, oz);
     return true;
 }
 

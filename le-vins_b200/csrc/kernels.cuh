@@ -226,6 +226,7 @@ constexpr int TILE_PTS = DESKEW_THREADS * DESKEW_PPT; // 1024 points = 32 KB
 constexpr int TILE_BYTES = TILE_PTS * 32;
 constexpr int DESKEW_STAGES = 3;
 constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 64;
+constexpr int DESKEW_BLOCK = DESKEW_THREADS; // 8 warps; lane 0 of warp 0 doubles as the TMA producer
 constexpr int DESKEW_PTS_PER_BLOCK = TILE_PTS;
 
 struct DeskewArgs {
@@ -250,6 +251,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned coun
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
     asm volatile(
@@ -281,16 +285,6 @@ __device__ __forceinline__ KfView kf_view(const KfState* __restrict__ kf, const 
     return kv;
 }
 
-// Returns true when this key is the first of the current generation in its cell (exactly one thread per cell sees that).
-__device__ __forceinline__ bool zbuf_min(unsigned long long* cell, unsigned long long key, unsigned gen) {
-    // most points lose: filter with a plain L2 read first (a stale value is only ever larger, so no update is missed)
-    if (key < __ldcg(cell)) {
-        const unsigned long long old = atomicMin(cell, key);
-        return !key_live(old, gen);
-    }
-    return false;
-}
-
 template <int LIBM_MODE>
 __device__ __noinline__ int cell_of_point_exact(float x, float y, float z, const Consts& c) {
     return cell_of_point<LIBM_MODE>(x, y, z, c);
@@ -306,26 +300,32 @@ __device__ __forceinline__ int cell_id(float x, float y, float z, const Consts& 
 }
 
 template <int LIBM_MODE, bool WRITE_CLOUD>
-__global__ void __launch_bounds__(DESKEW_THREADS, 2) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
+__global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + DESKEW_STAGES * TILE_BYTES);
+    unsigned long long* empty = full + DESKEW_STAGES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     const unsigned total = a.n_kf * a.tiles_per_kf;
-    const unsigned per = (total + gridDim.x - 1) / gridDim.x;
-    const unsigned t_begin = blockIdx.x * per;
-    const unsigned t_end = min(t_begin + per, total);
+    // even contiguous split: every CTA gets floor or ceil of total / gridDim.x tiles
+    const unsigned t_begin = (unsigned) (((unsigned long long) blockIdx.x * total) / gridDim.x);
+    const unsigned t_end = (unsigned) (((unsigned long long) (blockIdx.x + 1) * total) / gridDim.x);
     if (t_begin >= t_end) return;
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < DESKEW_STAGES; s++) mbar_init(full + s, 1);
+        for (int s = 0; s < DESKEW_STAGES; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, DESKEW_THREADS / 32); // one arrival per consumer warp
+        }
         mbar_fence_init();
     }
     __syncthreads();
 
-    // producer (thread 0): start the copy of tile t into stage s
-    auto issue = [&](unsigned t, int s) {
+    // producer duty (thread 0): tile t goes into stage (t - t_begin) % STAGES once all 8 warps have released that stage
+    auto issue = [&](unsigned t, unsigned it_t) {
+        const int s = it_t % DESKEW_STAGES;
+        if (it_t >= DESKEW_STAGES) mbar_wait(empty + s, ((it_t / DESKEW_STAGES) - 1) & 1);
         const KfState* kf = a.kfs + t / a.tiles_per_kf;
         const unsigned off = (t % a.tiles_per_kf) * TILE_PTS;
         const unsigned n = kf->n_proj;
@@ -346,26 +346,41 @@ __global__ void __launch_bounds__(DESKEW_THREADS, 2) k_deskew_bin(const __grid_c
             if (t_begin + i < t_end) issue(t_begin + i, i);
     }
 
+    // ---- consumer warps ----
     EntryRegs e;
     int cur = -1;
     unsigned cur_kf = 0xffffffffu;
     KfView kv{};
     unsigned n = 0;
-    unsigned first_fills = 0;
+    // The z-buffer phase of a tile is split over two iterations so that no warp ever waits on an L2 round trip:
+    // the probes (plain L2 reads) are issued at the end of the iteration that computed the keys, and compared
+    // one tile later, when they have long arrived; winners are sent as fire-and-forget RED.MIN (no return value).
+    unsigned long long pkey[DESKEW_PPT], pseen[DESKEW_PPT];
+    int pcell[DESKEW_PPT];
+    unsigned long long* pzb = a.zbuf;
+#pragma unroll
+    for (int j = 0; j < DESKEW_PPT; j++) {
+        pcell[j] = -1;
+        pkey[j] = 0;
+        pseen[j] = 0;
+    }
+    auto flush_pending = [&]() {
+#pragma unroll
+        for (int j = 0; j < DESKEW_PPT; j++) {
+            if (pcell[j] >= 0 && pkey[j] < pseen[j]) atomicMin(pzb + pcell[j], pkey[j]); // result unused -> RED
+            pcell[j] = -1;
+        }
+    };
 
     unsigned it = 0;
     for (unsigned t = t_begin; t < t_end; ++t, ++it) {
         const int s = it % DESKEW_STAGES;
-        if (tid == 0 && t + DESKEW_STAGES - 1 < t_end) issue(t + DESKEW_STAGES - 1, (it + DESKEW_STAGES - 1) % DESKEW_STAGES);
-
+        // keep the ring full: the stage freed by iteration it-1 takes tile t+STAGES-1.  Only warp 0 can wait here (for the
+        // other warps to release that stage); the other warps run on, up to a full tile ahead of it.
+        if (tid == 0 && t + DESKEW_STAGES - 1 < t_end) issue(t + DESKEW_STAGES - 1, it + DESKEW_STAGES - 1);
         const unsigned kfi = t / a.tiles_per_kf;
         KfState* __restrict__ kf = a.kfs + kfi;
-        if (kfi != cur_kf) { // new keyframe: flush the fill count, reload the view, drop the cached interval
-            if (cur_kf != 0xffffffffu) {
-                first_fills = __reduce_add_sync(0xffffffffu, first_fills);
-                if (lane == 0 && first_fills) atomicAdd(&a.kfs[cur_kf].m, first_fills);
-                first_fills = 0;
-            }
+        if (kfi != cur_kf) { // new keyframe: reload the view, drop the cached interval
             cur_kf = kfi;
             kv = kf_view(kf, a.table);
             n = kf->n_proj;
@@ -378,70 +393,119 @@ __global__ void __launch_bounds__(DESKEW_THREADS, 2) k_deskew_bin(const __grid_c
 
         if (cnt) {
             const float4* __restrict__ sp = reinterpret_cast<const float4*>(smem_raw + s * TILE_BYTES);
-            unsigned long long key[DESKEW_PPT];
-            int cell[DESKEW_PPT];
+            const unsigned i0 = tid * DESKEW_PPT; // 4 consecutive points per thread
+            float px[DESKEW_PPT], py[DESKEW_PPT], pz[DESKEW_PPT];
+            double tt[DESKEW_PPT];
+            bool kept[DESKEW_PPT];
+            bool any_kept = false;
 #pragma unroll
             for (int j = 0; j < DESKEW_PPT; j++) {
-                const unsigned i = warp * (DESKEW_PPT * 32) + j * 32 + lane;
-                cell[j] = -1;
-                key[j] = 0;
-                if (i < cnt) {
-                    const float4 xyz = sp[2 * i];
-                    const double tm = reinterpret_cast<const double2*>(sp)[2 * i + 1].y;
-                    const unsigned k = off + i;
-                    float ox, oy, oz;
-                    const bool kept = deskew_point(xyz.x, xyz.y, xyz.z, tm, kv, a.ext, a.c, e, cur, ox, oy, oz);
-                    if (WRITE_CLOUD) {
-                        float4* out = reinterpret_cast<float4*>(a.cloud_out + k);
-                        out[0] = kept ? make_float4(ox, oy, oz, 1.0f) : make_float4(0.f, 0.f, 0.f, 1.0f); // resize() default (le_vins.cc:438)
-                        out[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    if (kept) { // a default point lands at col = -150 and is dropped at tracking.cc:326-328
-                        const int cid = cell_id<LIBM_MODE>(ox, oy, oz, a.c);
-                        if (cid >= 0) {
-                            const float range = sqrtf(v3f_sqnorm(ox, oy, oz)); // tracking.cc:330
-                            if (range < FLT_MAX) {                             // tracking.cc:332 against the FLT_MAX initial value
-                                cell[j] = cid;
-                                key[j] = key_make(a.gen, range, k);
-                            }
+                const float4 xyz = sp[2 * (i0 + j)];
+                const double tm = reinterpret_cast<const double2*>(sp)[2 * (i0 + j) + 1].y;
+                px[j] = xyz.x;
+                py[j] = xyz.y;
+                pz[j] = xyz.z;
+                tt[j] = tm + a.ext.td_b_l; // le_vins.cc:455
+                const float n2 = v3f_sqnorm(xyz.x, xyz.y, xyz.z);
+                kept[j] = (i0 + j < cnt) && !((n2 > a.c.n2_far) || (n2 < a.c.n2_near)); // le_vins.cc:447-451
+                any_kept |= kept[j];
+            }
+            float ox[DESKEW_PPT], oy[DESKEW_PPT], oz[DESKEW_PPT];
+            if (any_kept) {
+                // one interval entry for all kept points of this thread?  (checked, not assumed)
+                bool all = true;
+#pragma unroll
+                for (int j = 0; j < DESKEW_PPT; j++) all &= !kept[j] || entry_serves(kv, e, cur, tt[j]);
+                if (!all) {
+                    bool sought = false;
+#pragma unroll
+                    for (int j = 0; j < DESKEW_PPT; j++)
+                        if (kept[j] && !sought) {
+                            seek_entry(kv, tt[j], e, cur);
+                            sought = true;
                         }
-                    }
+                    all = true;
+#pragma unroll
+                    for (int j = 0; j < DESKEW_PPT; j++) all &= !kept[j] || entry_serves(kv, e, cur, tt[j]);
+                }
+                if (all && e.theta * e.theta < 2.44140625e-4) {
+                    // common case: straight-line code, the 4 points interleave
+#pragma unroll
+                    for (int j = 0; j < DESKEW_PPT; j++) deskew_core<true>(px[j], py[j], pz[j], tt[j], e, a.ext, ox[j], oy[j], oz[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < DESKEW_PPT; j++)
+                        if (kept[j]) {
+                            seek_entry(kv, tt[j], e, cur);
+                            float x, y, z;
+                            deskew_core<false>(px[j], py[j], pz[j], tt[j], e, a.ext, x, y, z);
+                            ox[j] = x;
+                            oy[j] = y;
+                            oz[j] = z;
+                        }
                 }
             }
-            // z-buffer: probe the 4 cells together (independent L2 reads), then the few atomics that can still win
-            unsigned long long* __restrict__ zb = a.zbuf + (size_t) kfi * CELLS;
-            unsigned long long seen[DESKEW_PPT];
+            if (WRITE_CLOUD) {
 #pragma unroll
-            for (int j = 0; j < DESKEW_PPT; j++) seen[j] = cell[j] >= 0 ? __ldcg(zb + cell[j]) : 0ull;
+                for (int j = 0; j < DESKEW_PPT; j++)
+                    if (i0 + j < cnt) {
+                        float4* out = reinterpret_cast<float4*>(a.cloud_out + off + i0 + j);
+                        out[0] = kept[j] ? make_float4(ox[j], oy[j], oz[j], 1.0f) : make_float4(0.f, 0.f, 0.f, 1.0f); // resize() default (le_vins.cc:438)
+                        out[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+            }
+            // stage 2: cell ids (a default point lands at col = -150 and is dropped at tracking.cc:326-328)
+            unsigned long long key[DESKEW_PPT];
+            int cell[DESKEW_PPT];
+            bool amb_any = false;
+            bool amb[DESKEW_PPT];
 #pragma unroll
-            for (int j = 0; j < DESKEW_PPT; j++)
-                if (cell[j] >= 0 && key[j] < seen[j]) {
-                    const unsigned long long old = atomicMin(zb + cell[j], key[j]);
-                    first_fills += !key_live(old, a.gen);
-                }
+            for (int j = 0; j < DESKEW_PPT; j++) {
+                cell[j] = cell_of_point_fast(ox[j], oy[j], oz[j], a.c, amb[j]);
+                amb[j] = amb[j] && kept[j];
+                amb_any |= amb[j];
+            }
+            if (amb_any) {
+#pragma unroll
+                for (int j = 0; j < DESKEW_PPT; j++)
+                    if (amb[j]) cell[j] = cell_of_point_exact<LIBM_MODE>(ox[j], oy[j], oz[j], a.c);
+            }
+#pragma unroll
+            for (int j = 0; j < DESKEW_PPT; j++) {
+                const float range = sqrtf(v3f_sqnorm(ox[j], oy[j], oz[j])); // tracking.cc:330
+                if (!kept[j] || !(range < FLT_MAX)) cell[j] = -1;            // tracking.cc:332 against the FLT_MAX initial value
+                key[j] = key_make(a.gen, range, off + i0 + j);
+            }
+            // z-buffer: settle the previous tile (its probes have arrived), then probe this tile's cells
+            flush_pending();
+            pzb = a.zbuf + (size_t) kfi * CELLS;
+#pragma unroll
+            for (int j = 0; j < DESKEW_PPT; j++) {
+                pcell[j] = cell[j];
+                pkey[j] = key[j];
+                pseen[j] = cell[j] >= 0 ? __ldcg(pzb + cell[j]) : 0ull;
+            }
         }
-        __syncthreads(); // every thread is done with stage s before it is refilled (next iteration's issue)
+        // this warp is done reading stage s: let the producer refill it (no block-wide barrier, warps run decoupled)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
     }
-    first_fills = __reduce_add_sync(0xffffffffu, first_fills);
-    if (lane == 0 && first_fills) atomicAdd(&a.kfs[cur_kf].m, first_fills);
+    flush_pending();
 }
 
 // explicit-cloud binning for levins_build_range_image(cloud != NULL)
 template <int LIBM_MODE>
 __global__ void __launch_bounds__(256) k_bin_cloud(const PointXYZI* __restrict__ cloud, unsigned n, unsigned long long* zbuf,
-                                                   unsigned gen, KfState* kf, const __grid_constant__ Consts c) {
+                                                   unsigned gen, const __grid_constant__ Consts c) {
     const unsigned k = blockIdx.x * 256 + threadIdx.x;
-    unsigned ff = 0;
-    if (k < n) {
-        const float4 p = __ldg(reinterpret_cast<const float4*>(cloud + k));
-        const int cell = cell_id<LIBM_MODE>(p.x, p.y, p.z, c);
-        if (cell >= 0) {
-            const float range = sqrtf(v3f_sqnorm(p.x, p.y, p.z));
-            if (range < FLT_MAX) ff = zbuf_min(zbuf + cell, key_make(gen, range, k), gen);
-        }
-    }
-    ff = __reduce_add_sync(0xffffffffu, ff);
-    if ((threadIdx.x & 31) == 0 && ff) atomicAdd(&kf->m, ff);
+    if (k >= n) return;
+    const float4 p = __ldg(reinterpret_cast<const float4*>(cloud + k));
+    const int cell = cell_id<LIBM_MODE>(p.x, p.y, p.z, c);
+    if (cell < 0) return;
+    const float range = sqrtf(v3f_sqnorm(p.x, p.y, p.z));
+    if (!(range < FLT_MAX)) return;
+    const unsigned long long key = key_make(gen, range, k);
+    if (key < __ldcg(zbuf + cell)) atomicMin(zbuf + cell, key);
 }
 
 // unit vector + range of a camera-frame point (tracking.cc:346-351)
@@ -460,7 +524,7 @@ __device__ __forceinline__ float4 unit_and_range(float x, float y, float z) {
 // cells[] = (unit x, unit y, unit z, range), range = -1 marks an empty cell.
 // ------------------------------------------------------------------------------------------------
 struct FinalizeArgs {
-    const KfState* kfs;
+    KfState* kfs;
     const PointXYZIT* pts;
     unsigned long long pts_cap;
     const Interval* table;
@@ -475,34 +539,53 @@ struct FinalizeArgs {
 
 template <bool FROM_CLOUD>
 __global__ void __launch_bounds__(FINALIZE_THREADS) k_finalize(const __grid_constant__ FinalizeArgs a) {
-    const KfState* __restrict__ kf = a.kfs + blockIdx.y;
+    KfState* __restrict__ kf = a.kfs + blockIdx.y;
     const int cell = blockIdx.x * FINALIZE_THREADS + threadIdx.x;
-    if (cell >= CELLS) return;
-    const unsigned long long key = a.zbuf[(size_t) blockIdx.y * CELLS + cell];
-    float4 out = make_float4(0.f, 0.f, 0.f, -1.0f);
-    int win = -1;
-    if (key_live(key, a.gen)) {
-        const unsigned k = key_index(key);
-        float x, y, z;
-        if (FROM_CLOUD) {
-            const float4 p = __ldg(reinterpret_cast<const float4*>(a.cloud + k));
-            x = p.x;
-            y = p.y;
-            z = p.z;
-        } else { // recompute the winner's deskew: same function, same bits as in k_deskew_bin
-            const KfView kv = kf_view(kf, a.table);
-            const float4* __restrict__ p4 = reinterpret_cast<const float4*>(a.pts + wrap(kf->proj_begin + k, a.pts_cap));
-            const float4 xyz = __ldg(p4);
-            const double tm = __ldg(reinterpret_cast<const double2*>(p4 + 1)).y;
-            EntryRegs e;
-            int cur = -1;
-            deskew_point(xyz.x, xyz.y, xyz.z, tm, kv, a.ext, a.c, e, cur, x, y, z);
+    bool filled = false;
+    if (cell < CELLS) {
+        const unsigned long long key = a.zbuf[(size_t) blockIdx.y * CELLS + cell];
+        float4 out = make_float4(0.f, 0.f, 0.f, -1.0f);
+        int win = -1;
+        if (key_live(key, a.gen)) {
+            const unsigned k = key_index(key);
+            float x, y, z;
+            if (FROM_CLOUD) {
+                const float4 p = __ldg(reinterpret_cast<const float4*>(a.cloud + k));
+                x = p.x;
+                y = p.y;
+                z = p.z;
+            } else { // recompute the winner's deskew: same function, same bits as in k_deskew_bin
+                const KfView kv = kf_view(kf, a.table);
+                const float4* __restrict__ p4 = reinterpret_cast<const float4*>(a.pts + wrap(kf->proj_begin + k, a.pts_cap));
+                const float4 xyz = __ldg(p4);
+                const double tm = __ldg(reinterpret_cast<const double2*>(p4 + 1)).y;
+                EntryRegs e;
+                int cur = -1;
+                deskew_point(xyz.x, xyz.y, xyz.z, tm, kv, a.ext, a.c, e, cur, x, y, z);
+            }
+            out = unit_and_range(x, y, z);
+            win = (int) k;
+            filled = true;
         }
-        out = unit_and_range(x, y, z);
-        win = (int) k;
+        a.cells[(size_t) blockIdx.y * CELLS + cell] = out;
+        if (a.winner) a.winner[cell] = win;
     }
-    a.cells[(size_t) blockIdx.y * CELLS + cell] = out;
-    if (a.winner) a.winner[cell] = win;
+    const unsigned cnt = __syncthreads_count(filled); // M = number of non-empty cells (tracking.cc:356-358)
+    if (threadIdx.x == 0 && cnt) atomicAdd(&kf->m, cnt);
+}
+
+// M for the fused paths: counts the live cells of [blockIdx.y]'s z-buffer slice owned by this block
+__device__ __forceinline__ void count_live_cells(const unsigned long long* __restrict__ zb, unsigned gen, KfState* kf) {
+    const int chunk = (CELLS + gridDim.x - 1) / gridDim.x;
+    const int begin = blockIdx.x * chunk, end = min(begin + chunk, CELLS);
+    unsigned c = 0;
+    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) c += key_live(__ldg(zb + i), gen);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&kf->m, c);
+}
+
+__global__ void __launch_bounds__(256) k_count_cells(KfState* kfs, const unsigned long long* __restrict__ zbuf, unsigned gen) {
+    count_live_cells(zbuf + (size_t) blockIdx.y * CELLS, gen, kfs + blockIdx.y);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -568,7 +651,7 @@ __global__ void __launch_bounds__(1024) k_compact(const float4* __restrict__ cel
 //                  no 1.44 MB cell array per keyframe and only deskews the cells some feature actually looks at.
 // ------------------------------------------------------------------------------------------------
 struct AssocArgs {
-    const KfState* kfs;
+    KfState* kfs;
     const float* queries; // pool, 3 floats per query
     const float4* cells;  // !FUSED: [gridDim.y][CELLS]
     const int32_t* c2c;   // nullable (single keyframe): cell -> compact index
@@ -590,8 +673,9 @@ struct AssocArgs {
 
 template <bool FUSED>
 __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_constant__ AssocArgs a) {
-    const KfState* __restrict__ kf = a.kfs + blockIdx.y;
+    KfState* __restrict__ kf = a.kfs + blockIdx.y;
     const int lane = threadIdx.x & 31;
+    if (FUSED) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf); // M, piggy-backed on this launch
     const unsigned f = blockIdx.x * ASSOC_WARPS + (threadIdx.x >> 5);
     if (f >= kf->q_count) return;
     const size_t qi = kf->q_begin + f;

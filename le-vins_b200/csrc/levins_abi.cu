@@ -218,14 +218,14 @@ int launch_deskew(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_k
     const unsigned grid = std::min<unsigned>(total, 2u * (unsigned) ctx->num_sms);
     if (ctx->consts.libm_mode == 0) {
         if (write_cloud)
-            k_deskew_bin<0, true><<<grid, DESKEW_THREADS, DESKEW_SMEM, ctx->stream>>>(a);
+            k_deskew_bin<0, true><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
         else
-            k_deskew_bin<0, false><<<grid, DESKEW_THREADS, DESKEW_SMEM, ctx->stream>>>(a);
+            k_deskew_bin<0, false><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
     } else {
         if (write_cloud)
-            k_deskew_bin<1, true><<<grid, DESKEW_THREADS, DESKEW_SMEM, ctx->stream>>>(a);
+            k_deskew_bin<1, true><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
         else
-            k_deskew_bin<1, false><<<grid, DESKEW_THREADS, DESKEW_SMEM, ctx->stream>>>(a);
+            k_deskew_bin<1, false><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
     }
     ctx->launches++;
     CU(cudaGetLastError());
@@ -610,10 +610,10 @@ extern "C" int levins_build_range_image(levins_ctx* ctx, const levins_point_xyzi
             const unsigned grid = (unsigned) ((n + 255) / 256);
             if (ctx->consts.libm_mode == 0)
                 k_bin_cloud<0><<<grid, 256, 0, ctx->stream>>>(dcloud, (unsigned) n, ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen,
-                                                                 ctx->s_kf.as<KfState>(), ctx->consts);
+                                                                 ctx->consts);
             else
                 k_bin_cloud<1><<<grid, 256, 0, ctx->stream>>>(dcloud, (unsigned) n, ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen,
-                                                                 ctx->s_kf.as<KfState>(), ctx->consts);
+                                                                 ctx->consts);
             ctx->launches++;
             CU(cudaGetLastError());
         }
@@ -708,10 +708,15 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
                            reinterpret_cast<char*>(ctx->pinned) + 512, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (nf) {
-        r = run_associate_stream(ctx, nf, false, true);
+        r = run_associate_stream(ctx, nf, false, true); // also counts M
         if (r) return r;
         if (type) CU(cudaMemcpyAsync(type, ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
         if (xyz_depth) CU(cudaMemcpyAsync(xyz_depth, ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (!nf) { // no feature kernel to piggy-back the cell count on
+        k_count_cells<<<dim3(64, 1), 256, 0, ctx->stream>>>(ctx->s_kf.as<KfState>(), ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen);
+        ctx->launches++;
+        CU(cudaGetLastError());
     }
     KfState kf;
     r = fetch_kf(ctx, &kf);
@@ -899,6 +904,11 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             mark(3, true);
             k_associate<true><<<dim3((unsigned) ((max_q + ASSOC_WARPS - 1) / ASSOC_WARPS), nw), ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
             mark(3, false);
+            ctx->launches++;
+            CU(cudaGetLastError());
+        } else { // no feature kernel to piggy-back the cell count on
+            k_count_cells<<<dim3(64, nw), 256, 0, ctx->stream>>>(ctx->b_kfs.as<KfState>() + k0, ctx->b_zbuf.as<unsigned long long>(),
+                                                                 ctx->b_gen);
             ctx->launches++;
             CU(cudaGetLastError());
         }
