@@ -340,7 +340,7 @@ def run_gpu(args):
                          "frac": achieved / peak, "traffic": load_traffic(),
                          "algorithmic_bytes_per_launch": alg_bytes_per_launch, "launch_ms": deskew_launch_ms,
                          "peak_source": peak_src,
-                         "kernel_time_share": {"k_prepare": share[0], "k_deskew_bin": share[1], "k_finalize": share[2],
+                         "kernel_time_share": {"k_prepare": share[0], "k_deskew_bin": share[1], "k_plane": share[2],
                                                "k_associate": share[3]},
                          "whole_step_frac": (32.0 * n_proj_total / (ms_per_step * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
@@ -396,7 +396,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--keyframes", type=int, default=DEFAULT_KEYFRAMES, help="keyframes per GPU per step")
-    ap.add_argument("--wave", type=int, default=16)
+    ap.add_argument("--wave", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-keyframes", type=int, default=96)
     ap.add_argument("--no-cpu", action="store_true")

@@ -200,7 +200,7 @@ int levins_batch_result_pointers(levins_ctx *ctx, void **type, void **xyz_depth,
 /* Waves: how many keyframes share one set of launches (their z-buffers stay L2-resident). 0 = default. */
 int levins_batch_set_wave(levins_ctx *ctx, int keyframes_per_wave);
 /* Per-kernel device time of the last levins_batch_run, measured with CUDA events on the launching stream when
- * profiling is on.  ms[0] prepare, ms[1] deskew+bin, ms[2] finalise cells, ms[3] associate; launches[i] = number
+ * profiling is on.  ms[0] prepare, ms[1] deskew+bin, ms[2] plane fit, ms[3] k-NN; launches[i] = number
  * of launches of that kernel. */
 int levins_set_profiling(levins_ctx *ctx, int enabled);
 int levins_batch_kernel_ms(levins_ctx *ctx, float ms[4], uint32_t launches[4]);

@@ -4,9 +4,10 @@
 //                  per-INS-interval table that replaces the per-point pose interpolation (misc.cc:62-103)
 //   k_deskew_bin   per point: range gate + deskew (le_vins.cc:445-464) fused with range-image binning
 //                  (tracking.cc:307-336) through a 64-bit atomicMin key (range bits | point index)
-//   k_associate    per feature (one warp): exact windowed 5-NN + QR plane fit + validity + depth (tracking.cc:564-634);
+//   k_associate    per feature (one warp): exact windowed 5-NN (tracking.cc:571);
 //                  in the fused path it also turns the z-buffer winners of its window into unit vectors + ranges
 //                  (tracking.cc:340-354) on the fly
+//   k_plane        per feature (one thread): threshold, QR plane fit, validity checks, depth (tracking.cc:573-631)
 //   k_finalize     stage-wise API only: per cell winner -> unit vector + range
 // plus k_bin_cloud / k_compact / k_project / k_ring_append for the stage-wise ABI entry points.
 #pragma once
@@ -663,9 +664,8 @@ struct AssocArgs {
     unsigned gen;
     Extrinsics ext;
     // outputs
-    int8_t* type;
-    float4* xyz_depth;
-    int32_t* flags;
+    float4* nn;       // 5 per query: neighbours (unit vector + range) for k_plane
+    uint2* nn_meta;   // (found, bits of the 5th squared distance)
     int32_t* knn_idx; // nullable, 5 per query
     float* knn_d2;    // nullable
     Consts c;
@@ -816,20 +816,69 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_con
         }
     }
 
+    // hand the 5 neighbours to k_plane (one THREAD per feature there: the 5x3 QR runs at full lane efficiency
+    // instead of 32 lanes repeating one feature's solve)
+    if (lane < 5) {
+        float4 pp = nn_p[0];
+        unsigned d = nn_d[0];
+        int cI = nn_c[0];
+#pragma unroll
+        for (int k = 1; k < 5; k++)
+            if (lane == k) {
+                pp = nn_p[k];
+                d = nn_d[k];
+                cI = nn_c[k];
+            }
+        a.nn[5 * qi + lane] = pp;
+        if (lane == 4) a.nn_meta[qi] = make_uint2((unsigned) found, d);
+        if (a.knn_idx) {
+            const bool ok = d != 0x7f800000u;
+            a.knn_idx[5 * qi + lane] = ok ? (a.c2c ? a.c2c[cI] : cI) : -1;
+            if (a.knn_d2) a.knn_d2[5 * qi + lane] = ok ? __uint_as_float(d) : FLT_MAX;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_plane: one thread per feature.  Threshold on the 5th distance, least-squares plane through the 5 metric points
+// (Eigen ColPivHouseholderQR restated), the three validity checks and the ray-plane depth (tracking.cc:573-631),
+// in the reference's operation order (no contraction in this translation unit).
+// ------------------------------------------------------------------------------------------------
+struct PlaneArgs {
+    const float* queries;
+    const float4* nn;     // 5 per query: unit vector + range of the neighbours, ascending (d2, index)
+    const uint2* nn_meta; // (number found, bits of the 5th squared distance)
+    unsigned long long q_begin, q_count;
+    int8_t* type;
+    float4* xyz_depth;
+    int32_t* flags;
+    Consts c;
+};
+
+__global__ void __launch_bounds__(128) k_plane(const __grid_constant__ PlaneArgs a) {
+    const unsigned long long i = (unsigned long long) blockIdx.x * 128 + threadIdx.x;
+    if (i >= a.q_count) return;
+    const size_t qi = a.q_begin + i;
+    const float qx = __ldg(a.queries + 3 * qi), qy = __ldg(a.queries + 3 * qi + 1), qz = __ldg(a.queries + 3 * qi + 2);
+    const uint2 meta = __ldg(a.nn_meta + qi);
     int type = -1, flags = 0;
     float ox = qx, oy = qy, oz = qz, od = 0.f;
-    if (found < 5) {
+    if (meta.x < 5) {
         flags = 1;
-    } else if ((double) __uint_as_float(nn_d[4]) > a.c.thr2) { // tracking.cc:573-575
+    } else if ((double) __uint_as_float(meta.y) > a.c.thr2) { // tracking.cc:573-575
         flags = 2;
     } else {
         double P[5][3];
+        float rng0 = 0.f, rng4 = 0.f;
 #pragma unroll
         for (int k = 0; k < 5; k++) { // tracking.cc:577-581
-            const double rr = (double) nn_p[k].w;
-            P[k][0] = (double) nn_p[k].x * rr;
-            P[k][1] = (double) nn_p[k].y * rr;
-            P[k][2] = (double) nn_p[k].z * rr;
+            const float4 v = __ldg(a.nn + 5 * qi + k);
+            const double rr = (double) v.w;
+            P[k][0] = (double) v.x * rr;
+            P[k][1] = (double) v.y * rr;
+            P[k][2] = (double) v.z * rr;
+            if (k == 0) rng0 = v.w;
+            if (k == 4) rng4 = v.w;
         }
         double mx[3];
         colpiv_qr_solve_5x3(P, mx);                            // tracking.cc:584-589
@@ -852,7 +901,7 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_con
                 flags |= 4;
             }
         }
-        const float depth_diff = fabsf(nn_p[0].w - nn_p[4].w); // :607-608
+        const float depth_diff = fabsf(rng0 - rng4); // :607-608
         if ((double) depth_diff > a.c.range_spread) {
             isvalid = false;
             flags |= 8;
@@ -874,25 +923,9 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_con
             }
         }
     }
-    if (lane == 0) {
-        a.type[qi] = (int8_t) type;
-        a.xyz_depth[qi] = make_float4(ox, oy, oz, od);
-        a.flags[qi] = flags;
-    }
-    if (a.knn_idx && lane < 5) {
-        // nn_* are warp-uniform; select without dynamic register indexing
-        unsigned d = nn_d[0];
-        int cI = nn_c[0];
-#pragma unroll
-        for (int k = 1; k < 5; k++)
-            if (lane == k) {
-                d = nn_d[k];
-                cI = nn_c[k];
-            }
-        const bool ok = d != 0x7f800000u;
-        a.knn_idx[5 * qi + lane] = ok ? (a.c2c ? a.c2c[cI] : cI) : -1;
-        if (a.knn_d2) a.knn_d2[5 * qi + lane] = ok ? __uint_as_float(d) : FLT_MAX;
-    }
+    a.type[qi] = (int8_t) type;
+    a.xyz_depth[qi] = make_float4(ox, oy, oz, od);
+    a.flags[qi] = flags;
 }
 
 // PointCloudCommon::pointCloudProjection (pointcloud.cc:50-63): reference operation order, no contraction

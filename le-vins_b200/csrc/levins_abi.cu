@@ -61,7 +61,7 @@ struct levins_ctx {
     uint64_t ring_tail = 0;     // physical index one past the newest point
     uint64_t ring_count_ub = 0; // host's upper bound of the live point count
     DevBuf s_ins, s_table, s_kf, s_queries;
-    DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2;
+    DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2, s_nn, s_nn_meta;
     DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
     DevBuf s_in_cloud; // explicit cloud uploaded by build_range_image
     DevBuf s_zbuf, s_cells, s_c2c, s_unit, s_winner;
@@ -76,11 +76,11 @@ struct levins_ctx {
 
     // ---- batch state ----
     DevBuf b_pts, b_ins, b_table, b_queries, b_kfs;
-    DevBuf b_type, b_xyzd, b_flags;
+    DevBuf b_type, b_xyzd, b_flags, b_nn, b_nn_meta;
     DevBuf b_zbuf, b_cells;
     std::vector<levins_keyframe_desc> b_descs;
     size_t b_nq = 0, b_npts = 0, b_nins = 0;
-    int b_wave = 16;
+    int b_wave = 64;
     int b_wave_alloc = 0;
     unsigned b_gen = 255;
     bool b_valid = false;
@@ -180,6 +180,8 @@ int ensure_stream_buffers(levins_ctx* ctx, size_t n_ins, size_t n_feat) {
     CU(ctx->s_flags.ensure(std::max<size_t>(n_feat, 1) * 4));
     CU(ctx->s_knn_idx.ensure(std::max<size_t>(n_feat, 1) * 20));
     CU(ctx->s_knn_d2.ensure(std::max<size_t>(n_feat, 1) * 20));
+    CU(ctx->s_nn.ensure(std::max<size_t>(n_feat, 1) * 80));
+    CU(ctx->s_nn_meta.ensure(std::max<size_t>(n_feat, 1) * 8));
     CU(ctx->s_cells.ensure((size_t) CELLS * sizeof(float4)));
     CU(ctx->s_c2c.ensure((size_t) CELLS * 4));
     CU(ctx->s_unit.ensure((size_t) CELLS * sizeof(PointXYZI)));
@@ -327,9 +329,8 @@ int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused) 
     aa.table = ctx->s_table.as<Interval>();
     aa.gen = ctx->s_gen;
     aa.ext = ctx->ext;
-    aa.type = ctx->s_type.as<int8_t>();
-    aa.xyz_depth = ctx->s_xyzd.as<float4>();
-    aa.flags = ctx->s_flags.as<int32_t>();
+    aa.nn = ctx->s_nn.as<float4>();
+    aa.nn_meta = ctx->s_nn_meta.as<uint2>();
     aa.knn_idx = with_idx ? ctx->s_knn_idx.as<int32_t>() : nullptr;
     aa.knn_d2 = with_idx ? ctx->s_knn_d2.as<float>() : nullptr;
     aa.c = ctx->consts;
@@ -338,6 +339,19 @@ int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused) 
         k_associate<true><<<grid, ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
     else
         k_associate<false><<<grid, ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    PlaneArgs pa{};
+    pa.queries = ctx->s_queries.as<float>();
+    pa.nn = ctx->s_nn.as<float4>();
+    pa.nn_meta = ctx->s_nn_meta.as<uint2>();
+    pa.q_begin = 0;
+    pa.q_count = nf;
+    pa.type = ctx->s_type.as<int8_t>();
+    pa.xyz_depth = ctx->s_xyzd.as<float4>();
+    pa.flags = ctx->s_flags.as<int32_t>();
+    pa.c = ctx->consts;
+    k_plane<<<(unsigned) ((nf + 127) / 128), 128, 0, ctx->stream>>>(pa);
     ctx->launches++;
     CU(cudaGetLastError());
     return LEVINS_OK;
@@ -425,7 +439,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
-                      &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_cloud, &ctx->s_in_cloud,
+                      &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_type, &ctx->b_xyzd, &ctx->b_flags, &ctx->b_zbuf,
                       &ctx->b_cells})
@@ -755,7 +769,7 @@ extern "C" int levins_point_cloud_projection(levins_ctx* ctx, const levins_pose*
 // =================================================================================================
 extern "C" int levins_batch_set_wave(levins_ctx* ctx, int w) {
     if (!ctx || w < 0 || w > 4096) return LEVINS_ERR_ARG;
-    ctx->b_wave = w ? w : 16;
+    ctx->b_wave = w ? w : 64;
     return LEVINS_OK;
 }
 
@@ -794,6 +808,8 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
     CU(ctx->b_type.ensure(std::max<size_t>(n_queries, 1)));
     CU(ctx->b_xyzd.ensure(std::max<size_t>(n_queries, 1) * 16));
     CU(ctx->b_flags.ensure(std::max<size_t>(n_queries, 1) * 4));
+    CU(ctx->b_nn.ensure(std::max<size_t>(n_queries, 1) * 80));
+    CU(ctx->b_nn_meta.ensure(std::max<size_t>(n_queries, 1) * 8));
     CU(cudaMemcpyAsync(ctx->b_pts.p, points, n_points * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->b_ins.p, ins, n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
     if (n_queries) CU(cudaMemcpyAsync(ctx->b_queries.p, query_xyz, n_queries * 12, cudaMemcpyHostToDevice, ctx->stream));
@@ -895,9 +911,8 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             aa.table = ctx->b_table.as<Interval>();
             aa.gen = ctx->b_gen;
             aa.ext = ctx->ext;
-            aa.type = ctx->b_type.as<int8_t>();
-            aa.xyz_depth = ctx->b_xyzd.as<float4>();
-            aa.flags = ctx->b_flags.as<int32_t>();
+            aa.nn = ctx->b_nn.as<float4>();
+            aa.nn_meta = ctx->b_nn_meta.as<uint2>();
             aa.knn_idx = nullptr;
             aa.knn_d2 = nullptr;
             aa.c = ctx->consts;
@@ -912,6 +927,23 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             ctx->launches++;
             CU(cudaGetLastError());
         }
+    }
+    if (ctx->b_nq) { // plane fits for every feature of the batch in one launch (one thread per feature)
+        PlaneArgs pl{};
+        pl.queries = ctx->b_queries.as<float>();
+        pl.nn = ctx->b_nn.as<float4>();
+        pl.nn_meta = ctx->b_nn_meta.as<uint2>();
+        pl.q_begin = 0;
+        pl.q_count = ctx->b_nq;
+        pl.type = ctx->b_type.as<int8_t>();
+        pl.xyz_depth = ctx->b_xyzd.as<float4>();
+        pl.flags = ctx->b_flags.as<int32_t>();
+        pl.c = ctx->consts;
+        mark(2, true);
+        k_plane<<<(unsigned) ((ctx->b_nq + 127) / 128), 128, 0, ctx->stream>>>(pl);
+        mark(2, false);
+        ctx->launches++;
+        CU(cudaGetLastError());
     }
     return LEVINS_OK;
 }
