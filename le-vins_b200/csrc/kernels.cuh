@@ -411,6 +411,10 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                 kept[j] = (i0 + j < cnt) && !((n2 > a.c.n2_far) || (n2 < a.c.n2_near)); // le_vins.cc:447-451
                 any_kept |= kept[j];
             }
+            // the 4 points are in registers: release the stage right away (no block-wide barrier, warps run decoupled;
+            // the earlier the release, the longer the TMA has to refill it)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
             float ox[DESKEW_PPT], oy[DESKEW_PPT], oz[DESKEW_PPT];
             if (any_kept) {
                 // one interval entry for all kept points of this thread?  (checked, not assumed)
@@ -487,9 +491,10 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                 pseen[j] = cell[j] >= 0 ? __ldcg(pzb + cell[j]) : 0ull;
             }
         }
-        // this warp is done reading stage s: let the producer refill it (no block-wide barrier, warps run decoupled)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + s);
+        if (!cnt) { // empty tile: nothing was read, release the stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
+        }
     }
     flush_pending();
 }

@@ -1,0 +1,118 @@
+// Drives the C++ host mirror exactly like the estimator would (le_vins.cc:367-383, tracking.cc:160-172) on a keyframe
+// dumped by tests/test_host_mirror.py, and writes its outputs back for comparison with the oracle.
+//   test_host <dir>   reads  points.bin ins.bin pixels.bin meta.bin   writes  cloud.bin assoc.bin summary.txt
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "le_vins/vins_lidar.h"
+#include "visual/tracking_depth.h"
+
+template <typename T> static std::vector<T> read_bin(const std::string &path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    const size_t bytes = f.tellg();
+    f.seekg(0);
+    std::vector<T> v(bytes / sizeof(T));
+    f.read(reinterpret_cast<char *>(v.data()), bytes);
+    return v;
+}
+template <typename T> static void write_bin(const std::string &path, const std::vector<T> &v) {
+    std::ofstream f(path, std::ios::binary);
+    f.write(reinterpret_cast<const char *>(v.data()), v.size() * sizeof(T));
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) return 2;
+    const std::string dir = argv[1];
+    try {
+        // meta: stamp, td_b_l, pose_b_c[12], pose_c_l[12], intr[5], frame_ref_pose[12], scans
+        const auto meta = read_bin<double>(dir + "/meta.bin");
+        const double stamp = meta[0], td_b_l = meta[1];
+        Pose pose_b_c, pose_c_l, frame_pose;
+        std::memcpy(pose_b_c.R.data(), &meta[2], 72);
+        std::memcpy(pose_b_c.t.data(), &meta[11], 24);
+        std::memcpy(pose_c_l.R.data(), &meta[14], 72);
+        std::memcpy(pose_c_l.t.data(), &meta[23], 24);
+        visual::Camera camera(meta[26], meta[27], meta[28], meta[29], meta[30]);
+        std::memcpy(frame_pose.R.data(), &meta[31], 72);
+        std::memcpy(frame_pose.t.data(), &meta[40], 24);
+        const int n_scans = static_cast<int>(meta[43]);
+
+        const auto points = read_bin<PointXYZIT>(dir + "/points.bin");
+        const auto ins_raw = read_bin<double>(dir + "/ins.bin"); // 9 doubles per sample
+        const auto pixels = read_bin<float>(dir + "/pixels.bin");
+
+        MISC::InsWindow ins_window;
+        for (size_t i = 0; i + 8 < ins_raw.size(); i += 9) {
+            IMU imu;
+            imu.time = ins_raw[i];
+            IntegrationState st;
+            st.time = ins_raw[i + 1];
+            st.p = Vector3d(ins_raw[i + 2], ins_raw[i + 3], ins_raw[i + 4]);
+            st.q = Quaterniond(&ins_raw[i + 5]);
+            ins_window.push_back({imu, st});
+        }
+
+        levins_host::VinsLidarPath vins(pose_b_c, pose_c_l, td_b_l);
+        // the LiDAR callback: one addNewPointCloud per scan (fusion.cc:360 / 376)
+        const size_t per = (points.size() + n_scans - 1) / n_scans;
+        for (size_t b = 0; b < points.size(); b += per) {
+            PointCloudCustomPtr scan(new PointCloudCustom);
+            scan->points.assign(points.begin() + b, points.begin() + std::min(points.size(), b + per));
+            vins.addNewPointCloud(scan);
+        }
+        // le_vins.cc:376-381
+        static PointCloud pointcloud;
+        pointcloud.clear();
+        const bool stacked = vins.pointcloudStackForVisualTracking(stamp, ins_window, pointcloud);
+
+        // tracking.cc:160-172
+        visual::Tracking tracking;
+        std::vector<visual::DepthAssociated> associated;
+        int num_associated = 0;
+        bool projected = false;
+        if (!pointcloud.empty()) {
+            projected = tracking.depthAssociationProjection(pointcloud);
+            if (projected) {
+                std::vector<visual::Point2f> px(pixels.size() / 2);
+                for (size_t k = 0; k < px.size(); k++) px[k] = {pixels[2 * k], pixels[2 * k + 1]};
+                num_associated = tracking.depthAssociationReference(camera, px, std::vector<uint8_t>(), frame_pose, associated);
+            }
+        }
+        // single-query form on the first pixel (in-place semantics of tracking.cc:626-629)
+        PointType single;
+        int single_type = -1;
+        if (projected && !pixels.empty()) {
+            const Vector3d puc = camera.pixel2unitcam({pixels[0], pixels[1]});
+            single.x = (float) puc[0];
+            single.y = (float) puc[1];
+            single.z = (float) puc[2];
+            single_type = tracking.depthAssociationPlaneFitting(single);
+        }
+
+        write_bin(dir + "/cloud.bin", pointcloud.points);
+        std::vector<double> out;
+        for (const auto &a : associated) {
+            out.push_back((double) a.index);
+            out.push_back(a.pw[0]);
+            out.push_back(a.pw[1]);
+            out.push_back(a.pw[2]);
+            out.push_back(a.depth);
+            out.push_back((double) a.type);
+        }
+        write_bin(dir + "/assoc.bin", out);
+        std::ofstream s(dir + "/summary.txt");
+        s << "stacked " << stacked << "\nn " << pointcloud.size() << "\nprojected " << projected << "\nM " << tracking.unitSphereSize()
+          << "\nassociated " << num_associated << "\nsingle_type " << single_type << "\nsingle " << single.x << " " << single.y << " "
+          << single.z << " " << single.intensity << "\n";
+        std::printf("host mirror: n=%zu M=%zu associated=%d\n", pointcloud.size(), tracking.unitSphereSize(), num_associated);
+        levins_destroy(levins_host::context());
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "test_host failed: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
