@@ -445,8 +445,8 @@ __device__ __forceinline__ int cell_of_point_fast(float x, float y, float z, con
     const bool tiny = !(z > 1e-30f); // zero / denormal-range z: |z| 2^-25 may be inexact, leave it to the exact path
     const bool outside = outside_fov(x, y, z);
     // col_angle / ANGLE = (atan2(z, x) - pi/4) / ANGLE = 150 - atan(x / z) / ANGLE
-    const float rz = __frcp_rn(z);
-    const float tc = x * rz;
+    const float tc = __fdividef(x, z); // approximate: this path only has to be right to ~1e-4 cell
+
     const float qc = fmaf(-atan_poly(tc), c.inv_angle_f, 150.0f);
     // row_angle / ANGLE = (atan2(y, sqrt(x^2 + z^2)) + pi/4) / ANGLE = 150 + atan(y / sqrt(x^2 + z^2)) / ANGLE
     const float s = fmaf(x, x, z * z);
@@ -512,30 +512,33 @@ __device__ __forceinline__ void load_entry(const Interval* __restrict__ it, Entr
     e.c0x = v8.y; e.c0y = v9.x; e.c0z = v9.y; e.c1x = v10.x; e.c1y = v10.y; e.c1z = v11.x;
 }
 
-// does the cached entry `cur` serve time t?  (entry 0 = out-of-window fallback, misc.cc:28-30, 74-77)
-__device__ __forceinline__ bool entry_serves(const KfView& kv, const EntryRegs& e, int cur, double t) {
-    if (cur > 0) {
-        // GPS seconds of week are positive: IEEE doubles then order like their bit patterns (integer compares run on
-        // the ALU pipe instead of the busier FP64 pipe); negative or NaN times simply miss and take the slow path
-        const long long ti = __double_as_longlong(t);
-        return (__double_as_longlong(e.t_lo) <= ti) && (ti < __double_as_longlong(e.t_hi)) && (ti > 0);
-    }
-    const bool out_of_window = (kv.n_ins < 2) || (kv.t0 > t) || (kv.t_last <= t);
-    return cur == 0 && out_of_window;
+// does the cached interval entry (cur > 0) bracket time t, i.e. t_lo <= t < t_hi?  GPS seconds of week are positive,
+// so IEEE doubles order like their bit patterns and the test is one unsigned 64-bit compare on the ALU pipe:
+// (bits(t) - bits(t_lo)) < (bits(t_hi) - bits(t_lo)); a negative or NaN time wraps to a huge value and misses.
+__device__ __forceinline__ bool entry_brackets(const EntryRegs& e, double t) {
+    const unsigned long long lo = (unsigned long long) __double_as_longlong(e.t_lo);
+    const unsigned long long width = (unsigned long long) __double_as_longlong(e.t_hi) - lo;
+    return ((unsigned long long) __double_as_longlong(t) - lo) < width;
 }
 
-// Make `e` the entry for time t (misc.cc:25-60 semantics).  Fast when e already brackets t.
+// Make `e` the entry for time t (misc.cc:25-60 semantics).  Fast when e already brackets t.  Otherwise the entry at the
+// index predicted from the (near-uniform) INS spacing is loaded speculatively in one go and verified afterwards, so the
+// common case costs one memory round trip, not two (probe, then load).
 __device__ __forceinline__ void seek_entry(const KfView& kv, double t, EntryRegs& e, int& cur) {
-    if (cur > 0 && e.t_lo <= t && t < e.t_hi) return;
+    if (cur > 0 && e.t_lo > 0 && entry_brackets(e, t)) return;
     int idx = 0;
     if (!(kv.n_ins < 2 || kv.t0 > t || kv.t_last <= t)) { // misc.cc:28-30
         const int lo = 1, hi = kv.n_ins - 1;
         int g = 1 + (int) ((t - kv.t0) * kv.inv_mean_dt);
         g = min(max(g, lo), hi);
-        const double2 ab = __ldg(reinterpret_cast<const double2*>(kv.tab + g));
-        idx = (ab.x <= t && t < ab.y) ? g : find_interval_slow(kv.tab, kv.n_ins, t, g, lo, hi);
+        if (g != cur) {
+            load_entry(kv.tab + g, e);
+            cur = g;
+        }
+        if ((e.t_lo <= t) && (t < e.t_hi)) return;
+        idx = find_interval_slow(kv.tab, kv.n_ins, t, g, lo, hi);
     }
-    if (idx != cur || cur < 0) {
+    if (idx != cur) {
         load_entry(kv.tab + idx, e);
         cur = idx;
     }

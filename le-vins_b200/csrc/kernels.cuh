@@ -417,22 +417,18 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
             if (lane == 0) mbar_arrive(empty + s);
             float ox[DESKEW_PPT], oy[DESKEW_PPT], oz[DESKEW_PPT];
             if (any_kept) {
-                // one interval entry for all kept points of this thread?  (checked, not assumed)
-                bool all = true;
+                // bring the cached interval entry to this thread's first kept point (a few instructions when it still
+                // serves), then check -- not assume -- that it brackets every kept point of the thread
+                bool sought = false;
 #pragma unroll
-                for (int j = 0; j < DESKEW_PPT; j++) all &= !kept[j] || entry_serves(kv, e, cur, tt[j]);
-                if (!all) {
-                    bool sought = false;
+                for (int j = 0; j < DESKEW_PPT; j++)
+                    if (kept[j] && !sought) {
+                        seek_entry(kv, tt[j], e, cur);
+                        sought = true;
+                    }
+                bool all = cur > 0 && e.t_lo > 0;
 #pragma unroll
-                    for (int j = 0; j < DESKEW_PPT; j++)
-                        if (kept[j] && !sought) {
-                            seek_entry(kv, tt[j], e, cur);
-                            sought = true;
-                        }
-                    all = true;
-#pragma unroll
-                    for (int j = 0; j < DESKEW_PPT; j++) all &= !kept[j] || entry_serves(kv, e, cur, tt[j]);
-                }
+                for (int j = 0; j < DESKEW_PPT; j++) all &= !kept[j] || entry_brackets(e, tt[j]);
                 if (all && e.theta * e.theta < 2.44140625e-4) {
                     // common case: straight-line code, the 4 points interleave
 #pragma unroll
@@ -585,7 +581,14 @@ __device__ __forceinline__ void count_live_cells(const unsigned long long* __res
     const int chunk = (CELLS + gridDim.x - 1) / gridDim.x;
     const int begin = blockIdx.x * chunk, end = min(begin + chunk, CELLS);
     unsigned c = 0;
-    for (int i = begin + threadIdx.x; i < end; i += blockDim.x) c += key_live(__ldg(zb + i), gen);
+    const int stride = blockDim.x;
+    int i = begin + threadIdx.x;
+    for (; i + 3 * stride < end; i += 4 * stride) { // 4 independent loads in flight
+        const unsigned long long k0 = __ldg(zb + i), k1 = __ldg(zb + i + stride), k2 = __ldg(zb + i + 2 * stride),
+                                 k3 = __ldg(zb + i + 3 * stride);
+        c += key_live(k0, gen) + key_live(k1, gen) + key_live(k2, gen) + key_live(k3, gen);
+    }
+    for (; i < end; i += stride) c += key_live(__ldg(zb + i), gen);
     c = __reduce_add_sync(0xffffffffu, c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&kf->m, c);
 }
@@ -677,12 +680,14 @@ struct AssocArgs {
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_constant__ AssocArgs a) {
+__global__ void __launch_bounds__(ASSOC_WARPS * 32, 6) k_associate(const __grid_constant__ AssocArgs a) {
     KfState* __restrict__ kf = a.kfs + blockIdx.y;
     const int lane = threadIdx.x & 31;
-    if (FUSED) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf); // M, piggy-backed on this launch
     const unsigned f = blockIdx.x * ASSOC_WARPS + (threadIdx.x >> 5);
-    if (f >= kf->q_count) return;
+    if (f >= kf->q_count) {
+        if (FUSED) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf);
+        return;
+    }
     const size_t qi = kf->q_begin + f;
     const float qx = __ldg(a.queries + 3 * qi), qy = __ldg(a.queries + 3 * qi + 1), qz = __ldg(a.queries + 3 * qi + 2);
 
@@ -707,30 +712,37 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_con
     const unsigned long long* __restrict__ zb = FUSED ? a.zbuf + (size_t) blockIdx.y * CELLS : nullptr;
     const float4* __restrict__ cells = FUSED ? nullptr : a.cells + (size_t) blockIdx.y * CELLS;
     int count = 0;
+    bool inmask[4];
+    unsigned long long wkey[4];
+    int wcell[4];
 #pragma unroll
-    for (int itc = 0; itc < 4; itc++) {
+    for (int itc = 0; itc < 4; itc++) { // all loads of the window first: one L2 round trip, not four
         const int j = lane + 32 * itc;
         const int r = rowq - WIN_ROWS + j / WIN_W;
         const int cc = colq - WIN_COLS + j % WIN_W;
-        bool live = false;
-        unsigned long long key = 0;
+        inmask[itc] = false;
+        wkey[itc] = 0;
+        wcell[itc] = r * IMG + cc;
         if (j < WIN_CELLS && r >= 0 && r < IMG && cc >= 0 && cc < IMG) {
             const float dr = fmaxf(0.f, fabsf((float) r - rq) - 0.51f);
             const float dc = fmaxf(0.f, fabsf((float) cc - cq) - 0.51f);
-            if (dr * dr + cmin * dc * dc <= 9.0601f) { // 3.01^2
-                if (FUSED) {
-                    key = __ldg(zb + r * IMG + cc);
-                    live = key_live(key, a.gen);
-                } else {
-                    live = __ldg(&cells[r * IMG + cc].w) >= 0.f;
-                }
+            inmask[itc] = dr * dr + cmin * dc * dc <= 9.0601f; // 3.01^2
+            if (inmask[itc]) {
+                if (FUSED)
+                    wkey[itc] = __ldg(zb + wcell[itc]);
+                else
+                    wkey[itc] = __float_as_uint(__ldg(&cells[wcell[itc]].w)); // range, -1 (sign bit set) for empty cells
             }
         }
+    }
+#pragma unroll
+    for (int itc = 0; itc < 4; itc++) {
+        const bool live = inmask[itc] && (FUSED ? key_live(wkey[itc], a.gen) : !((unsigned) wkey[itc] >> 31));
         const unsigned bal = __ballot_sync(0xffffffffu, live);
         if (live) {
             const int pos = count + __popc(bal & ((1u << lane) - 1));
-            s_key[wib][pos] = key;
-            s_cid[wib][pos] = r * IMG + cc;
+            s_key[wib][pos] = wkey[itc];
+            s_cid[wib][pos] = wcell[itc];
         }
         count += __popc(bal);
     }
@@ -842,6 +854,8 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32) k_associate(const __grid_con
             if (a.knn_d2) a.knn_d2[5 * qi + lane] = ok ? __uint_as_float(d) : FLT_MAX;
         }
     }
+    // M (number of non-empty cells), piggy-backed on this launch: every block counts its slice of the z-buffer
+    if (FUSED) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf);
 }
 
 // ------------------------------------------------------------------------------------------------
