@@ -117,20 +117,35 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # CPU legs (oracle port)
 # ------------------------------------------------------------------------------------------------------------
-def cpu_keyframes(batch, ks, nthreads):
+def host_cores():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU legs pass the count explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_keyframes(batch, ks, nthreads, budget_s=None):
+    """Oracle port on keyframes `ks` (cycled until `budget_s` seconds of CPU work when given).  Returns
+    (seconds, features, points, keyframes)."""
     import oracle_py as orc
     from levins import synth
 
     t0 = time.perf_counter()
-    nf = 0
-    npts = 0
-    for k in ks:
-        kf = synth.batch_keyframe(batch, k)
-        r = orc.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries,
-                         kf.shape.stack_interval, nthreads=nthreads)
-        nf += len(kf.queries)
-        npts += r["n_projected"]
-    return time.perf_counter() - t0, nf, npts
+    nf = npts = nk = 0
+    ks = list(ks)
+    while True:
+        for k in ks:
+            kf = synth.batch_keyframe(batch, k)
+            r = orc.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries,
+                             kf.shape.stack_interval, nthreads=nthreads)
+            nf += len(kf.queries)
+            npts += r["n_projected"]
+            nk += 1
+            if budget_s is not None and time.perf_counter() - t0 >= budget_s:
+                return time.perf_counter() - t0, nf, npts, nk
+        if budget_s is None:
+            return time.perf_counter() - t0, nf, npts, nk
 
 
 def run_reference(args):
@@ -145,12 +160,12 @@ def run_reference(args):
     orc.build()
     n_sample = 8
     batch = synth.make_batch(CFG, n_sample, n_unique_scans=UNIQUE_SCANS)
-    cores = orc.max_threads()
+    cores = host_cores()
     for _ in range(args.warmup):
         cpu_keyframes(batch, range(n_sample), cores)
     t_total, nf_total, np_total = 0.0, 0, 0
     for _ in range(args.steps):
-        t, nf, npts = cpu_keyframes(batch, range(n_sample), cores)
+        t, nf, npts, _ = cpu_keyframes(batch, range(n_sample), cores)
         t_total += t
         nf_total += nf
         np_total += npts
@@ -306,20 +321,24 @@ def run_gpu(args):
     if rank == 0 and not args.no_stream:
         p50 = stream_latency(abi, synth, local_rank)
 
+    # ---- secondary workload: BASELINE configs[2], Ouster OS1-128, 20-scan (2.0 s) window, td_b_l = -0.48 s ----
+    also = None
+    if rank == 0 and world == 1 and not args.no_cfg3:
+        also = bench_cfg3(torch, abi, synth, local_rank, stream, peak)
+
     # ---- CPU baseline on a bounded sample (rank 0 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle_py as orc
 
         orc.build()
-        cores = orc.max_threads()
-        ks = list(range(min(args.cpu_keyframes, n_kf)))
-        cpu_keyframes(batch, ks[:2], cores)
-        t, nf, npts = cpu_keyframes(batch, ks, cores)
+        cores = host_cores()
+        cpu_keyframes(batch, range(2), cores)
+        t, nf, npts, nk = cpu_keyframes(batch, range(n_kf), cores, budget_s=args.cpu_seconds)
         cpu = {"value": nf / t, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{len(ks)} keyframes of the workload ({nf} features, {npts} points) in {t:.1f} s; stage 1 on "
+               "sample": f"{nk} keyframes of the workload ({nf} features, {npts} points) in {t:.1f} s; stage 1 on "
                          f"{cores} threads, stages 2-3 serial + KD-tree like the reference",
-               "lidar_pts_per_s": npts / t}
+               "lidar_pts_per_s": npts / t, "keyframes_per_s": nk / t}
 
     if rank == 0:
         line = {
@@ -344,12 +363,44 @@ def run_gpu(args):
                                                "k_associate": share[3]},
                          "whole_step_frac": (32.0 * n_proj_total / (ms_per_step * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
+            "also": also,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def bench_cfg3(torch, abi, synth, device, stream, peak, n_kf=6, steps=10):
+    """Device-resident throughput of the FusionPortableV2 vehicle shape (2.62 M points per keyframe)."""
+    b = synth.make_batch(3, n_kf, n_unique_scans=20, seed=synth.BASE_SEED + 3, ins_span=3.5)
+    ctx = abi.Context(device, stack_interval=b.shape.stack_interval)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_extrinsics(b.shape.rig.pose_b_c, b.shape.rig.pose_c_l, b.shape.rig.td_b_l)
+    ctx.batch_upload(b.points, b.ins, b.queries.reshape(-1, 3), abi.batch_descs(b))
+    for _ in range(3):
+        ctx.batch_run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        ctx.batch_run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = ctx.batch_download()
+    npts = int(out["n_projected"].astype(np.int64).sum())
+    ctx.set_profiling(True)
+    ctx.batch_run()
+    kms, kn = ctx.batch_kernel_ms()
+    ctx.close()
+    return {"workload": f"cfg3_fusionportable_os1_128_x20scans_1440x1080_F{b.queries.shape[1]}_batch{n_kf}",
+            "ms_per_step": ms, "lidar_pts_per_s": npts / (ms * 1e-3), "keyframes_per_s": n_kf / (ms * 1e-3),
+            "features_per_s": n_kf * b.queries.shape[1] / (ms * 1e-3), "points_per_keyframe": npts // n_kf,
+            "cells_per_keyframe": int(out["m"].mean()), "associated_fraction": float((out["type"] == 1).mean()),
+            "whole_step_hbm_frac": 32.0 * npts / (ms * 1e-3) / 1e9 / peak,
+            "k_deskew_bin_hbm_frac": 32.0 * npts / (float(kms[1]) * 1e-3) / 1e9 / peak}
 
 
 def load_traffic():
@@ -398,7 +449,8 @@ def main():
     ap.add_argument("--keyframes", type=int, default=DEFAULT_KEYFRAMES, help="keyframes per GPU per step")
     ap.add_argument("--wave", type=int, default=64)
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--cpu-keyframes", type=int, default=96)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the secondary Ouster OS1-128 x 20-scan measurement")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-stream", action="store_true")
     args = ap.parse_args()
