@@ -353,26 +353,6 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
     unsigned cur_kf = 0xffffffffu;
     KfView kv{};
     unsigned n = 0;
-    // The z-buffer phase of a tile is split over two iterations so that no warp ever waits on an L2 round trip:
-    // the probes (plain L2 reads) are issued at the end of the iteration that computed the keys, and compared
-    // one tile later, when they have long arrived; winners are sent as fire-and-forget RED.MIN (no return value).
-    unsigned long long pkey[DESKEW_PPT], pseen[DESKEW_PPT];
-    int pcell[DESKEW_PPT];
-    unsigned long long* pzb = a.zbuf;
-#pragma unroll
-    for (int j = 0; j < DESKEW_PPT; j++) {
-        pcell[j] = -1;
-        pkey[j] = 0;
-        pseen[j] = 0;
-    }
-    auto flush_pending = [&]() {
-#pragma unroll
-        for (int j = 0; j < DESKEW_PPT; j++) {
-            if (pcell[j] >= 0 && pkey[j] < pseen[j]) atomicMin(pzb + pcell[j], pkey[j]); // result unused -> RED
-            pcell[j] = -1;
-        }
-    };
-
     unsigned it = 0;
     for (unsigned t = t_begin; t < t_end; ++t, ++it) {
         const int s = it % DESKEW_STAGES;
@@ -394,21 +374,27 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
 
         if (cnt) {
             const float4* __restrict__ sp = reinterpret_cast<const float4*>(smem_raw + s * TILE_BYTES);
-            const unsigned i0 = tid * DESKEW_PPT; // 4 consecutive points per thread
+            // 4 consecutive points per thread (they almost always share one INS interval).  Lane l visits them in the order
+            // (j + l) & 3: with the plain order all lanes of a quarter-warp would hit the same 4 banks (128-byte lane stride,
+            // 8-way conflict on every LDS.128); rotated, the conflict is 2-way.
+            const unsigned i0 = tid * DESKEW_PPT;
+            unsigned pi[DESKEW_PPT];
+#pragma unroll
+            for (int j = 0; j < DESKEW_PPT; j++) pi[j] = i0 + ((j + lane) & (DESKEW_PPT - 1));
             float px[DESKEW_PPT], py[DESKEW_PPT], pz[DESKEW_PPT];
             double tt[DESKEW_PPT];
             bool kept[DESKEW_PPT];
             bool any_kept = false;
 #pragma unroll
             for (int j = 0; j < DESKEW_PPT; j++) {
-                const float4 xyz = sp[2 * (i0 + j)];
-                const double tm = reinterpret_cast<const double2*>(sp)[2 * (i0 + j) + 1].y;
+                const float4 xyz = sp[2 * pi[j]];
+                const double tm = reinterpret_cast<const double2*>(sp)[2 * pi[j] + 1].y;
                 px[j] = xyz.x;
                 py[j] = xyz.y;
                 pz[j] = xyz.z;
                 tt[j] = tm + a.ext.td_b_l; // le_vins.cc:455
                 const float n2 = v3f_sqnorm(xyz.x, xyz.y, xyz.z);
-                kept[j] = (i0 + j < cnt) && !((n2 > a.c.n2_far) || (n2 < a.c.n2_near)); // le_vins.cc:447-451
+                kept[j] = (pi[j] < cnt) && !((n2 > a.c.n2_far) || (n2 < a.c.n2_near)); // le_vins.cc:447-451
                 any_kept |= kept[j];
             }
             // the 4 points are in registers: release the stage right away (no block-wide barrier, warps run decoupled;
@@ -449,8 +435,8 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
             if (WRITE_CLOUD) {
 #pragma unroll
                 for (int j = 0; j < DESKEW_PPT; j++)
-                    if (i0 + j < cnt) {
-                        float4* out = reinterpret_cast<float4*>(a.cloud_out + off + i0 + j);
+                    if (pi[j] < cnt) {
+                        float4* out = reinterpret_cast<float4*>(a.cloud_out + off + pi[j]);
                         out[0] = kept[j] ? make_float4(ox[j], oy[j], oz[j], 1.0f) : make_float4(0.f, 0.f, 0.f, 1.0f); // resize() default (le_vins.cc:438)
                         out[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
@@ -475,24 +461,20 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
             for (int j = 0; j < DESKEW_PPT; j++) {
                 const float range = sqrtf(v3f_sqnorm(ox[j], oy[j], oz[j])); // tracking.cc:330
                 if (!kept[j] || !(range < FLT_MAX)) cell[j] = -1;            // tracking.cc:332 against the FLT_MAX initial value
-                key[j] = key_make(a.gen, range, off + i0 + j);
+                key[j] = key_make(a.gen, range, off + pi[j]);
             }
-            // z-buffer: settle the previous tile (its probes have arrived), then probe this tile's cells
-            flush_pending();
-            pzb = a.zbuf + (size_t) kfi * CELLS;
+            // z-buffer: fire-and-forget RED.MIN.64, one per in-grid point (no probe: a probe costs the L1/L2 path as much
+            // as the reduction itself and would put an L2 round trip on the critical path)
+            unsigned long long* __restrict__ zb = a.zbuf + (size_t) kfi * CELLS;
 #pragma unroll
-            for (int j = 0; j < DESKEW_PPT; j++) {
-                pcell[j] = cell[j];
-                pkey[j] = key[j];
-                pseen[j] = cell[j] >= 0 ? __ldcg(pzb + cell[j]) : 0ull;
-            }
+            for (int j = 0; j < DESKEW_PPT; j++)
+                if (cell[j] >= 0) atomicMin(zb + cell[j], key[j]);
         }
         if (!cnt) { // empty tile: nothing was read, release the stage
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + s);
         }
     }
-    flush_pending();
 }
 
 // explicit-cloud binning for levins_build_range_image(cloud != NULL)
