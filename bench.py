@@ -447,7 +447,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--keyframes", type=int, default=DEFAULT_KEYFRAMES, help="keyframes per GPU per step")
-    ap.add_argument("--wave", type=int, default=64)
+    ap.add_argument("--wave", type=int, default=256)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the secondary Ouster OS1-128 x 20-scan measurement")

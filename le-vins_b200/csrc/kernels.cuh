@@ -226,7 +226,7 @@ constexpr int DESKEW_PPT = 4;
 constexpr int TILE_PTS = DESKEW_THREADS * DESKEW_PPT; // 1024 points = 32 KB
 constexpr int TILE_BYTES = TILE_PTS * 32;
 constexpr int DESKEW_STAGES = 3;
-constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 64;
+constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 128; // + full/empty mbarriers + tile ids
 constexpr int DESKEW_BLOCK = DESKEW_THREADS; // 8 warps; lane 0 of warp 0 doubles as the TMA producer
 constexpr int DESKEW_PTS_PER_BLOCK = TILE_PTS;
 
@@ -240,6 +240,7 @@ struct DeskewArgs {
     unsigned long long* zbuf; // [n_kf][CELLS]
     PointXYZI* cloud_out;     // streaming only (n_kf == 1), nullable
     unsigned gen;             // z-buffer generation of this launch
+    unsigned* tile_counter;   // zeroed before the launch: dynamic tile hand-out
     Extrinsics ext;
     Consts c;
 };
@@ -307,11 +308,8 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
     unsigned long long* empty = full + DESKEW_STAGES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
+    unsigned* tile_id = reinterpret_cast<unsigned*>(empty + DESKEW_STAGES); // tile held by each stage
     const unsigned total = a.n_kf * a.tiles_per_kf;
-    // even contiguous split: every CTA gets floor or ceil of total / gridDim.x tiles
-    const unsigned t_begin = (unsigned) (((unsigned long long) blockIdx.x * total) / gridDim.x);
-    const unsigned t_end = (unsigned) (((unsigned long long) (blockIdx.x + 1) * total) / gridDim.x);
-    if (t_begin >= t_end) return;
 
     if (tid == 0) {
 #pragma unroll
@@ -323,15 +321,25 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
     }
     __syncthreads();
 
-    // producer duty (thread 0): tile t goes into stage (t - t_begin) % STAGES once all 8 warps have released that stage
-    auto issue = [&](unsigned t, unsigned it_t) {
+    // Producer duty (thread 0).  Tiles are handed out dynamically in keyframe-major order (one atomic per tile), so at any
+    // time the ~300 tiles in flight belong to two or three keyframes -- their z-buffers stay L2-resident -- and no CTA is
+    // left idle at the end of the launch.  The it_t-th tile of this CTA goes into stage it_t % STAGES once all 8 warps
+    // have released it; a tile id >= total is the stop signal.
+    auto issue = [&](unsigned it_t) {
         const int s = it_t % DESKEW_STAGES;
         if (it_t >= DESKEW_STAGES) mbar_wait(empty + s, ((it_t / DESKEW_STAGES) - 1) & 1);
-        const KfState* kf = a.kfs + t / a.tiles_per_kf;
-        const unsigned off = (t % a.tiles_per_kf) * TILE_PTS;
-        const unsigned n = kf->n_proj;
-        const unsigned cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
-        mbar_arrive_expect_tx(full + s, cnt * 32u);
+        const unsigned t = atomicAdd(a.tile_counter, 1u);
+        tile_id[s] = t;
+        unsigned cnt = 0;
+        const KfState* kf = nullptr;
+        unsigned off = 0;
+        if (t < total) {
+            kf = a.kfs + t / a.tiles_per_kf;
+            off = (t % a.tiles_per_kf) * TILE_PTS;
+            const unsigned n = kf->n_proj;
+            cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
+        }
+        mbar_arrive_expect_tx(full + s, cnt * 32u); // release: tile_id[s] is visible to whoever passes the barrier
         if (cnt) {
             unsigned char* dst = smem_raw + s * TILE_BYTES;
             const unsigned long long phys = wrap(kf->proj_begin + off, a.pts_cap);
@@ -343,8 +351,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
     };
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < DESKEW_STAGES - 1; i++)
-            if (t_begin + i < t_end) issue(t_begin + i, i);
+        for (int i = 0; i < DESKEW_STAGES - 1; i++) issue(i);
     }
 
     // ---- consumer warps ----
@@ -353,12 +360,14 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
     unsigned cur_kf = 0xffffffffu;
     KfView kv{};
     unsigned n = 0;
-    unsigned it = 0;
-    for (unsigned t = t_begin; t < t_end; ++t, ++it) {
+    for (unsigned it = 0;; ++it) {
         const int s = it % DESKEW_STAGES;
-        // keep the ring full: the stage freed by iteration it-1 takes tile t+STAGES-1.  Only warp 0 can wait here (for the
+        // keep the ring full: the stage freed by iteration it-1 takes the next tile.  Only warp 0 can wait here (for the
         // other warps to release that stage); the other warps run on, up to a full tile ahead of it.
-        if (tid == 0 && t + DESKEW_STAGES - 1 < t_end) issue(t + DESKEW_STAGES - 1, it + DESKEW_STAGES - 1);
+        if (tid == 0) issue(it + DESKEW_STAGES - 1);
+        mbar_wait(full + s, (it / DESKEW_STAGES) & 1);
+        const unsigned t = tile_id[s];
+        if (t >= total) break;
         const unsigned kfi = t / a.tiles_per_kf;
         KfState* __restrict__ kf = a.kfs + kfi;
         if (kfi != cur_kf) { // new keyframe: reload the view, drop the cached interval
@@ -369,8 +378,6 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
         }
         const unsigned off = (t % a.tiles_per_kf) * TILE_PTS;
         const unsigned cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
-
-        mbar_wait(full + s, (it / DESKEW_STAGES) & 1);
 
         if (cnt) {
             const float4* __restrict__ sp = reinterpret_cast<const float4*>(smem_raw + s * TILE_BYTES);
