@@ -91,7 +91,7 @@ struct PrepareArgs {
     Consts c;
 };
 
-__global__ void __launch_bounds__(128) k_prepare(const __grid_constant__ PrepareArgs a) {
+__global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ PrepareArgs a) {
     KfState* kf = a.kfs + blockIdx.x;
     __shared__ double sR0[9], st0[3];
     __shared__ unsigned long long s_first, s_end, s_begin, s_count;
@@ -226,7 +226,7 @@ constexpr int DESKEW_PPT = 4;
 constexpr int TILE_PTS = DESKEW_THREADS * DESKEW_PPT; // 1024 points = 32 KB
 constexpr int TILE_BYTES = TILE_PTS * 32;
 constexpr int DESKEW_STAGES = 3;
-constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 128; // + full/empty mbarriers + tile ids
+constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 48 + DESKEW_STAGES * 64; // + full/empty mbarriers + tile descriptors
 constexpr int DESKEW_BLOCK = DESKEW_THREADS; // 8 warps; lane 0 of warp 0 doubles as the TMA producer
 constexpr int DESKEW_PTS_PER_BLOCK = TILE_PTS;
 
@@ -301,6 +301,15 @@ __device__ __forceinline__ int cell_id(float x, float y, float z, const Consts& 
     return cell;
 }
 
+// per-stage tile descriptor: the producer reads the keyframe state once and passes it through shared memory, so the
+// consumers never wait on global memory for it
+struct __align__(16) TileDesc {
+    const Interval* tab;
+    double t0, t_last, inv_mean_dt;
+    unsigned tile, cnt, off, kfi;
+    int n_ins, pad;
+};
+
 template <int LIBM_MODE, bool WRITE_CLOUD>
 __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
     unsigned long long* empty = full + DESKEW_STAGES;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    unsigned* tile_id = reinterpret_cast<unsigned*>(empty + DESKEW_STAGES); // tile held by each stage
+    TileDesc* tdesc = reinterpret_cast<TileDesc*>(empty + DESKEW_STAGES); // what each stage holds (written by the producer)
     const unsigned total = a.n_kf * a.tiles_per_kf;
 
     if (tid == 0) {
@@ -329,17 +338,27 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
         const int s = it_t % DESKEW_STAGES;
         if (it_t >= DESKEW_STAGES) mbar_wait(empty + s, ((it_t / DESKEW_STAGES) - 1) & 1);
         const unsigned t = atomicAdd(a.tile_counter, 1u);
-        tile_id[s] = t;
         unsigned cnt = 0;
         const KfState* kf = nullptr;
         unsigned off = 0;
+        TileDesc d{};
+        d.tile = t;
         if (t < total) {
-            kf = a.kfs + t / a.tiles_per_kf;
+            d.kfi = t / a.tiles_per_kf;
+            kf = a.kfs + d.kfi;
             off = (t % a.tiles_per_kf) * TILE_PTS;
             const unsigned n = kf->n_proj;
             cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
+            d.tab = a.table + kf->table_begin;
+            d.n_ins = (int) kf->ins_count;
+            d.t0 = kf->ins_t0;
+            d.t_last = kf->ins_t_last;
+            d.inv_mean_dt = kf->inv_mean_dt;
         }
-        mbar_arrive_expect_tx(full + s, cnt * 32u); // release: tile_id[s] is visible to whoever passes the barrier
+        d.cnt = cnt;
+        d.off = off;
+        tdesc[s] = d;
+        mbar_arrive_expect_tx(full + s, cnt * 32u); // release: tdesc[s] is visible to whoever passes the barrier
         if (cnt) {
             unsigned char* dst = smem_raw + s * TILE_BYTES;
             const unsigned long long phys = wrap(kf->proj_begin + off, a.pts_cap);
@@ -359,25 +378,25 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
     int cur = -1;
     unsigned cur_kf = 0xffffffffu;
     KfView kv{};
-    unsigned n = 0;
     for (unsigned it = 0;; ++it) {
         const int s = it % DESKEW_STAGES;
         // keep the ring full: the stage freed by iteration it-1 takes the next tile.  Only warp 0 can wait here (for the
         // other warps to release that stage); the other warps run on, up to a full tile ahead of it.
         if (tid == 0) issue(it + DESKEW_STAGES - 1);
         mbar_wait(full + s, (it / DESKEW_STAGES) & 1);
-        const unsigned t = tile_id[s];
-        if (t >= total) break;
-        const unsigned kfi = t / a.tiles_per_kf;
-        KfState* __restrict__ kf = a.kfs + kfi;
-        if (kfi != cur_kf) { // new keyframe: reload the view, drop the cached interval
+        const TileDesc d = tdesc[s];
+        if (d.tile >= total) break;
+        const unsigned kfi = d.kfi;
+        if (kfi != cur_kf) { // other keyframe: other interval table, drop the cached interval
             cur_kf = kfi;
-            kv = kf_view(kf, a.table);
-            n = kf->n_proj;
             cur = -1;
         }
-        const unsigned off = (t % a.tiles_per_kf) * TILE_PTS;
-        const unsigned cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
+        kv.tab = d.tab;
+        kv.n_ins = d.n_ins;
+        kv.t0 = d.t0;
+        kv.t_last = d.t_last;
+        kv.inv_mean_dt = d.inv_mean_dt;
+        const unsigned off = d.off, cnt = d.cnt;
 
         if (cnt) {
             const float4* __restrict__ sp = reinterpret_cast<const float4*>(smem_raw + s * TILE_BYTES);

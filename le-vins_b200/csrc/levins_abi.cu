@@ -273,7 +273,7 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     pa.ring = ctx->ring_state.as<RingState>();
     pa.ext = ctx->ext;
     pa.c = ctx->consts;
-    k_prepare<<<1, 128, 0, ctx->stream>>>(pa);
+    k_prepare<<<1, 256, 0, ctx->stream>>>(pa);
     ctx->launches++;
     CU(cudaGetLastError());
 
@@ -872,7 +872,7 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
     pa.ext = ctx->ext;
     pa.c = ctx->consts;
     mark(0, true);
-    k_prepare<<<(unsigned) n_kf, 128, 0, ctx->stream>>>(pa);
+    k_prepare<<<(unsigned) n_kf, 256, 0, ctx->stream>>>(pa);
     mark(0, false);
     ctx->launches++;
     CU(cudaGetLastError());
