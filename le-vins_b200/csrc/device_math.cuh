@@ -74,8 +74,8 @@ struct Consts {
     float cell_guard;  // fast-path cell ids closer than this (in cells) to a rounding boundary are recomputed exactly
 };
 
-// per-keyframe state, device resident
-struct KfState {
+// per-keyframe state, device resident (a whole number of 16-byte chunks: k_deskew_bin prefetches it with cp.async)
+struct __align__(16) KfState {
     unsigned long long pt_begin, pt_count;
     unsigned long long ins_begin, ins_count;
     unsigned long long q_begin, q_count;
@@ -88,6 +88,7 @@ struct KfState {
     unsigned int m;
     double ins_t0, ins_t_last, inv_mean_dt;
 };
+static_assert(sizeof(KfState) % 16 == 0 && sizeof(KfState) <= 128, "KfState is copied in 16-byte chunks");
 
 // ------------------------------------------------------------------------------------------------
 // small algebra (column-major 3x3 like Eigen), mirrored summation order ((a0 b0 + a1 b1) + a2 b2)

@@ -226,7 +226,7 @@ constexpr int DESKEW_PPT = 4;
 constexpr int TILE_PTS = DESKEW_THREADS * DESKEW_PPT; // 1024 points = 32 KB
 constexpr int TILE_BYTES = TILE_PTS * 32;
 constexpr int DESKEW_STAGES = 3;
-constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 48 + DESKEW_STAGES * 64; // + full/empty mbarriers + tile descriptors
+constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 48 + DESKEW_STAGES * 64 + 2 * 128; // + mbarriers, tile descriptors, keyframe-state prefetch
 constexpr int DESKEW_BLOCK = DESKEW_THREADS; // 8 warps; lane 0 of warp 0 doubles as the TMA producer
 constexpr int DESKEW_PTS_PER_BLOCK = TILE_PTS;
 
@@ -240,7 +240,6 @@ struct DeskewArgs {
     unsigned long long* zbuf; // [n_kf][CELLS]
     PointXYZI* cloud_out;     // streaming only (n_kf == 1), nullable
     unsigned gen;             // z-buffer generation of this launch
-    unsigned* tile_counter;   // zeroed before the launch: dynamic tile hand-out
     Extrinsics ext;
     Consts c;
 };
@@ -330,25 +329,40 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
     }
     __syncthreads();
 
-    // Producer duty (thread 0).  Tiles are handed out dynamically in keyframe-major order (one atomic per tile), so at any
-    // time the ~300 tiles in flight belong to two or three keyframes -- their z-buffers stay L2-resident -- and no CTA is
-    // left idle at the end of the launch.  The it_t-th tile of this CTA goes into stage it_t % STAGES once all 8 warps
-    // have released it; a tile id >= total is the stop signal.
+    // Producer duty (thread 0).  CTA b takes tiles b, b + G, b + 2G, ... of the keyframe-major tile list: all CTAs move
+    // through the list together, so at any time the ~300 tiles in flight belong to two or three keyframes and their
+    // z-buffers stay L2-resident.  The keyframe state a tile needs is prefetched one iteration ahead with cp.async into
+    // shared memory, so that this thread (and with it warp 0) never waits on global memory; the it_t-th tile of the CTA
+    // goes into stage it_t % STAGES once all 8 warps have released it.  A tile id >= total is the stop signal.
+    KfState* kfcache = reinterpret_cast<KfState*>(tdesc + DESKEW_STAGES); // [2], 16-byte aligned
+    auto tile_of = [&](unsigned it_t) { return blockIdx.x + it_t * gridDim.x; };
+    auto prefetch_kf = [&](unsigned it_t) {
+        const unsigned t = tile_of(it_t);
+        if (t < total) {
+            const char* src = reinterpret_cast<const char*>(a.kfs + t / a.tiles_per_kf);
+            const unsigned dst = smem_u32(kfcache + (it_t & 1));
+#pragma unroll
+            for (int c = 0; c < (int) sizeof(KfState) / 16; c++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * c), "l"(src + 16 * c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     auto issue = [&](unsigned it_t) {
         const int s = it_t % DESKEW_STAGES;
+        asm volatile("cp.async.wait_group 0;" ::: "memory"); // the keyframe state of this tile has landed
         if (it_t >= DESKEW_STAGES) mbar_wait(empty + s, ((it_t / DESKEW_STAGES) - 1) & 1);
-        const unsigned t = atomicAdd(a.tile_counter, 1u);
-        unsigned cnt = 0;
-        const KfState* kf = nullptr;
-        unsigned off = 0;
+        const unsigned t = tile_of(it_t);
+        unsigned cnt = 0, off = 0;
+        unsigned long long pbegin = 0;
         TileDesc d{};
         d.tile = t;
         if (t < total) {
+            const KfState* kf = kfcache + (it_t & 1);
             d.kfi = t / a.tiles_per_kf;
-            kf = a.kfs + d.kfi;
             off = (t % a.tiles_per_kf) * TILE_PTS;
             const unsigned n = kf->n_proj;
             cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
+            pbegin = kf->proj_begin;
             d.tab = a.table + kf->table_begin;
             d.n_ins = (int) kf->ins_count;
             d.t0 = kf->ins_t0;
@@ -361,14 +375,16 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
         mbar_arrive_expect_tx(full + s, cnt * 32u); // release: tdesc[s] is visible to whoever passes the barrier
         if (cnt) {
             unsigned char* dst = smem_raw + s * TILE_BYTES;
-            const unsigned long long phys = wrap(kf->proj_begin + off, a.pts_cap);
+            const unsigned long long phys = wrap(pbegin + off, a.pts_cap);
             const unsigned long long room = a.pts_cap - phys; // ring: the tile may wrap around the end
             const unsigned first = room < cnt ? (unsigned) room : cnt;
             tma_bulk_g2s(dst, a.pts + phys, first * 32u, full + s);
             if (first < cnt) tma_bulk_g2s(dst + first * 32u, a.pts, (cnt - first) * 32u, full + s);
         }
+        prefetch_kf(it_t + 1);
     };
     if (tid == 0) {
+        prefetch_kf(0);
 #pragma unroll
         for (int i = 0; i < DESKEW_STAGES - 1; i++) issue(i);
     }

@@ -54,7 +54,6 @@ struct levins_ctx {
     uint64_t launches = 0;
     int num_sms = 148;
     bool deskew_attr_set = false;
-    DevBuf tile_counter;
 
     // ---- streaming state ----
     DevBuf ring;      // PointXYZIT x cfg.max_points
@@ -218,9 +217,6 @@ int launch_deskew(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_k
         CU(cudaFuncSetAttribute(k_deskew_bin<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
         ctx->deskew_attr_set = true;
     }
-    CU(ctx->tile_counter.ensure(sizeof(unsigned)));
-    CU(cudaMemsetAsync(ctx->tile_counter.p, 0, sizeof(unsigned), ctx->stream));
-    a.tile_counter = ctx->tile_counter.as<unsigned>();
     const unsigned grid = std::min<unsigned>(total, 2u * (unsigned) ctx->num_sms);
     if (ctx->consts.libm_mode == 0) {
         if (write_cloud)
@@ -446,7 +442,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_type, &ctx->b_xyzd, &ctx->b_flags, &ctx->b_zbuf,
-                      &ctx->b_cells, &ctx->tile_counter})
+                      &ctx->b_cells})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
