@@ -12,6 +12,8 @@
 // plus k_bin_cloud / k_compact / k_project / k_ring_append for the stage-wise ABI entry points.
 #pragma once
 
+#include <type_traits>
+
 #include "device_math.cuh"
 
 namespace lv {
@@ -717,16 +719,25 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32, 6) k_associate(const __grid_
 
     // The query's position in cell units.  Precision is irrelevant: the window and the mask below carry half a cell
     // of slack, and every candidate they keep is measured with the reference's exact f32 arithmetic afterwards.
-    const float el = atan2f(qy, sqrtf(qx * qx + qz * qz));
-    const float az = atan2f(qz, qx);
+    float rq, cq, ael;
     const float inv_ang = a.c.inv_angle_f, off = (float) a.c.half_offset;
-    const float rq = (el + off) * inv_ang, cq = (az - off) * inv_ang;
+    if (qz > 0.f && fabsf(qx) <= qz && fabsf(qy) <= qz) { // inside the 90-degree cone: both arguments lie in [-1, 1]
+        const float el = atan_poly(qy * rsqrtf(fmaf(qx, qx, qz * qz)));
+        rq = fmaf(el, inv_ang, 150.0f);
+        cq = fmaf(-atan_poly(__fdividef(qx, qz)), inv_ang, 150.0f);
+        ael = fabsf(el);
+    } else {
+        const float el = atan2f(qy, sqrtf(qx * qx + qz * qz));
+        const float az = atan2f(qz, qx);
+        rq = (el + off) * inv_ang;
+        cq = (az - off) * inv_ang;
+        ael = fabsf(el);
+    }
     const int rowq = (int) rintf(rq), colq = (int) rintf(cq);
     // Only points within the acceptance radius T = 3 sin(0.3 deg) (chord; 3.00002 cells of arc) can influence a result
     // (tracking.cc:573).  A point of cell (r, c) lies within +-0.5 cell of (r, c) in (row, col) angle, and by the
     // haversine formula its arc distance g to the query obeys  g^2 >= (1 - 3e-4) (dEl^2 + cos(el_q) cos(el_p) dAz^2),
     // |el_p| <= |el_q| + 0.91 deg.  Cells that cannot contain such a point are skipped (about 60 % of the window).
-    const float ael = fabsf(el);
     const float cmin = fmaxf(0.f, __cosf(ael) * __cosf(fminf(ael + 0.016f, 1.5707963f))) * 0.999f;
 
     // ---- candidates: scan the 9 x 13 window, keep live cells inside the mask, compact them across the warp ----
@@ -824,38 +835,45 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32, 6) k_associate(const __grid_
     int nn_c[5];
     float4 nn_p[5];
     int found = 0;
+    auto select5 = [&](auto nslots_tag) {
+        constexpr int NS = decltype(nslots_tag)::value;
 #pragma unroll
-    for (int r = 0; r < 5; r++) {
-        unsigned bd = dbits[0];
-        int bc = cid[0];
-        float4 bp = cand[0];
+        for (int r = 0; r < 5; r++) {
+            unsigned bd = dbits[0];
+            int bc = cid[0];
+            float4 bp = cand[0];
 #pragma unroll
-        for (int itc = 1; itc < 4; itc++)
-            if (dbits[itc] < bd || (dbits[itc] == bd && cid[itc] < bc)) {
-                bd = dbits[itc];
-                bc = cid[itc];
-                bp = cand[itc];
-            }
-        const unsigned m1 = __reduce_min_sync(0xffffffffu, bd);
-        const unsigned m2 = __reduce_min_sync(0xffffffffu, bd == m1 ? (unsigned) bc : 0xffffffffu);
-        const bool mine = (bd == m1) && ((unsigned) bc == m2);
-        const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-        nn_d[r] = m1;
-        nn_c[r] = (int) m2;
-        nn_p[r].x = __shfl_sync(0xffffffffu, bp.x, owner);
-        nn_p[r].y = __shfl_sync(0xffffffffu, bp.y, owner);
-        nn_p[r].z = __shfl_sync(0xffffffffu, bp.z, owner);
-        nn_p[r].w = __shfl_sync(0xffffffffu, bp.w, owner);
-        if (m1 != 0x7f800000u) found++;
-        if (mine) { // this lane owns the winner: retire it
-#pragma unroll
-            for (int itc = 0; itc < 4; itc++)
-                if (dbits[itc] == m1 && cid[itc] == (int) m2) {
-                    dbits[itc] = 0x7f800000u;
-                    cid[itc] = 0x7fffffff;
+            for (int itc = 1; itc < NS; itc++)
+                if (dbits[itc] < bd || (dbits[itc] == bd && cid[itc] < bc)) {
+                    bd = dbits[itc];
+                    bc = cid[itc];
+                    bp = cand[itc];
                 }
+            const unsigned m1 = __reduce_min_sync(0xffffffffu, bd);
+            const unsigned m2 = __reduce_min_sync(0xffffffffu, bd == m1 ? (unsigned) bc : 0xffffffffu);
+            const bool mine = (bd == m1) && ((unsigned) bc == m2);
+            const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+            nn_d[r] = m1;
+            nn_c[r] = (int) m2;
+            nn_p[r].x = __shfl_sync(0xffffffffu, bp.x, owner);
+            nn_p[r].y = __shfl_sync(0xffffffffu, bp.y, owner);
+            nn_p[r].z = __shfl_sync(0xffffffffu, bp.z, owner);
+            nn_p[r].w = __shfl_sync(0xffffffffu, bp.w, owner);
+            if (m1 != 0x7f800000u) found++;
+            if (mine) { // this lane owns the winner: retire it
+#pragma unroll
+                for (int itc = 0; itc < NS; itc++)
+                    if (dbits[itc] == m1 && cid[itc] == (int) m2) {
+                        dbits[itc] = 0x7f800000u;
+                        cid[itc] = 0x7fffffff;
+                    }
+            }
         }
-    }
+    };
+    if (count <= 32) // the usual case: at most one candidate per lane (warp-uniform branch)
+        select5(std::integral_constant<int, 1>());
+    else
+        select5(std::integral_constant<int, 4>());
 
     // hand the 5 neighbours to k_plane (one THREAD per feature there: the 5x3 QR runs at full lane efficiency
     // instead of 32 lanes repeating one feature's solve)
