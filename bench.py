@@ -238,16 +238,13 @@ def run_gpu(args):
     gather_buf = None
     if world > 1:
         dptr = ctx.batch_result_pointers()
-        local_xyzd = abi.device_tensor(torch, dptr["xyz_depth"], (nq, 4), torch.float32, local_rank)
-        local_type = abi.device_tensor(torch, dptr["type"], (nq,), torch.int8, local_rank)
-        gather_xyzd = torch.empty((world * nq, 4), dtype=torch.float32, device=dev)
-        gather_type = torch.empty((world * nq,), dtype=torch.int8, device=dev)
-        gather_buf = (local_xyzd, local_type, gather_xyzd, gather_type)
+        assert dptr["type"] == dptr["xyz_depth"] + 16 * nq  # one contiguous block: xyz_depth then type
+        local = abi.device_tensor(torch, dptr["xyz_depth"], (17 * nq,), torch.uint8, local_rank)
+        gather_buf = (local, torch.empty((world * 17 * nq,), dtype=torch.uint8, device=dev))
 
     def gather():
-        if gather_buf is not None:
-            dist.all_gather_into_tensor(gather_buf[2], gather_buf[0])
-            dist.all_gather_into_tensor(gather_buf[3], gather_buf[1])
+        if gather_buf is not None:  # one collective for depths + types of all ranks
+            dist.all_gather_into_tensor(gather_buf[1], gather_buf[0])
 
     def barrier():
         if world > 1:

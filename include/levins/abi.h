@@ -195,7 +195,8 @@ int levins_batch_download(levins_ctx *ctx, int8_t *type, float *xyz_depth, int32
                           uint32_t *m);
 /* Device addresses of the result arrays of the resident batch (type: int8[n_queries], xyz_depth: float[4*n_queries],
  * flags: int32[n_queries]), valid until the next levins_batch_upload.  For exchange steps that stay on the device
- * (e.g. an NCCL all-gather of the depths issued on the same stream). */
+ * (e.g. an NCCL all-gather of the depths issued on the same stream).  xyz_depth and type are one contiguous block:
+ * type == (int8_t *) xyz_depth + 16 * n_queries, so 17 * n_queries bytes from xyz_depth carry both. */
 int levins_batch_result_pointers(levins_ctx *ctx, void **type, void **xyz_depth, void **flags);
 /* Waves: how many keyframes share one set of launches (their z-buffers stay L2-resident). 0 = default. */
 int levins_batch_set_wave(levins_ctx *ctx, int keyframes_per_wave);

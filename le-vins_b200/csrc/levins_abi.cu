@@ -76,7 +76,10 @@ struct levins_ctx {
 
     // ---- batch state ----
     DevBuf b_pts, b_ins, b_table, b_queries, b_kfs;
-    DevBuf b_type, b_xyzd, b_flags, b_nn, b_nn_meta;
+    DevBuf b_results; // xyz_depth (16 B / query) immediately followed by type (1 B / query): one contiguous block, so that an
+                      // exchange step can move both with a single collective
+    size_t b_results_nq = 0;
+    DevBuf b_flags, b_nn, b_nn_meta;
     DevBuf b_zbuf, b_cells;
     std::vector<levins_keyframe_desc> b_descs;
     size_t b_nq = 0, b_npts = 0, b_nins = 0;
@@ -441,7 +444,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
     for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
-                      &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_type, &ctx->b_xyzd, &ctx->b_flags, &ctx->b_zbuf,
+                      &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
                       &ctx->b_cells})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
@@ -805,8 +808,8 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
     CU(ctx->b_table.ensure(table_entries * sizeof(Interval)));
     CU(ctx->b_queries.ensure(std::max<size_t>(n_queries, 1) * 12));
     CU(ctx->b_kfs.ensure(n_kf * sizeof(KfState)));
-    CU(ctx->b_type.ensure(std::max<size_t>(n_queries, 1)));
-    CU(ctx->b_xyzd.ensure(std::max<size_t>(n_queries, 1) * 16));
+    CU(ctx->b_results.ensure(std::max<size_t>(n_queries, 1) * 17));
+    ctx->b_results_nq = std::max<size_t>(n_queries, 1);
     CU(ctx->b_flags.ensure(std::max<size_t>(n_queries, 1) * 4));
     CU(ctx->b_nn.ensure(std::max<size_t>(n_queries, 1) * 80));
     CU(ctx->b_nn_meta.ensure(std::max<size_t>(n_queries, 1) * 8));
@@ -935,8 +938,8 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         pl.nn_meta = ctx->b_nn_meta.as<uint2>();
         pl.q_begin = 0;
         pl.q_count = ctx->b_nq;
-        pl.type = ctx->b_type.as<int8_t>();
-        pl.xyz_depth = ctx->b_xyzd.as<float4>();
+        pl.type = ctx->b_results.as<int8_t>() + ctx->b_results_nq * 16;
+        pl.xyz_depth = ctx->b_results.as<float4>();
         pl.flags = ctx->b_flags.as<int32_t>();
         pl.c = ctx->consts;
         mark(2, true);
@@ -951,8 +954,8 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
 extern "C" int levins_batch_result_pointers(levins_ctx* ctx, void** type, void** xyz_depth, void** flags) {
     if (!ctx) return LEVINS_ERR_ARG;
     if (!ctx->b_valid) return fail(ctx, LEVINS_ERR_STATE, "no batch");
-    if (type) *type = ctx->b_type.p;
-    if (xyz_depth) *xyz_depth = ctx->b_xyzd.p;
+    if (type) *type = ctx->b_results.as<int8_t>() + ctx->b_results_nq * 16;
+    if (xyz_depth) *xyz_depth = ctx->b_results.p;
     if (flags) *flags = ctx->b_flags.p;
     return LEVINS_OK;
 }
@@ -984,8 +987,9 @@ extern "C" int levins_batch_download(levins_ctx* ctx, int8_t* type, float* xyz_d
     CU(cudaSetDevice(ctx->device));
     if (!ctx->b_valid) return fail(ctx, LEVINS_ERR_STATE, "no batch");
     const size_t nq = ctx->b_nq, n_kf = ctx->b_descs.size();
-    if (type && nq) CU(cudaMemcpyAsync(type, ctx->b_type.p, nq, cudaMemcpyDeviceToHost, ctx->stream));
-    if (xyz_depth && nq) CU(cudaMemcpyAsync(xyz_depth, ctx->b_xyzd.p, nq * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    if (type && nq)
+        CU(cudaMemcpyAsync(type, ctx->b_results.as<int8_t>() + ctx->b_results_nq * 16, nq, cudaMemcpyDeviceToHost, ctx->stream));
+    if (xyz_depth && nq) CU(cudaMemcpyAsync(xyz_depth, ctx->b_results.p, nq * 16, cudaMemcpyDeviceToHost, ctx->stream));
     if (flags && nq) CU(cudaMemcpyAsync(flags, ctx->b_flags.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
     std::vector<KfState> kfs;
     if (n_projected || m) {

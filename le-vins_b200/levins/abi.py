@@ -277,5 +277,5 @@ class _CudaArray:
 
 
 def device_tensor(torch, ptr, shape, dtype, device_index):
-    typestr = {torch.float32: "<f4", torch.int8: "|i1", torch.int32: "<i4"}[dtype]
+    typestr = {torch.float32: "<f4", torch.int8: "|i1", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
     return torch.as_tensor(_CudaArray(ptr, shape, typestr), device=torch.device("cuda", device_index))
