@@ -696,6 +696,7 @@ struct AssocArgs {
     unsigned long long pts_cap;
     const Interval* table;
     unsigned gen;
+    int count_cells; // FUSED: also count the live cells of the z-buffer (M) in this launch
     Extrinsics ext;
     // outputs
     float4* nn;       // 5 per query: neighbours (unit vector + range) for k_plane
@@ -711,7 +712,7 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32, 6) k_associate(const __grid_
     const int lane = threadIdx.x & 31;
     const unsigned f = blockIdx.x * ASSOC_WARPS + (threadIdx.x >> 5);
     if (f >= kf->q_count) {
-        if (FUSED) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf);
+        if (FUSED && a.count_cells) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf);
         return;
     }
     const size_t qi = kf->q_begin + f;
@@ -897,7 +898,7 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32, 6) k_associate(const __grid_
         }
     }
     // M (number of non-empty cells), piggy-backed on this launch: every block counts its slice of the z-buffer
-    if (FUSED) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf);
+    if (FUSED && a.count_cells) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf);
 }
 
 // ------------------------------------------------------------------------------------------------

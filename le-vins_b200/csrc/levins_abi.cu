@@ -54,6 +54,8 @@ struct levins_ctx {
     uint64_t launches = 0;
     int num_sms = 148;
     bool deskew_attr_set = false;
+    cudaStream_t side = nullptr; // k_count_cells runs here, overlapped with the latency-bound k_associate
+    cudaEvent_t ev_binned = nullptr, ev_counted = nullptr;
 
     // ---- streaming state ----
     DevBuf ring;      // PointXYZIT x cfg.max_points
@@ -331,6 +333,7 @@ int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused) 
     aa.pts_cap = ctx->cfg.max_points;
     aa.table = ctx->s_table.as<Interval>();
     aa.gen = ctx->s_gen;
+    aa.count_cells = 1; // one keyframe: counting M inside this launch is free
     aa.ext = ctx->ext;
     aa.nn = ctx->s_nn.as<float4>();
     aa.nn_meta = ctx->s_nn_meta.as<uint2>();
@@ -448,6 +451,9 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
                       &ctx->b_cells})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->ev_binned) cudaEventDestroy(ctx->ev_binned);
+    if (ctx->ev_counted) cudaEventDestroy(ctx->ev_counted);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -848,6 +854,11 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         ctx->b_gen = 255; // fresh memory: force a clear at the first generation
         ctx->b_wave_alloc = wave;
     }
+    if (!ctx->side) {
+        CU(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->ev_binned, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_counted, cudaEventDisableTiming));
+    }
     size_t ev = 0;
     ctx->ev_spans.clear();
     auto mark = [&](int kind, bool begin) {
@@ -897,11 +908,20 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         da.ext = ctx->ext;
         da.c = ctx->consts;
         if (max_pts) {
+            if (k0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_counted, 0)); // the slots are about to be reused
             mark(1, true);
             r = launch_deskew(ctx, da, max_pts, (unsigned) nw, false);
             mark(1, false);
             if (r) return r;
         }
+        // M (non-empty cells per keyframe) streams the z-buffers once more; do it on the side stream while the
+        // latency-bound k_associate occupies the main one
+        CU(cudaEventRecord(ctx->ev_binned, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->side, ctx->ev_binned, 0));
+        k_count_cells<<<dim3(32, nw), 256, 0, ctx->side>>>(ctx->b_kfs.as<KfState>() + k0, ctx->b_zbuf.as<unsigned long long>(), ctx->b_gen);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->ev_counted, ctx->side));
         if (max_q) {
             AssocArgs aa{};
             aa.kfs = ctx->b_kfs.as<KfState>() + k0;
@@ -913,6 +933,7 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             aa.pts_cap = ~0ull;
             aa.table = ctx->b_table.as<Interval>();
             aa.gen = ctx->b_gen;
+            aa.count_cells = 0; // M is counted by k_count_cells on the side stream, concurrently with this kernel
             aa.ext = ctx->ext;
             aa.nn = ctx->b_nn.as<float4>();
             aa.nn_meta = ctx->b_nn_meta.as<uint2>();
@@ -924,13 +945,9 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             mark(3, false);
             ctx->launches++;
             CU(cudaGetLastError());
-        } else { // no feature kernel to piggy-back the cell count on
-            k_count_cells<<<dim3(64, nw), 256, 0, ctx->stream>>>(ctx->b_kfs.as<KfState>() + k0, ctx->b_zbuf.as<unsigned long long>(),
-                                                                 ctx->b_gen);
-            ctx->launches++;
-            CU(cudaGetLastError());
         }
     }
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_counted, 0)); // join the side stream
     if (ctx->b_nq) { // plane fits for every feature of the batch in one launch (one thread per feature)
         PlaneArgs pl{};
         pl.queries = ctx->b_queries.as<float>();
