@@ -1060,6 +1060,99 @@ int orc_plane_estimation(const orc_point_xyzi *points, size_t n, double threshol
     return 1;
 }
 
+/* symmetric 3x3 eigen-decomposition (cyclic Jacobi); stands in for Eigen::EigenSolver on the covariance at
+ * pointcloud.cc:132-134.  w: eigenvalues, v: eigenvectors as columns (row-major). */
+static void sym_eigen3(const double a_in[9], double w[3], double v[9]) {
+    double a[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) a[i][j] = a_in[3 * i + j];
+    for (int sweep = 0; sweep < 60; sweep++) {
+        double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (a[p][q] == 0.0) continue;
+                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                for (int k = 0; k < 3; k++) {
+                    double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = cs * akp - sn * akq;
+                    a[k][q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < 3; k++) {
+                    double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = cs * apk - sn * aqk;
+                    a[q][k] = sn * apk + cs * aqk;
+                }
+                for (int k = 0; k < 3; k++) {
+                    double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = cs * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + cs * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; i++) {
+        w[i] = a[i][i];
+        for (int j = 0; j < 3; j++) v[3 * i + j] = V[i][j];
+    }
+}
+
+/* pointcloud.cc:111-190  PointCloudCommon::pointToPlaneStd (no call site in the reference) */
+double orc_point_to_plane_std(const orc_point_xyzi *nearest, size_t n, const orc_point_xyzi *target, double point_std) {
+    const double pvv = point_std * point_std; /* :113-114 */
+    const double inv = 1.0 / (double) n;      /* :117 */
+    double cov[9] = {0}, center[3] = {0};
+    for (size_t i = 0; i < n; i++) { /* :120-126 */
+        double pv[3] = {nearest[i].x, nearest[i].y, nearest[i].z};
+        for (int r = 0; r < 3; r++) {
+            center[r] += pv[r];
+            for (int c = 0; c < 3; c++) cov[3 * r + c] += pv[r] * pv[c];
+        }
+    }
+    for (int r = 0; r < 3; r++) center[r] *= inv; /* :127 */
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) cov[3 * r + c] = cov[3 * r + c] * inv - center[r] * center[c]; /* :128 */
+    double evals[3], evecs[9];
+    sym_eigen3(cov, evals, evecs); /* :131-136 */
+    int emin = 0;                  /* :138-140 */
+    for (int m = 1; m < 3; m++)
+        if (evals[m] < evals[emin]) emin = m;
+    double nrm[3] = {evecs[emin], evecs[3 + emin], evecs[6 + emin]}; /* :151 */
+    double plane_cov[6][6];
+    memset(plane_cov, 0, sizeof(plane_cov));
+    for (size_t i = 0; i < n; i++) { /* :160-176 */
+        double d[3] = {nearest[i].x - center[0], nearest[i].y - center[1], nearest[i].z - center[2]};
+        double F[3][3];
+        memset(F, 0, sizeof(F));
+        for (int m = 0; m < 3; m++) {
+            if (m == emin) continue;
+            double em[3] = {evecs[m], evecs[3 + m], evecs[6 + m]};
+            double scale = inv / (evals[emin] - evals[m]);
+            double de = d[0] * em[0] + d[1] * em[1] + d[2] * em[2], dn = d[0] * nrm[0] + d[1] * nrm[1] + d[2] * nrm[2];
+            for (int c = 0; c < 3; c++) F[m][c] = scale * (de * nrm[c] + dn * em[c]);
+        }
+        double J[6][3];
+        memset(J, 0, sizeof(J));
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++)
+                for (int m = 0; m < 3; m++) J[r][c] += evecs[3 * r + m] * F[m][c];
+        for (int r = 0; r < 3; r++) J[3 + r][r] = inv;
+        for (int r = 0; r < 6; r++)
+            for (int c = 0; c < 6; c++) {
+                double sum = 0;
+                for (int k = 0; k < 3; k++) sum += J[r][k] * J[c][k];
+                plane_cov[r][c] += pvv * sum;
+            }
+    }
+    double jac[6] = {target->x - center[0], target->y - center[1], target->z - center[2], -nrm[0], -nrm[1], -nrm[2]}; /* :179-181 */
+    double var = 0;
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c < 6; c++) var += jac[r] * plane_cov[r][c] * jac[c]; /* :184 */
+    var += pvv * (nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);   /* :186 */
+    return sqrt(var);
+}
+
 /* ------------------------------------------------------------------------------------------
  * tracking.cc:564-634  Tracking::depthAssociationPlaneFitting
  * ------------------------------------------------------------------------------------------ */

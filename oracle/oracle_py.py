@@ -63,6 +63,8 @@ def lib():
         L.orc_point_square_distance.argtypes = [vp, vp]
         L.orc_plane_estimation.restype = i32
         L.orc_plane_estimation.argtypes = [vp, sz, dbl, vp, vp, vp, vp]
+        L.orc_point_to_plane_std.restype = dbl
+        L.orc_point_to_plane_std.argtypes = [vp, sz, vp, dbl]
         L.orc_ring_create.restype = vp
         L.orc_ring_destroy.argtypes = [vp]
         L.orc_ring_append.argtypes = [vp, vp, sz]
@@ -204,6 +206,12 @@ def plane_estimation(points, threshold):
     n, ninv, dist, nd = np.zeros(3), np.zeros(1), np.zeros(5), np.zeros(1, np.int32)
     ok = lib().orc_plane_estimation(_p(pts), len(pts), float(threshold), _p(n), _p(ninv), _p(dist), _p(nd))
     return bool(ok), n, float(ninv[0]), dist[: int(nd[0])]
+
+
+def point_to_plane_std(nearest, target, point_std):
+    pts = _c(nearest, XYZI)
+    t = _c(np.array([target], dtype=XYZI), XYZI)
+    return float(lib().orc_point_to_plane_std(_p(pts), len(pts), _p(t), float(point_std)))
 
 
 class Ring:
