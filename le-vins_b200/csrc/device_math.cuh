@@ -35,7 +35,9 @@ static_assert(sizeof(PointXYZIT) == 32 && sizeof(PointXYZI) == 32 && sizeof(InsS
 
 // One INS interval [i-1, i] pre-digested for the per-point deskew ("stage 1 algebra"):
 //   p_c0 = A * Rod(k, -s*theta) * (R_bc p_c1 + t_bc) + c0 + s * c1,   s = (t - ts0) * inv_dts
-// entry 0 of each keyframe's table is the out-of-window fallback (newest state, misc.cc:74-77).
+// entry 0 of each keyframe's table is the out-of-window fallback (newest state, misc.cc:74-77); its (t_lo, t_hi) are
+// (time of the last sample, time of the first sample), which makes entry_brackets() true exactly for the times OUTSIDE
+// the window (see entry_brackets).
 struct __align__(16) Interval {
     double t_lo, t_hi;   // IMU times of samples i-1, i (search keys, misc.cc:40-43)
     double ts0, inv_dts; // state time of sample i-1 and 1 / (ts1 - ts0)   (misc.cc:88)
@@ -44,7 +46,7 @@ struct __align__(16) Interval {
     double theta;        // its angle
     double c0[3];        // R0^T (p0 - t0)
     double c1[3];        // R0^T (p1 - p0)
-    double pad;
+    double fast;         // != 0: entry_brackets() may be used on (t_lo, t_hi) and theta is in sin_omc_small()'s range
 };
 static_assert(sizeof(Interval) == 192, "interval entry");
 
@@ -516,10 +518,28 @@ __device__ __forceinline__ void load_entry(const Interval* __restrict__ it, Entr
 // does the cached interval entry (cur > 0) bracket time t, i.e. t_lo <= t < t_hi?  GPS seconds of week are positive,
 // so IEEE doubles order like their bit patterns and the test is one unsigned 64-bit compare on the ALU pipe:
 // (bits(t) - bits(t_lo)) < (bits(t_hi) - bits(t_lo)); a negative or NaN time wraps to a huge value and misses.
+// With t_lo > t_hi > 0 (the fallback entry: t_lo = last sample, t_hi = first sample) the width wraps and the same
+// compare is true exactly when NOT (t_hi <= t < t_lo), i.e. for the times the reference sends to the fallback pose
+// (misc.cc:28-30), negative times included.
+__device__ __forceinline__ bool key_brackets(unsigned long long lo, unsigned long long width, double t) {
+    return ((unsigned long long) __double_as_longlong(t) - lo) < width;
+}
 __device__ __forceinline__ bool entry_brackets(const EntryRegs& e, double t) {
     const unsigned long long lo = (unsigned long long) __double_as_longlong(e.t_lo);
     const unsigned long long width = (unsigned long long) __double_as_longlong(e.t_hi) - lo;
-    return ((unsigned long long) __double_as_longlong(t) - lo) < width;
+    return key_brackets(lo, width, t);
+}
+
+// the same entry through plain loads: shared memory (k_deskew_bin stages the entries of a chunk next to its points) or,
+// with a generic pointer, either space
+__device__ __forceinline__ void load_entry_shared(const Interval* it, EntryRegs& e) {
+    const double2* p = reinterpret_cast<const double2*>(it);
+    const double2 v0 = p[0], v1 = p[1], v2 = p[2], v3 = p[3], v4 = p[4], v5 = p[5], v6 = p[6], v7 = p[7], v8 = p[8], v9 = p[9],
+                  v10 = p[10], v11 = p[11];
+    e.t_lo = v0.x; e.t_hi = v0.y; e.ts0 = v1.x; e.inv_dts = v1.y;
+    e.A0 = v2.x; e.A1 = v2.y; e.A2 = v3.x; e.A3 = v3.y; e.A4 = v4.x; e.A5 = v4.y; e.A6 = v5.x; e.A7 = v5.y; e.A8 = v6.x;
+    e.kx = v6.y; e.ky = v7.x; e.kz = v7.y; e.theta = v8.x;
+    e.c0x = v8.y; e.c0y = v9.x; e.c0z = v9.y; e.c1x = v10.x; e.c1y = v10.y; e.c1z = v11.x;
 }
 
 // Make `e` the entry for time t (misc.cc:25-60 semantics).  Fast when e already brackets t.  Otherwise the entry at the
@@ -543,6 +563,21 @@ __device__ __forceinline__ void seek_entry(const KfView& kv, double t, EntryRegs
         load_entry(kv.tab + idx, e);
         cur = idx;
     }
+}
+
+// The entry for time t straight from the keyframe's table in global memory (misc.cc:25-60 semantics), no cached state:
+// the rare path of k_deskew_bin (points whose interval is not one of the two staged with their chunk).
+__device__ __noinline__ const Interval* find_entry_global(const KfState* __restrict__ kf, const Interval* __restrict__ table, double t) {
+    const Interval* __restrict__ tab = table + kf->table_begin;
+    const int n = (int) kf->ins_count;
+    int idx = 0;
+    if (!(n < 2 || kf->ins_t0 > t || kf->ins_t_last <= t)) { // misc.cc:28-30
+        int g = 1 + (int) ((t - kf->ins_t0) * kf->inv_mean_dt);
+        g = min(max(g, 1), n - 1);
+        const double2 ab = __ldg(reinterpret_cast<const double2*>(tab + g));
+        idx = ((ab.x <= t) && (t < ab.y)) ? g : find_interval_slow(tab, n, t, g, 1, n - 1);
+    }
+    return tab + idx;
 }
 
 // sin(phi) and 1 - cos(phi) to full double precision for the small angles of one INS interval

@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
         if (j == 0) { // out-of-window fallback: newest state, no interpolation (misc.cc:74-77)
             const InsSample s = w[nins - 1];
             quat_to_matrix(s.q, Rq);
-            e.t_lo = e.t_hi = 0;
+            // (last, first): entry_brackets() is then true exactly outside the window (device_math.cuh)
+            e.t_lo = nins >= 2 ? s.time : 0.0;
+            e.t_hi = nins >= 2 ? w[0].time : 0.0;
             e.ts0 = 0;
             e.inv_dts = 0;
             e.k[0] = 1;
@@ -212,39 +214,100 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
         for (int r = 0; r < 3; r++)
 #pragma unroll
             for (int cI = 0; cI < 3; cI++) e.A[3 * r + cI] = C[3 * cI + r];
-        e.pad = 0;
+        // the one-compare bracket test needs positive, increasing times; the straight-line deskew a small angle
+        const bool ordered = j == 0 ? (e.t_hi > 0 && e.t_lo > e.t_hi) : (e.t_lo > 0 && e.t_hi > e.t_lo);
+        e.fast = (ordered && e.theta * e.theta < 2.44140625e-4) ? 1.0 : 0.0;
         tab[j] = e;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_deskew_bin: persistent CTAs, each walking a contiguous range of 1 024-point tiles.  The raw points (32 B each)
-// are streamed HBM -> shared memory by the TMA unit (cp.async.bulk, 1-D, completion on an mbarrier) through a
-// 3-stage ring, so that the memory system always has ~64 KB per CTA in flight while all 8 warps do arithmetic; the
-// per-point math never waits on an HBM load.  Each thread handles 4 points of a tile (lane-strided), keeps the INS
-// interval entry in registers across points and tiles, and issues its z-buffer probes for the 4 points together.
+// k_deskew_bin: persistent warps.  Every warp is its own pipeline: it walks the chunk list (128 consecutive points =
+// 4 KB per chunk; warp g takes chunks g, g + W, g + 2W, ...) and lane 0 streams chunk it+2 HBM -> shared memory with the
+// TMA unit (cp.async.bulk, 1-D, completion on the warp's own mbarrier) while the warp does the arithmetic of chunk it.
+// With the points travel the two INS-interval entries the chunk can need (the one of its first point, found by
+// k_chunk_desc, and its successor), so that the per-point math never waits on global memory and the warps of a CTA
+// never wait for each other.  Each thread handles 4 consecutive points; cell ids that the polynomial path cannot decide
+// are queued per warp and settled 32 at a time by the exact path.
 // ------------------------------------------------------------------------------------------------
 constexpr int DESKEW_PPT = 4;
-constexpr int TILE_PTS = DESKEW_THREADS * DESKEW_PPT; // 1024 points = 32 KB
-constexpr int TILE_BYTES = TILE_PTS * 32;
+constexpr int DESKEW_WARPS = DESKEW_THREADS / 32;
+constexpr int CHUNK_PTS = 32 * DESKEW_PPT; // 128 points = 4 KB: one warp, one iteration
+constexpr int CHUNK_BYTES = CHUNK_PTS * 32;
 constexpr int DESKEW_STAGES = 3;
-constexpr int DESKEW_SMEM = DESKEW_STAGES * TILE_BYTES + 48 + DESKEW_STAGES * 64 + 2 * 128; // + mbarriers, tile descriptors, keyframe-state prefetch
-constexpr int DESKEW_BLOCK = DESKEW_THREADS; // 8 warps; lane 0 of warp 0 doubles as the TMA producer
-constexpr int DESKEW_PTS_PER_BLOCK = TILE_PTS;
+constexpr int STAGE_ENT_OFF = CHUNK_BYTES;                        // two interval entries (2 x 192 B)
+constexpr int STAGE_HDR_OFF = STAGE_ENT_OFF + 2 * (int) sizeof(Interval); // {cnt}
+constexpr int STAGE_BYTES = STAGE_HDR_OFF + 16;
+constexpr int AMBQ = 32; // undecided cell ids queued per warp
+constexpr int WARP_BAR_OFF = DESKEW_STAGES * STAGE_BYTES;
+constexpr int WARP_Q_OFF = WARP_BAR_OFF + 32;
+constexpr int WARP_QKF_OFF = WARP_Q_OFF + AMBQ * 16;
+constexpr int WARP_SMEM = WARP_QKF_OFF + AMBQ * 4;
+constexpr int DESKEW_SMEM = DESKEW_WARPS * WARP_SMEM; // 113 280 B: two CTAs per SM
+constexpr int DESKEW_BLOCK = DESKEW_THREADS;
+static_assert(STAGE_BYTES % 16 == 0 && WARP_SMEM % 16 == 0 && WARP_Q_OFF % 16 == 0, "TMA / vector alignment");
+static_assert(2 * (DESKEW_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
+
+// what lane 0 needs to fetch one chunk, written by k_chunk_desc
+struct __align__(16) ChunkDesc {
+    unsigned long long phys; // physical index of the chunk's first point in the pool / ring
+    unsigned ent0;           // absolute index (into the interval-table pool) of the entry of the chunk's first point
+    unsigned cw;             // bits 0-7: points in the chunk (0 = empty); bits 8-31: signed offset of the second entry
+};
 
 struct DeskewArgs {
     KfState* kfs; // first keyframe of this launch
-    unsigned n_kf;         // keyframes in this launch
-    unsigned tiles_per_kf; // ceil(max points per keyframe / TILE_PTS)
+    unsigned n_kf;          // keyframes in this launch
+    unsigned chunks_per_kf; // ceil(max points per keyframe / CHUNK_PTS)
     const PointXYZIT* pts;
     unsigned long long pts_cap;
     const Interval* table;
+    ChunkDesc* chunks;        // [n_kf][chunks_per_kf]
     unsigned long long* zbuf; // [n_kf][CELLS]
     PointXYZI* cloud_out;     // streaming only (n_kf == 1), nullable
     unsigned gen;             // z-buffer generation of this launch
     Extrinsics ext;
     Consts c;
 };
+
+// k_chunk_desc: one thread per chunk.  The entry index is only a hint for k_deskew_bin (every point still checks that
+// its entry brackets it), so any answer is correct; the right one is fast.
+__global__ void __launch_bounds__(256) k_chunk_desc(const __grid_constant__ DeskewArgs a) {
+    const unsigned c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= a.n_kf * a.chunks_per_kf) return;
+    const unsigned kfi = c / a.chunks_per_kf;
+    const unsigned off = (c - kfi * a.chunks_per_kf) * CHUNK_PTS;
+    const KfState* __restrict__ kf = a.kfs + kfi;
+    const unsigned n = kf->n_proj;
+    ChunkDesc d;
+    d.phys = 0;
+    d.ent0 = 0;
+    d.cw = 0;
+    if (off < n) {
+        const unsigned cnt = min((unsigned) CHUNK_PTS, n - off);
+        const unsigned long long phys = wrap(kf->proj_begin + off, a.pts_cap);
+        const double t = a.pts[phys].time + a.ext.td_b_l; // le_vins.cc:455
+        const Interval* __restrict__ tab = a.table + kf->table_begin;
+        const int nins = (int) kf->ins_count;
+        int idx = 0, nxt = 0;
+        if (!(nins < 2 || kf->ins_t0 > t || kf->ins_t_last <= t)) { // misc.cc:28-30
+            int g = 1 + (int) ((t - kf->ins_t0) * kf->inv_mean_dt);
+            g = min(max(g, 1), nins - 1);
+            const double2 ab = __ldg(reinterpret_cast<const double2*>(tab + g));
+            idx = ((ab.x <= t) && (t < ab.y)) ? g : find_interval_slow(tab, nins, t, g, 1, nins - 1);
+        }
+        // the entry the later points of the chunk move on to: the next interval, the fallback after the last one,
+        // the first interval for a chunk that starts before the window
+        if (idx > 0)
+            nxt = idx + 1 < nins ? idx + 1 : 0;
+        else
+            nxt = (nins >= 2 && kf->ins_t0 > t) ? 1 : 0;
+        d.phys = phys;
+        d.ent0 = (unsigned) (kf->table_begin + idx);
+        d.cw = cnt | ((unsigned) (nxt - idx) << 8);
+    }
+    a.chunks[c] = d;
+}
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -302,126 +365,101 @@ __device__ __forceinline__ int cell_id(float x, float y, float z, const Consts& 
     return cell;
 }
 
-// per-stage tile descriptor: the producer reads the keyframe state once and passes it through shared memory, so the
-// consumers never wait on global memory for it
-struct __align__(16) TileDesc {
-    const Interval* tab;
-    double t0, t_last, inv_mean_dt;
-    unsigned tile, cnt, off, kfi;
-    int n_ins, pad;
-};
+// lane 0: start the copies of one chunk into a stage of the warp's ring
+__device__ __forceinline__ void issue_chunk(const DeskewArgs& a, const ChunkDesc& d, unsigned char* stage, unsigned long long* bar) {
+    const unsigned cnt = d.cw & 0xffu;
+    *reinterpret_cast<unsigned*>(stage + STAGE_HDR_OFF) = cnt;
+    if (cnt == 0) {
+        mbar_arrive(bar); // release: the header is visible to whoever passes the barrier
+        return;
+    }
+    mbar_arrive_expect_tx(bar, cnt * 32u + 2u * (unsigned) sizeof(Interval));
+    const Interval* e0 = a.table + d.ent0;
+    const Interval* e1 = e0 + ((int) d.cw >> 8);
+    tma_bulk_g2s(stage + STAGE_ENT_OFF, e0, (unsigned) sizeof(Interval), bar);
+    tma_bulk_g2s(stage + STAGE_ENT_OFF + sizeof(Interval), e1, (unsigned) sizeof(Interval), bar);
+    const unsigned long long room = a.pts_cap - d.phys; // ring: the chunk may wrap around the end
+    const unsigned first = room < cnt ? (unsigned) room : cnt;
+    tma_bulk_g2s(stage, a.pts + d.phys, first * 32u, bar);
+    if (first < cnt) tma_bulk_g2s(stage + first * 32u, a.pts, (cnt - first) * 32u, bar);
+}
+
+// settle the queued cell ids of a warp with the exact path (all lanes busy instead of one lane per rare case)
+template <int LIBM_MODE>
+__device__ __noinline__ void flush_undecided(const float4* q, const unsigned* qkf, unsigned n, unsigned long long* zbuf, unsigned gen,
+                                             const Consts& c) {
+    const unsigned lane = threadIdx.x & 31;
+    __syncwarp();
+    if (lane < n) {
+        const float4 v = q[lane];
+        const int cell = cell_of_point<LIBM_MODE>(v.x, v.y, v.z, c);
+        const float range = sqrtf(v3f_sqnorm(v.x, v.y, v.z)); // tracking.cc:330
+        if (cell >= 0 && (range < FLT_MAX)) atomicMin(zbuf + (size_t) qkf[lane] * CELLS + cell, key_make(gen, range, __float_as_uint(v.w)));
+    }
+    __syncwarp();
+}
 
 template <int LIBM_MODE, bool WRITE_CLOUD>
 __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + DESKEW_STAGES * TILE_BYTES);
-    unsigned long long* empty = full + DESKEW_STAGES;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = smem_raw + warp * WARP_SMEM;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(wbase + WARP_BAR_OFF);
+    float4* q_pt = reinterpret_cast<float4*>(wbase + WARP_Q_OFF);
+    unsigned* q_kf = reinterpret_cast<unsigned*>(wbase + WARP_QKF_OFF);
 
-    TileDesc* tdesc = reinterpret_cast<TileDesc*>(empty + DESKEW_STAGES); // what each stage holds (written by the producer)
-    const unsigned total = a.n_kf * a.tiles_per_kf;
+    const unsigned W = gridDim.x * DESKEW_WARPS; // the 8 warps of a CTA take 8 neighbouring chunks (32 KB of one keyframe)
+    const unsigned cpk = a.chunks_per_kf, total = a.n_kf * cpk;
+    unsigned c = blockIdx.x * DESKEW_WARPS + warp;
+    if (c >= total) return;
+    unsigned kfi = c / cpk, rem = c - kfi * cpk; // keyframe and chunk-in-keyframe of chunk c, advanced incrementally
+    const unsigned Wq = W / cpk, Wr = W - Wq * cpk;
 
-    if (tid == 0) {
+    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < DESKEW_STAGES; s++) {
-            mbar_init(full + s, 1);
-            mbar_init(empty + s, DESKEW_THREADS / 32); // one arrival per consumer warp
-        }
+        for (int s = 0; s < DESKEW_STAGES; s++) mbar_init(full + s, 1);
         mbar_fence_init();
-    }
-    __syncthreads();
-
-    // Producer duty (thread 0).  CTA b takes tiles b, b + G, b + 2G, ... of the keyframe-major tile list: all CTAs move
-    // through the list together, so at any time the ~300 tiles in flight belong to two or three keyframes and their
-    // z-buffers stay L2-resident.  The keyframe state a tile needs is prefetched one iteration ahead with cp.async into
-    // shared memory, so that this thread (and with it warp 0) never waits on global memory; the it_t-th tile of the CTA
-    // goes into stage it_t % STAGES once all 8 warps have released it.  A tile id >= total is the stop signal.
-    KfState* kfcache = reinterpret_cast<KfState*>(tdesc + DESKEW_STAGES); // [2], 16-byte aligned
-    auto tile_of = [&](unsigned it_t) { return blockIdx.x + it_t * gridDim.x; };
-    auto prefetch_kf = [&](unsigned it_t) {
-        const unsigned t = tile_of(it_t);
-        if (t < total) {
-            const char* src = reinterpret_cast<const char*>(a.kfs + t / a.tiles_per_kf);
-            const unsigned dst = smem_u32(kfcache + (it_t & 1));
 #pragma unroll
-            for (int c = 0; c < (int) sizeof(KfState) / 16; c++)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * c), "l"(src + 16 * c) : "memory");
+        for (int i = 0; i < DESKEW_STAGES - 1; i++) {
+            const unsigned cc = c + i * W;
+            if (cc < total) {
+                const uint4 r = __ldg(reinterpret_cast<const uint4*>(a.chunks + cc));
+                ChunkDesc d;
+                d.phys = (unsigned long long) r.x | ((unsigned long long) r.y << 32);
+                d.ent0 = r.z;
+                d.cw = r.w;
+                issue_chunk(a, d, wbase + i * STAGE_BYTES, full + i);
+            }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    auto issue = [&](unsigned it_t) {
-        const int s = it_t % DESKEW_STAGES;
-        asm volatile("cp.async.wait_group 0;" ::: "memory"); // the keyframe state of this tile has landed
-        if (it_t >= DESKEW_STAGES) mbar_wait(empty + s, ((it_t / DESKEW_STAGES) - 1) & 1);
-        const unsigned t = tile_of(it_t);
-        unsigned cnt = 0, off = 0;
-        unsigned long long pbegin = 0;
-        TileDesc d{};
-        d.tile = t;
-        if (t < total) {
-            const KfState* kf = kfcache + (it_t & 1);
-            d.kfi = t / a.tiles_per_kf;
-            off = (t % a.tiles_per_kf) * TILE_PTS;
-            const unsigned n = kf->n_proj;
-            cnt = off < n ? min((unsigned) TILE_PTS, n - off) : 0u;
-            pbegin = kf->proj_begin;
-            d.tab = a.table + kf->table_begin;
-            d.n_ins = (int) kf->ins_count;
-            d.t0 = kf->ins_t0;
-            d.t_last = kf->ins_t_last;
-            d.inv_mean_dt = kf->inv_mean_dt;
-        }
-        d.cnt = cnt;
-        d.off = off;
-        tdesc[s] = d;
-        mbar_arrive_expect_tx(full + s, cnt * 32u); // release: tdesc[s] is visible to whoever passes the barrier
-        if (cnt) {
-            unsigned char* dst = smem_raw + s * TILE_BYTES;
-            const unsigned long long phys = wrap(pbegin + off, a.pts_cap);
-            const unsigned long long room = a.pts_cap - phys; // ring: the tile may wrap around the end
-            const unsigned first = room < cnt ? (unsigned) room : cnt;
-            tma_bulk_g2s(dst, a.pts + phys, first * 32u, full + s);
-            if (first < cnt) tma_bulk_g2s(dst + first * 32u, a.pts, (cnt - first) * 32u, full + s);
-        }
-        prefetch_kf(it_t + 1);
-    };
-    if (tid == 0) {
-        prefetch_kf(0);
-#pragma unroll
-        for (int i = 0; i < DESKEW_STAGES - 1; i++) issue(i);
     }
+    // descriptor of the chunk that is issued next (one iteration ahead, so lane 0 never waits for it)
+    uint4 dn = make_uint4(0, 0, 0, 0);
+    if (c + (DESKEW_STAGES - 1) * W < total) dn = __ldg(reinterpret_cast<const uint4*>(a.chunks + c + (DESKEW_STAGES - 1) * W));
 
-    // ---- consumer warps ----
-    EntryRegs e;
-    int cur = -1;
-    unsigned cur_kf = 0xffffffffu;
-    KfView kv{};
-    for (unsigned it = 0;; ++it) {
-        const int s = it % DESKEW_STAGES;
-        // keep the ring full: the stage freed by iteration it-1 takes the next tile.  Only warp 0 can wait here (for the
-        // other warps to release that stage); the other warps run on, up to a full tile ahead of it.
-        if (tid == 0) issue(it + DESKEW_STAGES - 1);
-        mbar_wait(full + s, (it / DESKEW_STAGES) & 1);
-        const TileDesc d = tdesc[s];
-        if (d.tile >= total) break;
-        const unsigned kfi = d.kfi;
-        if (kfi != cur_kf) { // other keyframe: other interval table, drop the cached interval
-            cur_kf = kfi;
-            cur = -1;
+    unsigned s = 0, ph = 0, s_fill = DESKEW_STAGES - 1, qn = 0;
+    for (; c < total; c += W) {
+        // stage s_fill was read during the previous iteration: every lane is past those reads here
+        __syncwarp();
+        if (lane == 0 && c + (DESKEW_STAGES - 1) * W < total) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            ChunkDesc d;
+            d.phys = (unsigned long long) dn.x | ((unsigned long long) dn.y << 32);
+            d.ent0 = dn.z;
+            d.cw = dn.w;
+            issue_chunk(a, d, wbase + s_fill * STAGE_BYTES, full + s_fill);
         }
-        kv.tab = d.tab;
-        kv.n_ins = d.n_ins;
-        kv.t0 = d.t0;
-        kv.t_last = d.t_last;
-        kv.inv_mean_dt = d.inv_mean_dt;
-        const unsigned off = d.off, cnt = d.cnt;
+        if (c + DESKEW_STAGES * W < total) dn = __ldg(reinterpret_cast<const uint4*>(a.chunks + c + DESKEW_STAGES * W));
+        const unsigned char* st = wbase + s * STAGE_BYTES;
+        mbar_wait(full + s, ph);
+        const unsigned cnt = *reinterpret_cast<const unsigned*>(st + STAGE_HDR_OFF);
 
         if (cnt) {
-            const float4* __restrict__ sp = reinterpret_cast<const float4*>(smem_raw + s * TILE_BYTES);
+            const float4* __restrict__ sp = reinterpret_cast<const float4*>(st);
+            const unsigned off = rem * CHUNK_PTS;
             // 4 consecutive points per thread (they almost always share one INS interval).  Lane l visits them in the order
             // (j + l) & 3: with the plain order all lanes of a quarter-warp would hit the same 4 banks (128-byte lane stride,
             // 8-way conflict on every LDS.128); rotated, the conflict is 2-way.
-            const unsigned i0 = tid * DESKEW_PPT;
+            const unsigned i0 = lane * DESKEW_PPT;
             unsigned pi[DESKEW_PPT];
 #pragma unroll
             for (int j = 0; j < DESKEW_PPT; j++) pi[j] = i0 + ((j + lane) & (DESKEW_PPT - 1));
@@ -441,33 +479,47 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                 kept[j] = (pi[j] < cnt) && !((n2 > a.c.n2_far) || (n2 < a.c.n2_near)); // le_vins.cc:447-451
                 any_kept |= kept[j];
             }
-            // the 4 points are in registers: release the stage right away (no block-wide barrier, warps run decoupled;
-            // the earlier the release, the longer the TMA has to refill it)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + s);
             float ox[DESKEW_PPT], oy[DESKEW_PPT], oz[DESKEW_PPT];
             if (any_kept) {
-                // bring the cached interval entry to this thread's first kept point (a few instructions when it still
-                // serves), then check -- not assume -- that it brackets every kept point of the thread
-                bool sought = false;
+                // which of the two staged entries brackets every kept point of this thread (checked, not assumed)
+                const Interval* E0 = reinterpret_cast<const Interval*>(st + STAGE_ENT_OFF);
+                const Interval* E1 = E0 + 1;
+                const double2 T0 = *reinterpret_cast<const double2*>(E0);
+                const unsigned long long lo0 = (unsigned long long) __double_as_longlong(T0.x);
+                const unsigned long long w0 = E0->fast != 0.0 ? (unsigned long long) __double_as_longlong(T0.y) - lo0 : 0ull;
+                bool in0 = true;
 #pragma unroll
-                for (int j = 0; j < DESKEW_PPT; j++)
-                    if (kept[j] && !sought) {
-                        seek_entry(kv, tt[j], e, cur);
-                        sought = true;
-                    }
-                bool all = cur > 0 && e.t_lo > 0;
+                for (int j = 0; j < DESKEW_PPT; j++) in0 &= !kept[j] || key_brackets(lo0, w0, tt[j]);
+                const Interval* ep = E0;
+                bool fast = in0;
+                unsigned long long lo1 = 0, w1 = 0;
+                if (!in0) {
+                    const double2 T1 = *reinterpret_cast<const double2*>(E1);
+                    lo1 = (unsigned long long) __double_as_longlong(T1.x);
+                    w1 = E1->fast != 0.0 ? (unsigned long long) __double_as_longlong(T1.y) - lo1 : 0ull;
+                    bool in1 = true;
 #pragma unroll
-                for (int j = 0; j < DESKEW_PPT; j++) all &= !kept[j] || entry_brackets(e, tt[j]);
-                if (all && e.theta * e.theta < 2.44140625e-4) {
-                    // common case: straight-line code, the 4 points interleave
+                    for (int j = 0; j < DESKEW_PPT; j++) in1 &= !kept[j] || key_brackets(lo1, w1, tt[j]);
+                    ep = E1;
+                    fast = in1;
+                }
+                if (fast) {
+                    // common case: one entry for the 4 points, straight-line code, the 4 points interleave
+                    EntryRegs e;
+                    load_entry_shared(ep, e);
 #pragma unroll
                     for (int j = 0; j < DESKEW_PPT; j++) deskew_core<true>(px[j], py[j], pz[j], tt[j], e, a.ext, ox[j], oy[j], oz[j]);
                 } else {
+                    // the thread's points straddle intervals, or need an entry that was not staged (window edges, large
+                    // rotation, unordered times): one entry per point
 #pragma unroll
                     for (int j = 0; j < DESKEW_PPT; j++)
                         if (kept[j]) {
-                            seek_entry(kv, tt[j], e, cur);
+                            const Interval* epj = key_brackets(lo0, w0, tt[j])   ? E0
+                                                  : key_brackets(lo1, w1, tt[j]) ? E1
+                                                                                 : find_entry_global(a.kfs + kfi, a.table, tt[j]);
+                            EntryRegs e;
+                            load_entry_shared(epj, e); // generic pointer: shared or global
                             float x, y, z;
                             deskew_core<false>(px[j], py[j], pz[j], tt[j], e, a.ext, x, y, z);
                             ox[j] = x;
@@ -496,11 +548,6 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                 amb[j] = amb[j] && kept[j];
                 amb_any |= amb[j];
             }
-            if (amb_any) {
-#pragma unroll
-                for (int j = 0; j < DESKEW_PPT; j++)
-                    if (amb[j]) cell[j] = cell_of_point_exact<LIBM_MODE>(ox[j], oy[j], oz[j], a.c);
-            }
 #pragma unroll
             for (int j = 0; j < DESKEW_PPT; j++) {
                 const float range = sqrtf(v3f_sqnorm(ox[j], oy[j], oz[j])); // tracking.cc:330
@@ -513,13 +560,42 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
 #pragma unroll
             for (int j = 0; j < DESKEW_PPT; j++)
                 if (cell[j] >= 0) atomicMin(zb + cell[j], key[j]);
+            // cell ids next to a rounding boundary: queue them, the exact path settles 32 at a time
+            if (__any_sync(0xffffffffu, amb_any)) {
+#pragma unroll
+                for (int j = 0; j < DESKEW_PPT; j++) {
+                    const unsigned m = __ballot_sync(0xffffffffu, amb[j]);
+                    if (m) {
+                        const unsigned n = __popc(m);
+                        if (qn + n > AMBQ) {
+                            flush_undecided<LIBM_MODE>(q_pt, q_kf, qn, a.zbuf, a.gen, a.c);
+                            qn = 0;
+                        }
+                        if (amb[j]) {
+                            const unsigned pos = qn + __popc(m & ((1u << lane) - 1u));
+                            q_pt[pos] = make_float4(ox[j], oy[j], oz[j], __uint_as_float(off + pi[j]));
+                            q_kf[pos] = kfi;
+                        }
+                        qn += n;
+                    }
+                }
+            }
         }
-        if (!cnt) { // empty tile: nothing was read, release the stage
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + s);
+        s_fill = s;
+        if (++s == DESKEW_STAGES) {
+            s = 0;
+            ph ^= 1;
+        }
+        rem += Wr;
+        kfi += Wq;
+        if (rem >= cpk) {
+            rem -= cpk;
+            kfi++;
         }
     }
+    if (qn) flush_undecided<LIBM_MODE>(q_pt, q_kf, qn, a.zbuf, a.gen, a.c);
 }
+
 
 // explicit-cloud binning for levins_build_range_image(cloud != NULL)
 template <int LIBM_MODE>

@@ -63,6 +63,7 @@ struct levins_ctx {
     uint64_t ring_tail = 0;     // physical index one past the newest point
     uint64_t ring_count_ub = 0; // host's upper bound of the live point count
     DevBuf s_ins, s_table, s_kf, s_queries;
+    DevBuf chunks; // ChunkDesc of the current k_deskew_bin launch (streaming and batch)
     DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2, s_nn, s_nn_meta;
     DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
     DevBuf s_in_cloud; // explicit cloud uploaded by build_range_image
@@ -209,11 +210,25 @@ int ensure_ring(levins_ctx* ctx) {
     return LEVINS_OK;
 }
 
-// k_deskew_bin is persistent: at most two CTAs per SM (96 KB of TMA staging each), each walking a contiguous tile range.
-int launch_deskew(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf, bool write_cloud) {
+// Chunk descriptors for k_deskew_bin (one thread per 128-point chunk; needs the KfState written by k_prepare).
+int launch_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf) {
     a.n_kf = n_kf;
-    a.tiles_per_kf = (unsigned) ((max_pts + TILE_PTS - 1) / TILE_PTS);
-    const unsigned total = a.n_kf * a.tiles_per_kf;
+    a.chunks_per_kf = (unsigned) ((max_pts + CHUNK_PTS - 1) / CHUNK_PTS);
+    const uint64_t total = (uint64_t) a.n_kf * a.chunks_per_kf;
+    if (total == 0) return LEVINS_OK;
+    if (total >= (1ull << 30)) return fail(ctx, LEVINS_ERR_CAPACITY, "more than 2^30 chunks in one launch: lower the wave size");
+    CU(ctx->chunks.ensure(total * sizeof(ChunkDesc)));
+    a.chunks = ctx->chunks.as<ChunkDesc>();
+    k_chunk_desc<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return LEVINS_OK;
+}
+
+// k_deskew_bin is persistent: two CTAs per SM (111 KB of TMA staging each), every warp walking its own chunk list.
+// launch_chunks() must have filled a.chunks / a.chunks_per_kf.
+int launch_deskew(levins_ctx* ctx, DeskewArgs& a, bool write_cloud) {
+    const unsigned total = a.n_kf * a.chunks_per_kf;
     if (total == 0) return LEVINS_OK;
     if (!ctx->deskew_attr_set) {
         CU(cudaFuncSetAttribute(k_deskew_bin<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
@@ -222,7 +237,7 @@ int launch_deskew(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_k
         CU(cudaFuncSetAttribute(k_deskew_bin<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
         ctx->deskew_attr_set = true;
     }
-    const unsigned grid = std::min<unsigned>(total, 2u * (unsigned) ctx->num_sms);
+    const unsigned grid = std::min<unsigned>((total + DESKEW_WARPS - 1) / DESKEW_WARPS, 2u * (unsigned) ctx->num_sms);
     if (ctx->consts.libm_mode == 0) {
         if (write_cloud)
             k_deskew_bin<0, true><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
@@ -296,7 +311,11 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     da.ext = ctx->ext;
     da.c = ctx->consts;
     (void) bin;
-    return launch_deskew(ctx, da, n_ub, 1, write_cloud);
+    {
+        int r = launch_chunks(ctx, da, n_ub, 1);
+        if (r) return r;
+    }
+    return launch_deskew(ctx, da, write_cloud);
 }
 
 int run_finalize_stream(levins_ctx* ctx, bool from_cloud, const PointXYZI* cloud, bool want_winner) {
@@ -909,8 +928,12 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         da.c = ctx->consts;
         if (max_pts) {
             if (k0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_counted, 0)); // the slots are about to be reused
+            mark(0, true);
+            r = launch_chunks(ctx, da, max_pts, (unsigned) nw);
+            mark(0, false);
+            if (r) return r;
             mark(1, true);
-            r = launch_deskew(ctx, da, max_pts, (unsigned) nw, false);
+            r = launch_deskew(ctx, da, false);
             mark(1, false);
             if (r) return r;
         }
