@@ -364,7 +364,37 @@ __device__ __forceinline__ float atan2f_fd(float y, float x) {
 }
 
 // Eigen Vector3f redux order: e0 + (e1 + e2)
-__device__ __forceinline__ float v3f_sqnorm(float x, float y, float z) { return x * x + (y * y + z * z); }
+// ---- packed f32x2 arithmetic (Blackwell FMUL2 / FADD2 / FFMA2: two IEEE round-to-nearest operations per issue slot;
+// each half is bit-identical to the scalar instruction) ----
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; "
+        "mov.b64 {%0, %1}, rd; }"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
+
+// Eigen's Vector3f::squaredNorm() order: x*x + (y*y + z*z), no contraction
+__device__ __forceinline__ float v3f_sqnorm(float x, float y, float z) {
+    const float2 q = f2_mul(make_float2(y, z), make_float2(y, z));
+    return x * x + (q.x + q.y);
+}
 
 // ------------------------------------------------------------------------------------------------
 // stage 2: cell of a camera-frame point (tracking.cc:311-331).  Returns -1 when the point is rejected.
@@ -441,29 +471,48 @@ __device__ __forceinline__ bool outside_fov(float x, float y, float z) {
     return (z < 0.f) || (fabsf(x) - az >= lim) || (fabsf(y) - az >= lim);
 }
 
+// atan for the pair (t.x, t.y): atan_poly() on both halves at once
+__device__ __forceinline__ float2 atan_poly2(float2 t) {
+    const float2 u = f2_mul(t, t);
+    float2 p = f2_splat(0.0024566929787397385f);
+    p = f2_fma(p, u, f2_splat(-0.014401225373148918f));
+    p = f2_fma(p, u, f2_splat(0.03978099301457405f));
+    p = f2_fma(p, u, f2_splat(-0.07234836369752884f));
+    p = f2_fma(p, u, f2_splat(0.10498934984207153f));
+    p = f2_fma(p, u, f2_splat(-0.14161226153373718f));
+    p = f2_fma(p, u, f2_splat(0.19985906779766083f));
+    p = f2_fma(p, u, f2_splat(-0.33332598209381104f));
+    p = f2_fma(p, u, f2_splat(0.9999998807907104f));
+    return f2_mul(t, p);
+}
+
 // returns the cell id or -1; sets `ambiguous` when the exact path must decide.  Straight-line code (no early exits) so
-// that several points per thread interleave; rounding uses the 1.5 * 2^23 magic constant instead of FRND / F2I.
+// that several points per thread interleave.  The column and the row travel as the two halves of packed f32x2
+// operations; 1/z and 1/sqrt(x^2+z^2) are single MUFU approximations (this path only has to be right to ~1e-4 cell);
+// rounding uses the 1.5 * 2^23 magic constant instead of FRND / F2I.
 __device__ __forceinline__ int cell_of_point_fast(float x, float y, float z, const Consts& c, bool& ambiguous) {
     const bool behind = z < 0.f;
-    const bool tiny = !(z > 1e-30f); // zero / denormal-range z: |z| 2^-25 may be inexact, leave it to the exact path
+    // z outside [2^-61, 2^59) (zero, denormal range, huge, NaN; negative too, but `behind` wins): 1/z or z*z may leave
+    // the normal range, so the exact path decides.  Never the case for a point that passed the range gate.
+    const bool odd = (__float_as_uint(z) - 0x21000000u) >= 0x3c000000u;
     const bool outside = outside_fov(x, y, z);
-    // col_angle / ANGLE = (atan2(z, x) - pi/4) / ANGLE = 150 - atan(x / z) / ANGLE
-    const float tc = __fdividef(x, z); // approximate: this path only has to be right to ~1e-4 cell
-
-    const float qc = fmaf(-atan_poly(tc), c.inv_angle_f, 150.0f);
-    // row_angle / ANGLE = (atan2(y, sqrt(x^2 + z^2)) + pi/4) / ANGLE = 150 + atan(y / sqrt(x^2 + z^2)) / ANGLE
+    float rz, rs;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(z));
     const float s = fmaf(x, x, z * z);
-    const float tr = y * rsqrtf(s);
-    const float qr = fmaf(atan_poly(tr), c.inv_angle_f, 150.0f);
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(s));
+    // col_angle / ANGLE = (atan2(z, x) - pi/4) / ANGLE = 150 - atan(x / z) / ANGLE
+    // row_angle / ANGLE = (atan2(y, sqrt(x^2 + z^2)) + pi/4) / ANGLE = 150 + atan(y / sqrt(x^2 + z^2)) / ANGLE
+    const float2 at = atan_poly2(f2_mul(make_float2(x, y), make_float2(rz, rs)));
+    const float2 q = f2_fma(at, make_float2(-c.inv_angle_f, c.inv_angle_f), f2_splat(150.0f));
     const float MAGIC = 12582912.0f; // 1.5 * 2^23: (q + MAGIC) - MAGIC = rint(q) for |q| < 2^22
-    const float mc = qc + MAGIC, mr = qr + MAGIC;
-    const float rc = mc - MAGIC, rr = mr - MAGIC;
-    const int col = __float_as_int(mc) - 0x4B400000, row = __float_as_int(mr) - 0x4B400000;
-    const float edge = 0.5f - c.cell_guard;
-    const bool near_edge = (fabsf(qc - rc) > edge) || (fabsf(qr - rr) > edge);
+    const float2 m = f2_add(q, f2_splat(MAGIC));
+    const float2 r = f2_add(m, f2_splat(-MAGIC));
+    const float2 d = f2_add(q, make_float2(-r.x, -r.y));
+    const int col = __float_as_int(m.x) - 0x4B400000, row = __float_as_int(m.y) - 0x4B400000;
+    const bool near_edge = fmaxf(fabsf(d.x), fabsf(d.y)) > 0.5f - c.cell_guard;
     const bool in_grid = ((unsigned) row < (unsigned) IMG) && ((unsigned) col < (unsigned) IMG);
-    ambiguous = !behind && (tiny || (!outside && near_edge));
-    return (behind || tiny || outside || near_edge || !in_grid) ? -1 : col + row * IMG;
+    ambiguous = !behind && (odd || (!outside && near_edge));
+    return (behind || odd || outside || near_edge || !in_grid) ? -1 : col + row * IMG;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -628,20 +677,33 @@ __device__ __forceinline__ void sin_omc_small(double phi, double& sn, double& om
 
 // Deskew one raw point into the keyframe's camera frame (le_vins.cc:455-461) with the entry in registers.
 // The two f32 roundings of pointcloud.cc:68 are kept.
+#ifndef LV_KO
+#define LV_KO 0
+#endif
+#if LV_KO & 16 // timing experiment: no XU conversions (results are wrong)
+#define LV_F2D(v) __hiloint2double(__float_as_int(v), 0)
+#define LV_D2F(v) __int_as_float(__double2hiint(v))
+#else
+#define LV_F2D(v) ((double) (v))
+#define LV_D2F(v) ((float) (v))
+#endif
 template <bool SMALL_ANGLE = false>
 __device__ __forceinline__ void deskew_core(float x, float y, float z, double t, const EntryRegs& e, const Extrinsics& ex,
                                             float& ox, float& oy, float& oz) {
     // p_c1 = f32(R_cl p + t_cl)   (pointcloud.cc:38 -> 68, first rounding)
-    const double xd = x, yd = y, zd = z;
-    const float p1x = (float) fma(ex.Rcl[6], zd, fma(ex.Rcl[3], yd, fma(ex.Rcl[0], xd, ex.tcl[0])));
-    const float p1y = (float) fma(ex.Rcl[7], zd, fma(ex.Rcl[4], yd, fma(ex.Rcl[1], xd, ex.tcl[1])));
-    const float p1z = (float) fma(ex.Rcl[8], zd, fma(ex.Rcl[5], yd, fma(ex.Rcl[2], xd, ex.tcl[2])));
-    const double ax = p1x, ay = p1y, az = p1z;
+    const double xd = LV_F2D(x), yd = LV_F2D(y), zd = LV_F2D(z);
+    const float p1x = LV_D2F(fma(ex.Rcl[6], zd, fma(ex.Rcl[3], yd, fma(ex.Rcl[0], xd, ex.tcl[0]))));
+    const float p1y = LV_D2F(fma(ex.Rcl[7], zd, fma(ex.Rcl[4], yd, fma(ex.Rcl[1], xd, ex.tcl[1]))));
+    const float p1z = LV_D2F(fma(ex.Rcl[8], zd, fma(ex.Rcl[5], yd, fma(ex.Rcl[2], xd, ex.tcl[2]))));
+    const double ax = LV_F2D(p1x), ay = LV_F2D(p1y), az = LV_F2D(p1z);
     // u = R_bc p_c1 + t_bc
     const double ux = fma(ex.Rbc[6], az, fma(ex.Rbc[3], ay, fma(ex.Rbc[0], ax, ex.tbc[0])));
     const double uy = fma(ex.Rbc[7], az, fma(ex.Rbc[4], ay, fma(ex.Rbc[1], ax, ex.tbc[1])));
     const double uz = fma(ex.Rbc[8], az, fma(ex.Rbc[5], ay, fma(ex.Rbc[2], ax, ex.tbc[2])));
     const double s = (t - e.ts0) * e.inv_dts;
+#if LV_KO & 64 // timing experiment: no rotation correction (28 of the 61 FP64 operations)
+    const double wx = ux, wy = uy, wz = uz;
+#else
     double sn, omc;
     if (SMALL_ANGLE)
         sin_omc_small(-s * e.theta, sn, omc);
@@ -653,10 +715,11 @@ __device__ __forceinline__ void deskew_core(float x, float y, float z, double t,
     const double wx = fma(omc, dx, fma(sn, cx, ux));
     const double wy = fma(omc, dy, fma(sn, cy, uy));
     const double wz = fma(omc, dz, fma(sn, cz, uz));
+#endif
     // p_c0 = A w + c0 + s c1   (second rounding, pointcloud.cc:45 -> 68)
-    ox = (float) fma(e.A2, wz, fma(e.A1, wy, fma(e.A0, wx, fma(s, e.c1x, e.c0x))));
-    oy = (float) fma(e.A5, wz, fma(e.A4, wy, fma(e.A3, wx, fma(s, e.c1y, e.c0y))));
-    oz = (float) fma(e.A8, wz, fma(e.A7, wy, fma(e.A6, wx, fma(s, e.c1z, e.c0z))));
+    ox = LV_D2F(fma(e.A2, wz, fma(e.A1, wy, fma(e.A0, wx, fma(s, e.c1x, e.c0x)))));
+    oy = LV_D2F(fma(e.A5, wz, fma(e.A4, wy, fma(e.A3, wx, fma(s, e.c1y, e.c0y)))));
+    oz = LV_D2F(fma(e.A8, wz, fma(e.A7, wy, fma(e.A6, wx, fma(s, e.c1z, e.c0z)))));
 }
 
 // Range gate (le_vins.cc:447-451) on the squared norm (see Consts) + entry lookup + deskew.  false for gated points.

@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
         const bool ordered = j == 0 ? (e.t_hi > 0 && e.t_lo > e.t_hi) : (e.t_lo > 0 && e.t_hi > e.t_lo);
         e.fast = (ordered && e.theta * e.theta < 2.44140625e-4) ? 1.0 : 0.0;
         tab[j] = e;
+        if (j == 0) tab[nins] = e; // slot nins: the fallback again, as the successor of the last interval (k_chunk_desc)
     }
 }
 
@@ -226,19 +227,35 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
 // 4 KB per chunk; warp g takes chunks g, g + W, g + 2W, ...) and lane 0 streams chunk it+2 HBM -> shared memory with the
 // TMA unit (cp.async.bulk, 1-D, completion on the warp's own mbarrier) while the warp does the arithmetic of chunk it.
 // With the points travel the two INS-interval entries the chunk can need (the one of its first point, found by
-// k_chunk_desc, and its successor), so that the per-point math never waits on global memory and the warps of a CTA
+// k_chunk_desc, and its successor in the table), so that the per-point math never waits on global memory and the warps of a CTA
 // never wait for each other.  Each thread handles 4 consecutive points; cell ids that the polynomial path cannot decide
 // are queued per warp and settled 32 at a time by the exact path.
 // ------------------------------------------------------------------------------------------------
-constexpr int DESKEW_PPT = 4;
+#ifndef LV_GROUP
+#define LV_GROUP 4
+#endif
+#ifndef LV_STAGES
+#define LV_STAGES 3
+#endif
+#ifndef LV_AMBQ
+#define LV_AMBQ 32
+#endif
+#ifndef LV_MINBLK
+#define LV_MINBLK 2
+#endif
+#ifndef LV_KO // knock-out experiments (timing only, results are wrong): 1 no RED, 2 no deskew math, 4 no cell math, 8 loads only
+#define LV_KO 0
+#endif
+constexpr int DESKEW_PPT = 4;          // points per thread and chunk
+constexpr int DESKEW_GROUP = LV_GROUP; // of which this many are in flight together (register pressure vs interleaving)
 constexpr int DESKEW_WARPS = DESKEW_THREADS / 32;
 constexpr int CHUNK_PTS = 32 * DESKEW_PPT; // 128 points = 4 KB: one warp, one iteration
 constexpr int CHUNK_BYTES = CHUNK_PTS * 32;
-constexpr int DESKEW_STAGES = 3;
+constexpr int DESKEW_STAGES = LV_STAGES;
 constexpr int STAGE_ENT_OFF = CHUNK_BYTES;                        // two interval entries (2 x 192 B)
 constexpr int STAGE_HDR_OFF = STAGE_ENT_OFF + 2 * (int) sizeof(Interval); // {cnt}
 constexpr int STAGE_BYTES = STAGE_HDR_OFF + 16;
-constexpr int AMBQ = 32; // undecided cell ids queued per warp
+constexpr int AMBQ = LV_AMBQ; // undecided cell ids queued per warp
 constexpr int WARP_BAR_OFF = DESKEW_STAGES * STAGE_BYTES;
 constexpr int WARP_Q_OFF = WARP_BAR_OFF + 32;
 constexpr int WARP_QKF_OFF = WARP_Q_OFF + AMBQ * 16;
@@ -246,13 +263,13 @@ constexpr int WARP_SMEM = WARP_QKF_OFF + AMBQ * 4;
 constexpr int DESKEW_SMEM = DESKEW_WARPS * WARP_SMEM; // 113 280 B: two CTAs per SM
 constexpr int DESKEW_BLOCK = DESKEW_THREADS;
 static_assert(STAGE_BYTES % 16 == 0 && WARP_SMEM % 16 == 0 && WARP_Q_OFF % 16 == 0, "TMA / vector alignment");
-static_assert(2 * (DESKEW_SMEM + 1024) <= 228 * 1024, "two CTAs per SM");
+static_assert(LV_MINBLK * (DESKEW_SMEM + 1024) <= 228 * 1024, "CTAs per SM");
 
 // what lane 0 needs to fetch one chunk, written by k_chunk_desc
 struct __align__(16) ChunkDesc {
     unsigned long long phys; // physical index of the chunk's first point in the pool / ring
     unsigned ent0;           // absolute index (into the interval-table pool) of the entry of the chunk's first point
-    unsigned cw;             // bits 0-7: points in the chunk (0 = empty); bits 8-31: signed offset of the second entry
+    unsigned cnt;            // points in the chunk (0 = empty)
 };
 
 struct DeskewArgs {
@@ -282,29 +299,25 @@ __global__ void __launch_bounds__(256) k_chunk_desc(const __grid_constant__ Desk
     ChunkDesc d;
     d.phys = 0;
     d.ent0 = 0;
-    d.cw = 0;
+    d.cnt = 0;
     if (off < n) {
         const unsigned cnt = min((unsigned) CHUNK_PTS, n - off);
         const unsigned long long phys = wrap(kf->proj_begin + off, a.pts_cap);
         const double t = a.pts[phys].time + a.ext.td_b_l; // le_vins.cc:455
         const Interval* __restrict__ tab = a.table + kf->table_begin;
         const int nins = (int) kf->ins_count;
-        int idx = 0, nxt = 0;
+        int idx = 0;
         if (!(nins < 2 || kf->ins_t0 > t || kf->ins_t_last <= t)) { // misc.cc:28-30
             int g = 1 + (int) ((t - kf->ins_t0) * kf->inv_mean_dt);
             g = min(max(g, 1), nins - 1);
             const double2 ab = __ldg(reinterpret_cast<const double2*>(tab + g));
             idx = ((ab.x <= t) && (t < ab.y)) ? g : find_interval_slow(tab, nins, t, g, 1, nins - 1);
         }
-        // the entry the later points of the chunk move on to: the next interval, the fallback after the last one,
-        // the first interval for a chunk that starts before the window
-        if (idx > 0)
-            nxt = idx + 1 < nins ? idx + 1 : 0;
-        else
-            nxt = (nins >= 2 && kf->ins_t0 > t) ? 1 : 0;
+        // k_deskew_bin stages entries idx and idx + 1: the next interval, the fallback copy in slot nins after the last
+        // one, the first interval for a chunk that starts before the window
         d.phys = phys;
         d.ent0 = (unsigned) (kf->table_begin + idx);
-        d.cw = cnt | ((unsigned) (nxt - idx) << 8);
+        d.cnt = cnt;
     }
     a.chunks[c] = d;
 }
@@ -367,17 +380,14 @@ __device__ __forceinline__ int cell_id(float x, float y, float z, const Consts& 
 
 // lane 0: start the copies of one chunk into a stage of the warp's ring
 __device__ __forceinline__ void issue_chunk(const DeskewArgs& a, const ChunkDesc& d, unsigned char* stage, unsigned long long* bar) {
-    const unsigned cnt = d.cw & 0xffu;
+    const unsigned cnt = d.cnt;
     *reinterpret_cast<unsigned*>(stage + STAGE_HDR_OFF) = cnt;
     if (cnt == 0) {
         mbar_arrive(bar); // release: the header is visible to whoever passes the barrier
         return;
     }
     mbar_arrive_expect_tx(bar, cnt * 32u + 2u * (unsigned) sizeof(Interval));
-    const Interval* e0 = a.table + d.ent0;
-    const Interval* e1 = e0 + ((int) d.cw >> 8);
-    tma_bulk_g2s(stage + STAGE_ENT_OFF, e0, (unsigned) sizeof(Interval), bar);
-    tma_bulk_g2s(stage + STAGE_ENT_OFF + sizeof(Interval), e1, (unsigned) sizeof(Interval), bar);
+    tma_bulk_g2s(stage + STAGE_ENT_OFF, a.table + d.ent0, 2u * (unsigned) sizeof(Interval), bar); // entries ent0, ent0 + 1
     const unsigned long long room = a.pts_cap - d.phys; // ring: the chunk may wrap around the end
     const unsigned first = room < cnt ? (unsigned) room : cnt;
     tma_bulk_g2s(stage, a.pts + d.phys, first * 32u, bar);
@@ -400,7 +410,7 @@ __device__ __noinline__ void flush_undecided(const float4* q, const unsigned* qk
 }
 
 template <int LIBM_MODE, bool WRITE_CLOUD>
-__global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
+__global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + warp * WARP_SMEM;
@@ -427,7 +437,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                 ChunkDesc d;
                 d.phys = (unsigned long long) r.x | ((unsigned long long) r.y << 32);
                 d.ent0 = r.z;
-                d.cw = r.w;
+                d.cnt = r.w;
                 issue_chunk(a, d, wbase + i * STAGE_BYTES, full + i);
             }
         }
@@ -441,11 +451,10 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
         // stage s_fill was read during the previous iteration: every lane is past those reads here
         __syncwarp();
         if (lane == 0 && c + (DESKEW_STAGES - 1) * W < total) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             ChunkDesc d;
             d.phys = (unsigned long long) dn.x | ((unsigned long long) dn.y << 32);
             d.ent0 = dn.z;
-            d.cw = dn.w;
+            d.cnt = dn.w;
             issue_chunk(a, d, wbase + s_fill * STAGE_BYTES, full + s_fill);
         }
         if (c + DESKEW_STAGES * W < total) dn = __ldg(reinterpret_cast<const uint4*>(a.chunks + c + DESKEW_STAGES * W));
@@ -460,15 +469,17 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
             // (j + l) & 3: with the plain order all lanes of a quarter-warp would hit the same 4 banks (128-byte lane stride,
             // 8-way conflict on every LDS.128); rotated, the conflict is 2-way.
             const unsigned i0 = lane * DESKEW_PPT;
-            unsigned pi[DESKEW_PPT];
+#pragma unroll 1
+            for (int g0 = 0; g0 < DESKEW_PPT; g0 += DESKEW_GROUP) {
+            unsigned pi[DESKEW_GROUP];
 #pragma unroll
-            for (int j = 0; j < DESKEW_PPT; j++) pi[j] = i0 + ((j + lane) & (DESKEW_PPT - 1));
-            float px[DESKEW_PPT], py[DESKEW_PPT], pz[DESKEW_PPT];
-            double tt[DESKEW_PPT];
-            bool kept[DESKEW_PPT];
+            for (int j = 0; j < DESKEW_GROUP; j++) pi[j] = i0 + ((g0 + j + lane) & (DESKEW_PPT - 1));
+            float px[DESKEW_GROUP], py[DESKEW_GROUP], pz[DESKEW_GROUP];
+            double tt[DESKEW_GROUP];
+            bool kept[DESKEW_GROUP];
             bool any_kept = false;
 #pragma unroll
-            for (int j = 0; j < DESKEW_PPT; j++) {
+            for (int j = 0; j < DESKEW_GROUP; j++) {
                 const float4 xyz = sp[2 * pi[j]];
                 const double tm = reinterpret_cast<const double2*>(sp)[2 * pi[j] + 1].y;
                 px[j] = xyz.x;
@@ -479,8 +490,27 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                 kept[j] = (pi[j] < cnt) && !((n2 > a.c.n2_far) || (n2 < a.c.n2_near)); // le_vins.cc:447-451
                 any_kept |= kept[j];
             }
-            float ox[DESKEW_PPT], oy[DESKEW_PPT], oz[DESKEW_PPT];
+            float ox[DESKEW_GROUP], oy[DESKEW_GROUP], oz[DESKEW_GROUP];
+#if LV_KO & 8
+            {
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < DESKEW_GROUP; j++) acc += px[j] + py[j] + pz[j] + (float) tt[j];
+                if (acc == 12345.678f) atomicMin(a.zbuf, (unsigned long long) __float_as_uint(acc));
+                continue;
+            }
+#endif
+#if LV_KO & 2
+#pragma unroll
+            for (int j = 0; j < DESKEW_GROUP; j++) {
+                ox[j] = px[j] + (float) tt[j];
+                oy[j] = py[j];
+                oz[j] = pz[j];
+            }
+            if (false) {
+#else
             if (any_kept) {
+#endif
                 // which of the two staged entries brackets every kept point of this thread (checked, not assumed)
                 const Interval* E0 = reinterpret_cast<const Interval*>(st + STAGE_ENT_OFF);
                 const Interval* E1 = E0 + 1;
@@ -489,7 +519,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                 const unsigned long long w0 = E0->fast != 0.0 ? (unsigned long long) __double_as_longlong(T0.y) - lo0 : 0ull;
                 bool in0 = true;
 #pragma unroll
-                for (int j = 0; j < DESKEW_PPT; j++) in0 &= !kept[j] || key_brackets(lo0, w0, tt[j]);
+                for (int j = 0; j < DESKEW_GROUP; j++) in0 &= !kept[j] || key_brackets(lo0, w0, tt[j]);
                 const Interval* ep = E0;
                 bool fast = in0;
                 unsigned long long lo1 = 0, w1 = 0;
@@ -499,7 +529,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                     w1 = E1->fast != 0.0 ? (unsigned long long) __double_as_longlong(T1.y) - lo1 : 0ull;
                     bool in1 = true;
 #pragma unroll
-                    for (int j = 0; j < DESKEW_PPT; j++) in1 &= !kept[j] || key_brackets(lo1, w1, tt[j]);
+                    for (int j = 0; j < DESKEW_GROUP; j++) in1 &= !kept[j] || key_brackets(lo1, w1, tt[j]);
                     ep = E1;
                     fast = in1;
                 }
@@ -508,12 +538,12 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                     EntryRegs e;
                     load_entry_shared(ep, e);
 #pragma unroll
-                    for (int j = 0; j < DESKEW_PPT; j++) deskew_core<true>(px[j], py[j], pz[j], tt[j], e, a.ext, ox[j], oy[j], oz[j]);
+                    for (int j = 0; j < DESKEW_GROUP; j++) deskew_core<true>(px[j], py[j], pz[j], tt[j], e, a.ext, ox[j], oy[j], oz[j]);
                 } else {
                     // the thread's points straddle intervals, or need an entry that was not staged (window edges, large
                     // rotation, unordered times): one entry per point
 #pragma unroll
-                    for (int j = 0; j < DESKEW_PPT; j++)
+                    for (int j = 0; j < DESKEW_GROUP; j++)
                         if (kept[j]) {
                             const Interval* epj = key_brackets(lo0, w0, tt[j])   ? E0
                                                   : key_brackets(lo1, w1, tt[j]) ? E1
@@ -530,7 +560,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
             }
             if (WRITE_CLOUD) {
 #pragma unroll
-                for (int j = 0; j < DESKEW_PPT; j++)
+                for (int j = 0; j < DESKEW_GROUP; j++)
                     if (pi[j] < cnt) {
                         float4* out = reinterpret_cast<float4*>(a.cloud_out + off + pi[j]);
                         out[0] = kept[j] ? make_float4(ox[j], oy[j], oz[j], 1.0f) : make_float4(0.f, 0.f, 0.f, 1.0f); // resize() default (le_vins.cc:438)
@@ -538,18 +568,23 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                     }
             }
             // stage 2: cell ids (a default point lands at col = -150 and is dropped at tracking.cc:326-328)
-            unsigned long long key[DESKEW_PPT];
-            int cell[DESKEW_PPT];
+            unsigned long long key[DESKEW_GROUP];
+            int cell[DESKEW_GROUP];
             bool amb_any = false;
-            bool amb[DESKEW_PPT];
+            bool amb[DESKEW_GROUP];
 #pragma unroll
-            for (int j = 0; j < DESKEW_PPT; j++) {
+            for (int j = 0; j < DESKEW_GROUP; j++) {
+#if LV_KO & 4
+                cell[j] = (int) (__float_as_uint(ox[j] + oy[j] * oz[j]) % 90000u);
+                amb[j] = false;
+#else
                 cell[j] = cell_of_point_fast(ox[j], oy[j], oz[j], a.c, amb[j]);
+#endif
                 amb[j] = amb[j] && kept[j];
                 amb_any |= amb[j];
             }
 #pragma unroll
-            for (int j = 0; j < DESKEW_PPT; j++) {
+            for (int j = 0; j < DESKEW_GROUP; j++) {
                 const float range = sqrtf(v3f_sqnorm(ox[j], oy[j], oz[j])); // tracking.cc:330
                 if (!kept[j] || !(range < FLT_MAX)) cell[j] = -1;            // tracking.cc:332 against the FLT_MAX initial value
                 key[j] = key_make(a.gen, range, off + pi[j]);
@@ -558,12 +593,16 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
             // as the reduction itself and would put an L2 round trip on the critical path)
             unsigned long long* __restrict__ zb = a.zbuf + (size_t) kfi * CELLS;
 #pragma unroll
-            for (int j = 0; j < DESKEW_PPT; j++)
+            for (int j = 0; j < DESKEW_GROUP; j++)
+#if LV_KO & 1
+                if (cell[j] == 123456789 && key[j] == 42) atomicMin(zb, key[j]);
+#else
                 if (cell[j] >= 0) atomicMin(zb + cell[j], key[j]);
+#endif
             // cell ids next to a rounding boundary: queue them, the exact path settles 32 at a time
             if (__any_sync(0xffffffffu, amb_any)) {
 #pragma unroll
-                for (int j = 0; j < DESKEW_PPT; j++) {
+                for (int j = 0; j < DESKEW_GROUP; j++) {
                     const unsigned m = __ballot_sync(0xffffffffu, amb[j]);
                     if (m) {
                         const unsigned n = __popc(m);
@@ -580,6 +619,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, 2) k_deskew_bin(const __grid_con
                     }
                 }
             }
+            } // group
         }
         s_fill = s;
         if (++s == DESKEW_STAGES) {

@@ -178,7 +178,7 @@ int next_gen(levins_ctx* ctx, unsigned long long* z, size_t n, unsigned* gen) {
 
 int ensure_stream_buffers(levins_ctx* ctx, size_t n_ins, size_t n_feat) {
     CU(ctx->s_ins.ensure(std::max<size_t>(n_ins, 1) * sizeof(InsSample)));
-    CU(ctx->s_table.ensure(std::max<size_t>(n_ins, 1) * sizeof(Interval)));
+    CU(ctx->s_table.ensure((std::max<size_t>(n_ins, 1) + 1) * sizeof(Interval))); // + the fallback copy
     CU(ctx->s_kf.ensure(sizeof(KfState)));
     CU(ctx->s_queries.ensure(std::max<size_t>(n_feat, 1) * 3 * sizeof(float)));
     CU(ctx->s_type.ensure(std::max<size_t>(n_feat, 1)));
@@ -237,7 +237,7 @@ int launch_deskew(levins_ctx* ctx, DeskewArgs& a, bool write_cloud) {
         CU(cudaFuncSetAttribute(k_deskew_bin<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
         ctx->deskew_attr_set = true;
     }
-    const unsigned grid = std::min<unsigned>((total + DESKEW_WARPS - 1) / DESKEW_WARPS, 2u * (unsigned) ctx->num_sms);
+    const unsigned grid = std::min<unsigned>((total + DESKEW_WARPS - 1) / DESKEW_WARPS, (unsigned) LV_MINBLK * (unsigned) ctx->num_sms);
     if (ctx->consts.libm_mode == 0) {
         if (write_cloud)
             k_deskew_bin<0, true><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
@@ -463,7 +463,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
+    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->chunks, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
@@ -825,7 +825,7 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
         s.q_count = d.q_count;
         s.stamp = d.stamp;
         s.table_begin = table_entries;
-        table_entries += d.ins_count;
+        table_entries += d.ins_count + 1; // + the fallback copy (k_prepare)
         kfs[k] = s;
     }
     CU(ctx->b_pts.ensure(std::max<size_t>(n_points, 1) * sizeof(PointXYZIT)));

@@ -14,7 +14,8 @@ import numpy as np
 from .synth import INS, XYZI, XYZIT
 
 PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(PKG_DIR, "liblevins_b200.so")
+# LEVINS_LIB: an alternative build of the same library (A/B timing of kernel variants on one box; tests and bench only)
+LIB_PATH = os.environ.get("LEVINS_LIB") or os.path.join(PKG_DIR, "liblevins_b200.so")
 
 OK, EMPTY = 0, 1
 ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = -1, -2, -3, -4
