@@ -225,7 +225,7 @@ def run_gpu(args):
     t_q, q = pinned_copy(torch, q_flat)
     keep += [t_pts, t_ins, t_q]
 
-    ctx = abi.Context(local_rank)
+    ctx = abi.Context(local_rank, deskew_precision=args.precision)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.set_extrinsics(batch.shape.rig.pose_b_c, batch.shape.rig.pose_c_l, batch.shape.rig.td_b_l)
@@ -323,6 +323,12 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_cfg3:
         also = bench_cfg3(torch, abi, synth, local_rank, stream, peak)
 
+    # ---- the opt-in single-precision deskew (levins_config.deskew_precision = 1) on the same batch, and how far its
+    #      results are from the default mode's (which equals the reference bit for bit in tests/) ----
+    f32_mode = None
+    if rank == 0 and world == 1 and not args.no_f32 and args.precision == 0:
+        f32_mode = bench_f32_mode(torch, abi, args, local_rank, stream, batch, (pts, ins, q, descs), out, peak, n_proj_total)
+
     # ---- CPU baseline on a bounded sample (rank 0 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -361,12 +367,59 @@ def run_gpu(args):
                          "whole_step_frac": (32.0 * n_proj_total / (ms_per_step * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
             "also": also,
+            "single_precision_mode": f32_mode,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def bench_f32_mode(torch, abi, args, device, stream, batch, arrays, exact, peak, n_proj_total):
+    """Same batch, deskew_precision = 1: step time, k_deskew_bin roofline fraction, agreement with the default mode."""
+    pts, ins, q, descs = arrays
+    ctx = abi.Context(device, deskew_precision=1)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_extrinsics(batch.shape.rig.pose_b_c, batch.shape.rig.pose_c_l, batch.shape.rig.td_b_l)
+    ctx.batch_set_wave(args.wave)
+    ctx.batch_upload(pts, ins, q, descs)
+    for _ in range(3):
+        ctx.batch_run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        ctx.batch_run()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    ctx.set_profiling(True)
+    prof_ms, prof_n = np.zeros(4), np.zeros(4)
+    for _ in range(3):
+        ctx.batch_run()
+        m, n = ctx.batch_kernel_ms()
+        prof_ms += m
+        prof_n += n
+    ctx.set_profiling(False)
+    got = ctx.batch_download()
+    ctx.close()
+    launch_ms = prof_ms[1] / max(prof_n[1], 1)
+    both = (got["type"] == 1) & (exact["type"] == 1)
+    d0, d1 = exact["xyz_depth"][both, 3].astype(np.float64), got["xyz_depth"][both, 3].astype(np.float64)
+    rel = np.abs(d1 - d0) / np.abs(d0) if both.any() else np.zeros(1)
+    nq = len(got["type"])
+    return {
+        "ms_per_step": ms, "features_per_s": nq / (ms * 1e-3), "lidar_pts_per_s": n_proj_total / (ms * 1e-3),
+        "k_deskew_bin_launch_ms": launch_ms,
+        "k_deskew_bin_hbm_frac": 32.0 * n_proj_total / (launch_ms * 1e-3) / 1e9 / peak,
+        "validity_agreement": float(np.mean(got["type"] == exact["type"])),
+        "depth_within_1e-4": float(np.mean(rel <= 1e-4)),
+        "depth_identical": float(np.mean(d0 == d1)),
+        "max_depth_rel_diff": float(rel.max()),
+        "cells_m_equal": float(np.mean(got["m"] == exact["m"])),
+        "note": "agreement is against the default (f64) mode of this library on the same batch",
+    }
 
 
 def bench_cfg3(torch, abi, synth, device, stream, peak, n_kf=6, steps=10):
@@ -449,6 +502,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-cfg3", action="store_true", help="skip the secondary Ouster OS1-128 x 20-scan measurement")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--precision", type=int, default=0, choices=[0, 1], help="levins_config.deskew_precision of the measured context")
+    ap.add_argument("--no-f32", action="store_true", help="skip the secondary measurement of the single-precision deskew mode")
     ap.add_argument("--no-stream", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

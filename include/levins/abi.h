@@ -92,7 +92,9 @@ typedef struct levins_config {
     double plane_residual_threshold; /* 0.1 m, tracking.cc:600 */
     double range_spread_threshold;   /* 0.5 m, tracking.cc:609 */
     int32_t nearest_distance_counts; /* ASSOCIATE_NEAREST_DISTANCE_COUNTS = 3, tracking.h:121 */
-    int32_t reserved0;
+    int32_t deskew_precision;        /* 0 (default): the reference's f64 pose algebra, deskewed coordinates bit-identical to the
+                                      * reference; 1: f32 algebra (f64 time differences), coordinates within ~1e-6 relative
+                                      * (bar: 1e-4), cell membership of points next to a cell boundary may differ */
     uint64_t max_points;             /* device ring-buffer capacity in points (streaming API) */
     uint64_t max_ins;                /* INS samples per keyframe (reference: MAXIMUM_INS_NUMBER 1000 + RESERVED 400) */
     uint64_t max_features;           /* feature queries per keyframe */

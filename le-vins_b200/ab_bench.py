@@ -21,6 +21,9 @@ if __name__ == "__main__":
                 d = json.loads(r.stdout.strip().splitlines()[-1])
                 ro = d["roofline"]
                 print(f"{n:10s} round {rnd}: step {d['ms_per_step']:.4f} ms  k_deskew_bin {1e3 * ro['launch_ms']:.1f} us  frac {ro['frac']:.3f}  "
-                      f"share {ro['kernel_time_share']}  cfg3 {d['also']['k_deskew_bin_hbm_frac'] if d.get('also') else None}", flush=True)
+                      f"cfg3 {d['also']['k_deskew_bin_hbm_frac'] if d.get('also') else None}  "
+                      f"f32 {d['single_precision_mode']['k_deskew_bin_launch_ms'] * 1e3 if d.get('single_precision_mode') else None} us "
+                      f"step {d['single_precision_mode']['ms_per_step'] if d.get('single_precision_mode') else None}  "
+                      f"share {[round(v, 3) for v in ro['kernel_time_share'].values()]}", flush=True)
             except Exception as ex:  # noqa: BLE001
                 print(n, "failed", ex, r.stdout[-500:], r.stderr[-1500:], flush=True)

@@ -88,6 +88,7 @@ struct PrepareArgs {
     unsigned long long pts_cap; // ring capacity (ULLONG_MAX for linear pools)
     const InsSample* ins;
     Interval* table;
+    IntervalF* tableF; // the same entries in f32 (single-precision mode), same indexing
     RingState* ring; // streaming: the keyframe's buffer is the ring (le_vins.cc:410-437), and is popped
     Extrinsics ext;
     Consts c;
@@ -219,6 +220,27 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
         e.fast = (ordered && e.theta * e.theta < 2.44140625e-4) ? 1.0 : 0.0;
         tab[j] = e;
         if (j == 0) tab[nins] = e; // slot nins: the fallback again, as the successor of the last interval (k_chunk_desc)
+        {
+            IntervalF f;
+            f.t_lo = e.t_lo;
+            f.t_hi = e.t_hi;
+            f.ts0 = e.ts0;
+            f.inv_dts = (float) e.inv_dts;
+            f.fast = (float) e.fast;
+#pragma unroll
+            for (int i = 0; i < 9; i++) f.A[i] = (float) e.A[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+                f.k[i] = (float) e.k[i];
+                f.c0[i] = (float) e.c0[i];
+                f.c1[i] = (float) e.c1[i];
+            }
+            f.theta = (float) e.theta;
+            f.pad = 0.f;
+            IntervalF* __restrict__ tabF = a.tableF + kf->table_begin;
+            tabF[j] = f;
+            if (j == 0) tabF[nins] = f;
+        }
     }
 }
 
@@ -243,6 +265,9 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
 #ifndef LV_MINBLK
 #define LV_MINBLK 2
 #endif
+#ifndef LV_MINBLK_F // CTAs per SM of the single-precision instantiations (half the register state per point)
+#define LV_MINBLK_F LV_MINBLK
+#endif
 #ifndef LV_KO // knock-out experiments (timing only, results are wrong): 1 no RED, 2 no deskew math, 4 no cell math, 8 loads only
 #define LV_KO 0
 #endif
@@ -263,7 +288,7 @@ constexpr int WARP_SMEM = WARP_QKF_OFF + AMBQ * 4;
 constexpr int DESKEW_SMEM = DESKEW_WARPS * WARP_SMEM; // 113 280 B: two CTAs per SM
 constexpr int DESKEW_BLOCK = DESKEW_THREADS;
 static_assert(STAGE_BYTES % 16 == 0 && WARP_SMEM % 16 == 0 && WARP_Q_OFF % 16 == 0, "TMA / vector alignment");
-static_assert(LV_MINBLK * (DESKEW_SMEM + 1024) <= 228 * 1024, "CTAs per SM");
+static_assert(LV_MINBLK * (DESKEW_SMEM + 1024) <= 228 * 1024 && LV_MINBLK_F * (DESKEW_SMEM + 1024) <= 228 * 1024, "CTAs per SM");
 
 // what lane 0 needs to fetch one chunk, written by k_chunk_desc
 struct __align__(16) ChunkDesc {
@@ -279,11 +304,13 @@ struct DeskewArgs {
     const PointXYZIT* pts;
     unsigned long long pts_cap;
     const Interval* table;
+    const IntervalF* tableF;  // single-precision mode
     ChunkDesc* chunks;        // [n_kf][chunks_per_kf]
     unsigned long long* zbuf; // [n_kf][CELLS]
     PointXYZI* cloud_out;     // streaming only (n_kf == 1), nullable
     unsigned gen;             // z-buffer generation of this launch
     Extrinsics ext;
+    ExtrinsicsF extf; // single-precision mode
     Consts c;
 };
 
@@ -379,6 +406,7 @@ __device__ __forceinline__ int cell_id(float x, float y, float z, const Consts& 
 }
 
 // lane 0: start the copies of one chunk into a stage of the warp's ring
+template <bool FAST>
 __device__ __forceinline__ void issue_chunk(const DeskewArgs& a, const ChunkDesc& d, unsigned char* stage, unsigned long long* bar) {
     const unsigned cnt = d.cnt;
     *reinterpret_cast<unsigned*>(stage + STAGE_HDR_OFF) = cnt;
@@ -386,8 +414,12 @@ __device__ __forceinline__ void issue_chunk(const DeskewArgs& a, const ChunkDesc
         mbar_arrive(bar); // release: the header is visible to whoever passes the barrier
         return;
     }
-    mbar_arrive_expect_tx(bar, cnt * 32u + 2u * (unsigned) sizeof(Interval));
-    tma_bulk_g2s(stage + STAGE_ENT_OFF, a.table + d.ent0, 2u * (unsigned) sizeof(Interval), bar); // entries ent0, ent0 + 1
+    constexpr unsigned ENT = 2u * (unsigned) (FAST ? sizeof(IntervalF) : sizeof(Interval)); // entries ent0, ent0 + 1
+    mbar_arrive_expect_tx(bar, cnt * 32u + ENT);
+    if (FAST)
+        tma_bulk_g2s(stage + STAGE_ENT_OFF, a.tableF + d.ent0, ENT, bar);
+    else
+        tma_bulk_g2s(stage + STAGE_ENT_OFF, a.table + d.ent0, ENT, bar);
     const unsigned long long room = a.pts_cap - d.phys; // ring: the chunk may wrap around the end
     const unsigned first = room < cnt ? (unsigned) room : cnt;
     tma_bulk_g2s(stage, a.pts + d.phys, first * 32u, bar);
@@ -409,8 +441,8 @@ __device__ __noinline__ void flush_undecided(const float4* q, const unsigned* qk
     __syncwarp();
 }
 
-template <int LIBM_MODE, bool WRITE_CLOUD>
-__global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
+template <int LIBM_MODE, bool WRITE_CLOUD, bool FAST>
+__global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + warp * WARP_SMEM;
@@ -438,7 +470,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __
                 d.phys = (unsigned long long) r.x | ((unsigned long long) r.y << 32);
                 d.ent0 = r.z;
                 d.cnt = r.w;
-                issue_chunk(a, d, wbase + i * STAGE_BYTES, full + i);
+                issue_chunk<FAST>(a, d, wbase + i * STAGE_BYTES, full + i);
             }
         }
     }
@@ -455,7 +487,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __
             d.phys = (unsigned long long) dn.x | ((unsigned long long) dn.y << 32);
             d.ent0 = dn.z;
             d.cnt = dn.w;
-            issue_chunk(a, d, wbase + s_fill * STAGE_BYTES, full + s_fill);
+            issue_chunk<FAST>(a, d, wbase + s_fill * STAGE_BYTES, full + s_fill);
         }
         if (c + DESKEW_STAGES * W < total) dn = __ldg(reinterpret_cast<const uint4*>(a.chunks + c + DESKEW_STAGES * W));
         const unsigned char* st = wbase + s * STAGE_BYTES;
@@ -512,21 +544,25 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __
             if (any_kept) {
 #endif
                 // which of the two staged entries brackets every kept point of this thread (checked, not assumed)
-                const Interval* E0 = reinterpret_cast<const Interval*>(st + STAGE_ENT_OFF);
-                const Interval* E1 = E0 + 1;
+                constexpr unsigned ENT_SZ = FAST ? sizeof(IntervalF) : sizeof(Interval);
+                const unsigned char* E0 = st + STAGE_ENT_OFF;
+                const unsigned char* E1 = E0 + ENT_SZ;
+                auto usable = [](const unsigned char* e) { // Interval::fast / IntervalF::fast
+                    return FAST ? reinterpret_cast<const IntervalF*>(e)->fast != 0.f : reinterpret_cast<const Interval*>(e)->fast != 0.0;
+                };
                 const double2 T0 = *reinterpret_cast<const double2*>(E0);
                 const unsigned long long lo0 = (unsigned long long) __double_as_longlong(T0.x);
-                const unsigned long long w0 = E0->fast != 0.0 ? (unsigned long long) __double_as_longlong(T0.y) - lo0 : 0ull;
+                const unsigned long long w0 = usable(E0) ? (unsigned long long) __double_as_longlong(T0.y) - lo0 : 0ull;
                 bool in0 = true;
 #pragma unroll
                 for (int j = 0; j < DESKEW_GROUP; j++) in0 &= !kept[j] || key_brackets(lo0, w0, tt[j]);
-                const Interval* ep = E0;
+                const unsigned char* ep = E0;
                 bool fast = in0;
                 unsigned long long lo1 = 0, w1 = 0;
                 if (!in0) {
                     const double2 T1 = *reinterpret_cast<const double2*>(E1);
                     lo1 = (unsigned long long) __double_as_longlong(T1.x);
-                    w1 = E1->fast != 0.0 ? (unsigned long long) __double_as_longlong(T1.y) - lo1 : 0ull;
+                    w1 = usable(E1) ? (unsigned long long) __double_as_longlong(T1.y) - lo1 : 0ull;
                     bool in1 = true;
 #pragma unroll
                     for (int j = 0; j < DESKEW_GROUP; j++) in1 &= !kept[j] || key_brackets(lo1, w1, tt[j]);
@@ -534,24 +570,36 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __
                     fast = in1;
                 }
                 if (fast) {
-                    // common case: one entry for the 4 points, straight-line code, the 4 points interleave
-                    EntryRegs e;
-                    load_entry_shared(ep, e);
+                    // common case: one entry for the group, straight-line code, the points interleave
+                    if constexpr (FAST) {
+                        EntryRegsF e;
+                        load_entry_f(reinterpret_cast<const IntervalF*>(ep), e);
 #pragma unroll
-                    for (int j = 0; j < DESKEW_GROUP; j++) deskew_core<true>(px[j], py[j], pz[j], tt[j], e, a.ext, ox[j], oy[j], oz[j]);
+                        for (int j = 0; j < DESKEW_GROUP; j++) deskew_core_f32(px[j], py[j], pz[j], tt[j], e, a.extf, ox[j], oy[j], oz[j]);
+                    } else {
+                        EntryRegs e;
+                        load_entry_shared(reinterpret_cast<const Interval*>(ep), e);
+#pragma unroll
+                        for (int j = 0; j < DESKEW_GROUP; j++) deskew_core<true>(px[j], py[j], pz[j], tt[j], e, a.ext, ox[j], oy[j], oz[j]);
+                    }
                 } else {
                     // the thread's points straddle intervals, or need an entry that was not staged (window edges, large
                     // rotation, unordered times): one entry per point
 #pragma unroll
                     for (int j = 0; j < DESKEW_GROUP; j++)
                         if (kept[j]) {
-                            const Interval* epj = key_brackets(lo0, w0, tt[j])   ? E0
-                                                  : key_brackets(lo1, w1, tt[j]) ? E1
-                                                                                 : find_entry_global(a.kfs + kfi, a.table, tt[j]);
-                            EntryRegs e;
-                            load_entry_shared(epj, e); // generic pointer: shared or global
+                            const unsigned char* es = key_brackets(lo0, w0, tt[j]) ? E0 : key_brackets(lo1, w1, tt[j]) ? E1 : nullptr;
                             float x, y, z;
-                            deskew_core<false>(px[j], py[j], pz[j], tt[j], e, a.ext, x, y, z);
+                            if (FAST && es) {
+                                EntryRegsF e;
+                                load_entry_f(reinterpret_cast<const IntervalF*>(es), e);
+                                deskew_core_f32(px[j], py[j], pz[j], tt[j], e, a.extf, x, y, z);
+                            } else { // (in single-precision mode too: the rare cases take the f64 formula)
+                                const Interval* epj = (!FAST && es) ? reinterpret_cast<const Interval*>(es) : find_entry_global(a.kfs + kfi, a.table, tt[j]);
+                                EntryRegs e;
+                                load_entry_shared(epj, e); // generic pointer: shared or global
+                                deskew_core<false>(px[j], py[j], pz[j], tt[j], e, a.ext, x, y, z);
+                            }
                             ox[j] = x;
                             oy[j] = y;
                             oz[j] = z;

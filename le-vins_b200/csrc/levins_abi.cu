@@ -46,6 +46,7 @@ struct levins_ctx {
     levins_config cfg{};
     Consts consts{};
     Extrinsics ext{};
+    ExtrinsicsF extf{}; // the same, rounded to f32 (single-precision mode)
     bool have_ext = false;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -62,7 +63,7 @@ struct levins_ctx {
     DevBuf ring_state; // RingState
     uint64_t ring_tail = 0;     // physical index one past the newest point
     uint64_t ring_count_ub = 0; // host's upper bound of the live point count
-    DevBuf s_ins, s_table, s_kf, s_queries;
+    DevBuf s_ins, s_table, s_tableF, s_kf, s_queries;
     DevBuf chunks; // ChunkDesc of the current k_deskew_bin launch (streaming and batch)
     DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2, s_nn, s_nn_meta;
     DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
@@ -78,7 +79,11 @@ struct levins_ctx {
     size_t pinned_bytes = 0;
 
     // ---- batch state ----
-    DevBuf b_pts, b_ins, b_table, b_queries, b_kfs;
+    DevBuf b_pts, b_ins, b_table, b_tableF, b_queries, b_kfs;
+    // the f32 twin of an interval-table pool (same indexing)
+    const IntervalF* tableF_of(const Interval* t) const {
+        return t == static_cast<const Interval*>(s_table.p) ? static_cast<const IntervalF*>(s_tableF.p) : static_cast<const IntervalF*>(b_tableF.p);
+    }
     DevBuf b_results; // xyz_depth (16 B / query) immediately followed by type (1 B / query): one contiguous block, so that an
                       // exchange step can move both with a single collective
     size_t b_results_nq = 0;
@@ -179,6 +184,7 @@ int next_gen(levins_ctx* ctx, unsigned long long* z, size_t n, unsigned* gen) {
 int ensure_stream_buffers(levins_ctx* ctx, size_t n_ins, size_t n_feat) {
     CU(ctx->s_ins.ensure(std::max<size_t>(n_ins, 1) * sizeof(InsSample)));
     CU(ctx->s_table.ensure((std::max<size_t>(n_ins, 1) + 1) * sizeof(Interval))); // + the fallback copy
+    CU(ctx->s_tableF.ensure((std::max<size_t>(n_ins, 1) + 1) * sizeof(IntervalF)));
     CU(ctx->s_kf.ensure(sizeof(KfState)));
     CU(ctx->s_queries.ensure(std::max<size_t>(n_feat, 1) * 3 * sizeof(float)));
     CU(ctx->s_type.ensure(std::max<size_t>(n_feat, 1)));
@@ -230,25 +236,21 @@ int launch_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_k
 int launch_deskew(levins_ctx* ctx, DeskewArgs& a, bool write_cloud) {
     const unsigned total = a.n_kf * a.chunks_per_kf;
     if (total == 0) return LEVINS_OK;
+    using Kernel = void (*)(DeskewArgs);
+    static const Kernel kernels[2][2][2] = {
+        {{k_deskew_bin<0, false, false>, k_deskew_bin<0, false, true>}, {k_deskew_bin<0, true, false>, k_deskew_bin<0, true, true>}},
+        {{k_deskew_bin<1, false, false>, k_deskew_bin<1, false, true>}, {k_deskew_bin<1, true, false>, k_deskew_bin<1, true, true>}}};
     if (!ctx->deskew_attr_set) {
-        CU(cudaFuncSetAttribute(k_deskew_bin<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
-        CU(cudaFuncSetAttribute(k_deskew_bin<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
-        CU(cudaFuncSetAttribute(k_deskew_bin<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
-        CU(cudaFuncSetAttribute(k_deskew_bin<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
+        for (int i = 0; i < 8; i++)
+            CU(cudaFuncSetAttribute(kernels[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
         ctx->deskew_attr_set = true;
     }
-    const unsigned grid = std::min<unsigned>((total + DESKEW_WARPS - 1) / DESKEW_WARPS, (unsigned) LV_MINBLK * (unsigned) ctx->num_sms);
-    if (ctx->consts.libm_mode == 0) {
-        if (write_cloud)
-            k_deskew_bin<0, true><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
-        else
-            k_deskew_bin<0, false><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
-    } else {
-        if (write_cloud)
-            k_deskew_bin<1, true><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
-        else
-            k_deskew_bin<1, false><<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
-    }
+    const bool fast = ctx->cfg.deskew_precision == 1;
+    const unsigned grid = std::min<unsigned>((total + DESKEW_WARPS - 1) / DESKEW_WARPS,
+                                             (unsigned) (fast ? LV_MINBLK_F : LV_MINBLK) * (unsigned) ctx->num_sms);
+    a.tableF = fast ? ctx->tableF_of(a.table) : nullptr;
+    a.extf = ctx->extf;
+    kernels[ctx->consts.libm_mode ? 1 : 0][write_cloud ? 1 : 0][fast ? 1 : 0]<<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return LEVINS_OK;
@@ -286,6 +288,7 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     pa.pts_cap = ctx->cfg.max_points;
     pa.ins = ctx->s_ins.as<InsSample>();
     pa.table = ctx->s_table.as<Interval>();
+    pa.tableF = ctx->s_tableF.as<IntervalF>();
     pa.ring = ctx->ring_state.as<RingState>();
     pa.ext = ctx->ext;
     pa.c = ctx->consts;
@@ -442,7 +445,8 @@ extern "C" int levins_create(int device, const levins_config* cfg, levins_ctx** 
         memcpy(&ctx->cfg, cfg, n);
         ctx->cfg.struct_size = sizeof(levins_config);
     }
-    if (ctx->cfg.max_points == 0 || ctx->cfg.max_ins == 0 || ctx->cfg.stack_interval <= 0) {
+    if (ctx->cfg.max_points == 0 || ctx->cfg.max_ins == 0 || ctx->cfg.stack_interval <= 0 || ctx->cfg.deskew_precision < 0 ||
+        ctx->cfg.deskew_precision > 1) {
         delete ctx;
         return LEVINS_ERR_ARG;
     }
@@ -463,7 +467,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->chunks, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
+    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->chunks, &ctx->s_tableF, &ctx->b_tableF, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
@@ -506,6 +510,14 @@ extern "C" int levins_set_extrinsics(levins_ctx* ctx, const levins_pose* pose_b_
     memcpy(ctx->ext.Rcl, pose_c_l->R, sizeof(double) * 9);
     memcpy(ctx->ext.tcl, pose_c_l->t, sizeof(double) * 3);
     ctx->ext.td_b_l = td_b_l;
+    for (int i = 0; i < 9; i++) {
+        ctx->extf.Rcl[i] = (float) ctx->ext.Rcl[i];
+        ctx->extf.Rbc[i] = (float) ctx->ext.Rbc[i];
+    }
+    for (int i = 0; i < 3; i++) {
+        ctx->extf.tcl[i] = (float) ctx->ext.tcl[i];
+        ctx->extf.tbc[i] = (float) ctx->ext.tbc[i];
+    }
     ctx->have_ext = true;
     return LEVINS_OK;
 }
@@ -831,6 +843,7 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
     CU(ctx->b_pts.ensure(std::max<size_t>(n_points, 1) * sizeof(PointXYZIT)));
     CU(ctx->b_ins.ensure(n_ins * sizeof(InsSample)));
     CU(ctx->b_table.ensure(table_entries * sizeof(Interval)));
+    CU(ctx->b_tableF.ensure(table_entries * sizeof(IntervalF)));
     CU(ctx->b_queries.ensure(std::max<size_t>(n_queries, 1) * 12));
     CU(ctx->b_kfs.ensure(n_kf * sizeof(KfState)));
     CU(ctx->b_results.ensure(std::max<size_t>(n_queries, 1) * 17));
@@ -897,6 +910,7 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
     pa.pts_cap = ~0ull;
     pa.ins = ctx->b_ins.as<InsSample>();
     pa.table = ctx->b_table.as<Interval>();
+    pa.tableF = ctx->b_tableF.as<IntervalF>();
     pa.ring = nullptr;
     pa.ext = ctx->ext;
     pa.c = ctx->consts;

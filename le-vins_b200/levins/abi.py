@@ -36,7 +36,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("libm_mode", C.c_int32), ("stack_interval", C.c_double),
         ("reserved_buffer_length", C.c_double), ("nearest_depth", C.c_double), ("farthest_depth", C.c_double),
         ("plane_residual_threshold", C.c_double), ("range_spread_threshold", C.c_double),
-        ("nearest_distance_counts", C.c_int32), ("reserved0", C.c_int32), ("max_points", C.c_uint64),
+        ("nearest_distance_counts", C.c_int32), ("deskew_precision", C.c_int32), ("max_points", C.c_uint64),
         ("max_ins", C.c_uint64), ("max_features", C.c_uint64),
     ]
 

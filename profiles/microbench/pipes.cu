@@ -32,6 +32,10 @@ __global__ void k(float* out, long long* cyc, float seed) {
             if (OP == 4) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(f[i]));
             if (OP == 5) d[i] = d[i] * da;
             if (OP == 6) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pa));
+            if (OP == 7) { d[i] = fma(d[i], da, db); f[i] = fmaf(f[i], a, b); }                       // DFMA + FFMA, independent
+            if (OP == 8) { asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(f[i])); d[i] = fma(d[i], da, db); } // MUFU + DFMA
+            if (OP == 9) { d[i] = fma(d[i], da, db); p[i] = p[i] * 0x9E3779B97F4A7C15ull + (p[i] >> 7); } // DFMA + integer work
+            if (OP == 10) { f[i] = fmaf(f[i], a, b); p[i] = (p[i] ^ (p[i] >> 7)) + pa; }                // FFMA + ALU
         }
     }
     const long long t1 = clock64();
@@ -49,7 +53,7 @@ void run(const char* name, int warps, float* out, long long* cyc) {
     long long c;
     cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
     const double per = (double) c / ITERS;
-    const int ops_per_iter = CHAINS * (OP == 3 ? 2 : 1);
+    const int ops_per_iter = CHAINS * ((OP == 3 || OP >= 7) ? 2 : 1);
     printf("%-22s chains %d warps/SM %2d: %7.2f cyc/iter  -> %.2f cyc per dependent op, %.3f warp-instr/cyc/SMSP\n", name, CHAINS, warps, per,
            per / (OP == 3 ? 2 : 1), (double) ops_per_iter * warps / 4.0 / per);
 }
@@ -71,5 +75,9 @@ int main() {
     ALL(5, "DMUL")
     ALL(3, "F2F f32->f64->f32")
     ALL(4, "MUFU.RCP")
+    ALL(7, "DFMA+FFMA mixed")
+    ALL(8, "MUFU+DFMA mixed")
+    ALL(9, "DFMA+int mixed")
+    ALL(10, "FFMA+ALU mixed")
     return 0;
 }
