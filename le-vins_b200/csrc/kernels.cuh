@@ -18,7 +18,10 @@
 
 namespace lv {
 
-constexpr int DESKEW_THREADS = 256;
+#ifndef LV_THREADS
+#define LV_THREADS 256
+#endif
+constexpr int DESKEW_THREADS = LV_THREADS;
 constexpr int FINALIZE_THREADS = 256;
 constexpr int ASSOC_WARPS = 4;
 constexpr int WIN_ROWS = 4; // |d row| <= 4, |d col| <= 6: every point within the acceptance radius 3*sin(0.3 deg)
