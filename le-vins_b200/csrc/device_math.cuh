@@ -547,10 +547,18 @@ struct KfView {
     double t0, t_last, inv_mean_dt;
 };
 
+template <bool NC = true> // NC: the table is read-only for this kernel (ld.global.nc); false inside the kernel that writes it
 __device__ __noinline__ int find_interval_slow(const Interval* __restrict__ tab, int n_ins, double t, int g, int lo, int hi) {
 #pragma unroll 1
     for (int it = 0; it < 48; it++) {
-        const double2 ab = __ldg(reinterpret_cast<const double2*>(tab + g));
+        double2 ab;
+        if (NC) {
+            ab = __ldg(reinterpret_cast<const double2*>(tab + g));
+        } else {
+            const volatile double* pv = reinterpret_cast<const volatile double*>(tab + g);
+            ab.x = pv[0];
+            ab.y = pv[1];
+        }
         if (t < ab.x) {
             hi = g - 1;
             g = (it < 2) ? g - 1 : (lo + hi) >> 1;

@@ -83,6 +83,55 @@ __global__ void k_ring_append(RingState* ring, const PointXYZIT* __restrict__ pt
 }
 
 // ------------------------------------------------------------------------------------------------
+// chunks: k_deskew_bin's unit of work is 128 consecutive points of one keyframe (one warp, one iteration)
+// ------------------------------------------------------------------------------------------------
+constexpr int DESKEW_PPT = 4;              // points per thread and chunk
+constexpr int CHUNK_PTS = 32 * DESKEW_PPT; // 128 points = 4 KB
+// what lane 0 of the owning warp needs to fetch one chunk
+struct __align__(16) ChunkDesc {
+    unsigned long long phys; // physical index of the chunk's first point in the pool / ring
+    unsigned ent0;           // absolute index (into the interval-table pool) of the entry of the chunk's first point
+    unsigned cnt;            // points in the chunk (0 = empty)
+};
+
+// Descriptor of chunk `c` of a keyframe.  The entry index is only a hint for k_deskew_bin (every point still checks
+// that its entry brackets it), so any answer is correct; the right one is fast.  k_deskew_bin stages entries idx and
+// idx + 1: the next interval, the fallback copy in slot nins after the last one, the first interval for a chunk that
+// starts before the window.  NC = false inside the kernel that has just written the table.
+template <bool NC>
+__device__ __forceinline__ ChunkDesc make_chunk_desc(unsigned c, unsigned n_proj, unsigned long long proj_begin, const PointXYZIT* __restrict__ pts,
+                                                     unsigned long long pts_cap, double td_b_l, const Interval* __restrict__ tab,
+                                                     unsigned long long table_begin, int nins, double t0, double t_last, double inv_mean_dt) {
+    ChunkDesc d;
+    d.phys = 0;
+    d.ent0 = 0;
+    d.cnt = 0;
+    const unsigned off = c * CHUNK_PTS;
+    if (off < n_proj) {
+        const unsigned long long phys = wrap(proj_begin + off, pts_cap);
+        const double t = pts[phys].time + td_b_l; // le_vins.cc:455
+        int idx = 0;
+        if (!(nins < 2 || t0 > t || t_last <= t)) { // misc.cc:28-30
+            int g = 1 + (int) ((t - t0) * inv_mean_dt);
+            g = min(max(g, 1), nins - 1);
+            double2 ab;
+            if (NC) {
+                ab = __ldg(reinterpret_cast<const double2*>(tab + g));
+            } else {
+                const volatile double* pv = reinterpret_cast<const volatile double*>(tab + g);
+                ab.x = pv[0];
+                ab.y = pv[1];
+            }
+            idx = ((ab.x <= t) && (t < ab.y)) ? g : find_interval_slow<NC>(tab, nins, t, g, 1, nins - 1);
+        }
+        d.phys = phys;
+        d.ent0 = (unsigned) (table_begin + idx);
+        d.cnt = min((unsigned) CHUNK_PTS, n_proj - off);
+    }
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_prepare: one block per keyframe
 // ------------------------------------------------------------------------------------------------
 struct PrepareArgs {
@@ -92,6 +141,8 @@ struct PrepareArgs {
     const InsSample* ins;
     Interval* table;
     IntervalF* tableF; // the same entries in f32 (single-precision mode), same indexing
+    ChunkDesc* chunks; // batch: [gridDim.x][chunks_per_kf], written here; streaming (null): k_chunk_desc does it
+    unsigned chunks_per_kf;
     RingState* ring; // streaming: the keyframe's buffer is the ring (le_vins.cc:410-437), and is popped
     Extrinsics ext;
     Consts c;
@@ -245,6 +296,21 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
             if (j == 0) tabF[nins] = f;
         }
     }
+    // batch mode: the chunk descriptors of this keyframe (k_deskew_bin's work list), while the table is hot in L1/L2
+    if (a.chunks) {
+        __syncthreads(); // the table entries written by the other threads of the block are visible now
+        const unsigned long long first = s_first;
+        const unsigned long long end = s_end > first ? s_end : first;
+        const unsigned n_proj = (unsigned) (end - first);
+        const unsigned long long proj_begin = wrap(begin + first, a.pts_cap);
+        const double t_first = w[0].time, t_last = w[nins - 1].time;
+        const double inv_mean_dt = nins > 1 ? (double) (nins - 1) / (t_last - t_first) : 0.0;
+        const unsigned long long table_begin = kf->table_begin;
+        ChunkDesc* __restrict__ out = a.chunks + (size_t) blockIdx.x * a.chunks_per_kf;
+        for (unsigned c = threadIdx.x; c < a.chunks_per_kf; c += blockDim.x)
+            out[c] = make_chunk_desc<false>(c, n_proj, proj_begin, a.pts, a.pts_cap, a.ext.td_b_l, tab, table_begin, nins, t_first, t_last,
+                                            inv_mean_dt);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -274,10 +340,8 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
 #ifndef LV_KO // knock-out experiments (timing only, results are wrong): 1 no RED, 2 no deskew math, 4 no cell math, 8 loads only
 #define LV_KO 0
 #endif
-constexpr int DESKEW_PPT = 4;          // points per thread and chunk
 constexpr int DESKEW_GROUP = LV_GROUP; // of which this many are in flight together (register pressure vs interleaving)
 constexpr int DESKEW_WARPS = DESKEW_THREADS / 32;
-constexpr int CHUNK_PTS = 32 * DESKEW_PPT; // 128 points = 4 KB: one warp, one iteration
 constexpr int CHUNK_BYTES = CHUNK_PTS * 32;
 constexpr int DESKEW_STAGES = LV_STAGES;
 constexpr int STAGE_ENT_OFF = CHUNK_BYTES;                        // two interval entries (2 x 192 B)
@@ -292,13 +356,6 @@ constexpr int DESKEW_SMEM = DESKEW_WARPS * WARP_SMEM; // 113 280 B: two CTAs per
 constexpr int DESKEW_BLOCK = DESKEW_THREADS;
 static_assert(STAGE_BYTES % 16 == 0 && WARP_SMEM % 16 == 0 && WARP_Q_OFF % 16 == 0, "TMA / vector alignment");
 static_assert(LV_MINBLK * (DESKEW_SMEM + 1024) <= 228 * 1024 && LV_MINBLK_F * (DESKEW_SMEM + 1024) <= 228 * 1024, "CTAs per SM");
-
-// what lane 0 needs to fetch one chunk, written by k_chunk_desc
-struct __align__(16) ChunkDesc {
-    unsigned long long phys; // physical index of the chunk's first point in the pool / ring
-    unsigned ent0;           // absolute index (into the interval-table pool) of the entry of the chunk's first point
-    unsigned cnt;            // points in the chunk (0 = empty)
-};
 
 struct DeskewArgs {
     KfState* kfs; // first keyframe of this launch
@@ -317,39 +374,16 @@ struct DeskewArgs {
     Consts c;
 };
 
-// k_chunk_desc: one thread per chunk.  The entry index is only a hint for k_deskew_bin (every point still checks that
-// its entry brackets it), so any answer is correct; the right one is fast.
+// k_chunk_desc: one thread per chunk (streaming: a single keyframe with many chunks; batches get their descriptors from
+// k_prepare)
 __global__ void __launch_bounds__(256) k_chunk_desc(const __grid_constant__ DeskewArgs a) {
     const unsigned c = blockIdx.x * 256 + threadIdx.x;
     if (c >= a.n_kf * a.chunks_per_kf) return;
     const unsigned kfi = c / a.chunks_per_kf;
-    const unsigned off = (c - kfi * a.chunks_per_kf) * CHUNK_PTS;
     const KfState* __restrict__ kf = a.kfs + kfi;
-    const unsigned n = kf->n_proj;
-    ChunkDesc d;
-    d.phys = 0;
-    d.ent0 = 0;
-    d.cnt = 0;
-    if (off < n) {
-        const unsigned cnt = min((unsigned) CHUNK_PTS, n - off);
-        const unsigned long long phys = wrap(kf->proj_begin + off, a.pts_cap);
-        const double t = a.pts[phys].time + a.ext.td_b_l; // le_vins.cc:455
-        const Interval* __restrict__ tab = a.table + kf->table_begin;
-        const int nins = (int) kf->ins_count;
-        int idx = 0;
-        if (!(nins < 2 || kf->ins_t0 > t || kf->ins_t_last <= t)) { // misc.cc:28-30
-            int g = 1 + (int) ((t - kf->ins_t0) * kf->inv_mean_dt);
-            g = min(max(g, 1), nins - 1);
-            const double2 ab = __ldg(reinterpret_cast<const double2*>(tab + g));
-            idx = ((ab.x <= t) && (t < ab.y)) ? g : find_interval_slow(tab, nins, t, g, 1, nins - 1);
-        }
-        // k_deskew_bin stages entries idx and idx + 1: the next interval, the fallback copy in slot nins after the last
-        // one, the first interval for a chunk that starts before the window
-        d.phys = phys;
-        d.ent0 = (unsigned) (kf->table_begin + idx);
-        d.cnt = cnt;
-    }
-    a.chunks[c] = d;
+    a.chunks[c] = make_chunk_desc<true>(c - kfi * a.chunks_per_kf, kf->n_proj, kf->proj_begin, a.pts, a.pts_cap, a.ext.td_b_l,
+                                        a.table + kf->table_begin, kf->table_begin, (int) kf->ins_count, kf->ins_t0, kf->ins_t_last,
+                                        kf->inv_mean_dt);
 }
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) ----

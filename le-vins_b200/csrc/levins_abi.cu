@@ -216,15 +216,23 @@ int ensure_ring(levins_ctx* ctx) {
     return LEVINS_OK;
 }
 
-// Chunk descriptors for k_deskew_bin (one thread per 128-point chunk; needs the KfState written by k_prepare).
-int launch_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf) {
+// Chunk descriptors for k_deskew_bin: size the buffer for `n_kf` keyframes of at most `max_pts` points ...
+int size_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf) {
     a.n_kf = n_kf;
     a.chunks_per_kf = (unsigned) ((max_pts + CHUNK_PTS - 1) / CHUNK_PTS);
     const uint64_t total = (uint64_t) a.n_kf * a.chunks_per_kf;
-    if (total == 0) return LEVINS_OK;
     if (total >= (1ull << 30)) return fail(ctx, LEVINS_ERR_CAPACITY, "more than 2^30 chunks in one launch: lower the wave size");
-    CU(ctx->chunks.ensure(total * sizeof(ChunkDesc)));
+    CU(ctx->chunks.ensure(std::max<uint64_t>(total, 1) * sizeof(ChunkDesc)));
     a.chunks = ctx->chunks.as<ChunkDesc>();
+    return LEVINS_OK;
+}
+// ... and fill it with one thread per chunk (streaming: one keyframe, many chunks; needs the KfState written by
+// k_prepare).  Batches get their descriptors from k_prepare itself.
+int launch_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf) {
+    int r = size_chunks(ctx, a, max_pts, n_kf);
+    if (r) return r;
+    const uint64_t total = (uint64_t) a.n_kf * a.chunks_per_kf;
+    if (total == 0) return LEVINS_OK;
     k_chunk_desc<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -914,11 +922,6 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
     pa.ring = nullptr;
     pa.ext = ctx->ext;
     pa.c = ctx->consts;
-    mark(0, true);
-    k_prepare<<<(unsigned) n_kf, 256, 0, ctx->stream>>>(pa);
-    mark(0, false);
-    ctx->launches++;
-    CU(cudaGetLastError());
 
     for (size_t k0 = 0; k0 < n_kf; k0 += wave) {
         const int nw = (int) std::min<size_t>(wave, n_kf - k0);
@@ -940,12 +943,27 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         da.gen = ctx->b_gen;
         da.ext = ctx->ext;
         da.c = ctx->consts;
+        // window search, interval tables and chunk descriptors of the wave (one block per keyframe)
+        r = size_chunks(ctx, da, max_pts, (unsigned) nw);
+        if (r) return r;
+        // (a keyframe's block writes its own descriptors when that is a few rounds of its 256 threads; keyframes with
+        // more chunks than that leave them to k_chunk_desc, one thread per chunk)
+        const bool fused_desc = da.chunks_per_kf <= 2048;
+        pa.kfs = ctx->b_kfs.as<KfState>() + k0;
+        pa.chunks = fused_desc ? da.chunks : nullptr;
+        pa.chunks_per_kf = da.chunks_per_kf;
+        mark(0, true);
+        k_prepare<<<(unsigned) nw, 256, 0, ctx->stream>>>(pa);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        if (!fused_desc) {
+            k_chunk_desc<<<(unsigned) (((uint64_t) da.n_kf * da.chunks_per_kf + 255) / 256), 256, 0, ctx->stream>>>(da);
+            ctx->launches++;
+            CU(cudaGetLastError());
+        }
+        mark(0, false);
         if (max_pts) {
             if (k0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_counted, 0)); // the slots are about to be reused
-            mark(0, true);
-            r = launch_chunks(ctx, da, max_pts, (unsigned) nw);
-            mark(0, false);
-            if (r) return r;
             mark(1, true);
             r = launch_deskew(ctx, da, false);
             mark(1, false);
