@@ -413,10 +413,7 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 __device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
 
 // Eigen's Vector3f::squaredNorm() order: x*x + (y*y + z*z), no contraction
-__device__ __forceinline__ float v3f_sqnorm(float x, float y, float z) {
-    const float2 q = f2_mul(make_float2(y, z), make_float2(y, z));
-    return x * x + (q.x + q.y);
-}
+__device__ __forceinline__ float v3f_sqnorm(float x, float y, float z) { return x * x + (y * y + z * z); }
 
 // ------------------------------------------------------------------------------------------------
 // stage 2: cell of a camera-frame point (tracking.cc:311-331).  Returns -1 when the point is rejected.
@@ -490,7 +487,8 @@ __device__ __forceinline__ float atan_poly(float t) {
 __device__ __forceinline__ bool outside_fov(float x, float y, float z) {
     const float az = fabsf(z);
     const float lim = -az * 2.98023223876953125e-8f; // 2^-25
-    return (z < 0.f) || (fabsf(x) - az >= lim) || (fabsf(y) - az >= lim);
+    // (|x| - az >= lim) or (|y| - az >= lim)  <=>  max(|x|, |y|) - az >= lim: the rounded subtraction is monotone
+    return (z < 0.f) | (fmaxf(fabsf(x), fabsf(y)) - az >= lim);
 }
 
 // atan for the pair (t.x, t.y): atan_poly() on both halves at once
