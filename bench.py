@@ -353,7 +353,8 @@ def run_gpu(args):
                        "l2": f"inputs larger than L2: {pts.nbytes / 1e6:.0f} MB of points per GPU per step"},
             "lidar_pts_per_s": world * pts_per_step * args.steps / (ms_total * 1e-3),
             "keyframes_per_s": world * n_kf * args.steps / (ms_total * 1e-3),
-            "p50_keyframe_ms": p50,
+            "p50_keyframe_ms": p50["pageable"] if p50 else None,
+            "p50_keyframe_ms_pinned_scans": p50["pinned"] if p50 else None,
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
@@ -466,28 +467,39 @@ def load_traffic():
 
 
 def stream_latency(abi, synth, device, n_keyframes=40):
-    """Config-2 streaming: one scan appended per 0.1 s of sensor time, one keyframe every 0.4 s.  Wall time from the
-    first append of a keyframe's new scans to its results on the host; p50 over the keyframes."""
+    """Config-2 streaming: one scan appended per 0.1 s of sensor time, one keyframe every 0.5 s.  Wall time from the
+    first append of a keyframe's new scans to its results on the host; p50 over the keyframes.  Twice: with the scans in
+    ordinary pageable memory (what the unmodified ROS converter hands over) and in page-locked buffers from
+    levins_alloc_host (INTEGRATION.md)."""
     shp = synth.shape(CFG)
     b = synth.make_batch(CFG, n_keyframes, n_unique_scans=12, seed=synth.BASE_SEED + 77)
     per = shp.pts_per_scan
-    ctx = abi.Context(device)
-    ctx.set_extrinsics(shp.rig.pose_b_c, shp.rig.pose_c_l, shp.rig.td_b_l)
-    n_scans = len(b.points) // per
-    times = []
-    scan = 0
-    stamps = b.stamps[::1]
-    # keyframes every 0.4 s of sensor time = every 4th scan boundary; b.stamps are 0.5 s apart, use them directly
-    for k, stamp in enumerate(stamps):
-        kf_ins = b.ins[b.ins_begin[k]: b.ins_begin[k] + b.ins_count[k]]
-        t0 = time.perf_counter()
-        while scan < n_scans and b.points["time"][scan * per] <= stamp + 1e-9:  # everything that started before the stamp
-            ctx.append_scan(b.points[scan * per:(scan + 1) * per])
-            scan += 1
-        ctx.keyframe(float(stamp), kf_ins, b.queries[k])
-        times.append(1e3 * (time.perf_counter() - t0))
-    ctx.close()
-    return float(np.median(times[3:])) if len(times) > 3 else None
+    out = {}
+    for kind in ("pageable", "pinned"):
+        pts, hb = b.points, None
+        if kind == "pinned":
+            hb = abi.HostBuffer(len(b.points))
+            hb.array[:] = b.points
+            pts = hb.array
+        ctx = abi.Context(device)
+        ctx.set_extrinsics(shp.rig.pose_b_c, shp.rig.pose_c_l, shp.rig.td_b_l)
+        n_scans = len(pts) // per
+        times = []
+        scan = 0
+        for k, stamp in enumerate(b.stamps):
+            kf_ins = b.ins[b.ins_begin[k]: b.ins_begin[k] + b.ins_count[k]]
+            t0 = time.perf_counter()
+            while scan < n_scans and pts["time"][scan * per] <= stamp + 1e-9:  # everything that started before the stamp
+                ctx.append_scan(pts[scan * per:(scan + 1) * per])
+                scan += 1
+            ctx.keyframe(float(stamp), kf_ins, b.queries[k])
+            times.append(1e3 * (time.perf_counter() - t0))
+        ctx.close()
+        if hb is not None:
+            pts = None
+            hb.close()
+        out[kind] = float(np.median(times[3:])) if len(times) > 3 else None
+    return out
 
 
 def main():

@@ -127,6 +127,14 @@ int levins_set_extrinsics(levins_ctx *ctx, const levins_pose *pose_b_c, const le
  * and evict from the front while |t_back - t_front| > reserved_buffer_length + 2*stack_interval.
  * Points must be time-sorted within and across scans (the reference assumes it, le_vins.cc:431-437). */
 int levins_append_scan(levins_ctx *ctx, const levins_point_xyzit *points, size_t n);
+
+/* Page-locked host memory for scan buffers (optional).  A scan that lives in such memory is copied to the device
+ * asynchronously at PCIe speed (levins_append_scan returns after ~10 us); a scan in ordinary pageable memory -- e.g. the
+ * pcl::PointCloud the ROS converter fills (ROS/lidar/lidar_converter.cc:35-256) -- is staged by the driver first and
+ * costs ~80 us per 24 000 points.  Typical use: allocate two or three scan-sized buffers once and let the converter
+ * write PointXYZIT records into them in turn. */
+int levins_alloc_host(size_t bytes, void **out);
+int levins_free_host(void *p);
 /* current deque size and its front/back times (synchronises) */
 int levins_buffer_info(levins_ctx *ctx, size_t *n_points, double *t_front, double *t_back);
 int levins_buffer_clear(levins_ctx *ctx);

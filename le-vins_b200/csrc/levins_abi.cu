@@ -75,8 +75,16 @@ struct levins_ctx {
     bool s_cloud_valid = false;
     bool s_image_valid = false;
     bool s_image_from_raw = false; // cells were built from the ring (fused) rather than from a cloud
-    void* pinned = nullptr;        // small pinned staging area for results / state
+    // pinned staging area: [0,256) KfState | [256,512) RingState | [512,1024) misc | INS window | queries | type | xyz_depth.
+    // Small host arrays go through it so that every copy of the streaming path is truly asynchronous (copies from / to
+    // pageable memory block the calling thread one by one).
+    void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    size_t pin_ins() const { return 1024; }
+    size_t pin_q() const { return pin_ins() + ((cfg.max_ins * sizeof(InsSample) + 255) & ~size_t(255)); }
+    size_t pin_type() const { return pin_q() + ((cfg.max_features * 12 + 255) & ~size_t(255)); }
+    size_t pin_xyzd() const { return pin_type() + ((cfg.max_features + 255) & ~size_t(255)); }
+    size_t pin_total() const { return pin_xyzd() + cfg.max_features * 16 + 256; }
 
     // ---- batch state ----
     DevBuf b_pts, b_ins, b_table, b_tableF, b_queries, b_kfs;
@@ -274,19 +282,21 @@ int read_ring_state(levins_ctx* ctx, RingState* out) {
 }
 
 // stage 1 on the ring: k_prepare (+ pops) then k_deskew_bin.  Leaves KfState in s_kf.
-int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins, bool write_cloud, bool bin) {
+int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins, bool write_cloud, bool bin, size_t n_queries = 0) {
     if (!ctx->have_ext) return fail(ctx, LEVINS_ERR_STATE, "levins_set_extrinsics has not been called");
     if (!ins || n_ins == 0) return fail(ctx, LEVINS_ERR_ARG, "empty INS window");
     if (n_ins > ctx->cfg.max_ins) return fail(ctx, LEVINS_ERR_CAPACITY, "INS window larger than config.max_ins");
     if (!ctx->ring.p || ctx->ring_count_ub == 0) return LEVINS_EMPTY; // le_vins.cc:378: lidar_point_buffer_.empty()
-    CU(cudaMemcpyAsync(ctx->s_ins.p, ins, n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
+    char* pin = reinterpret_cast<char*>(ctx->pinned);
+    memcpy(pin + ctx->pin_ins(), ins, n_ins * sizeof(InsSample));
+    CU(cudaMemcpyAsync(ctx->s_ins.p, pin + ctx->pin_ins(), n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
     KfState kf{};
     kf.pt_begin = 0;
     kf.pt_count = 0;
     kf.ins_begin = 0;
     kf.ins_count = n_ins;
     kf.q_begin = 0;
-    kf.q_count = 0;
+    kf.q_count = n_queries; // levins_keyframe: the features follow in the same call
     kf.stamp = stamp;
     memcpy(ctx->pinned, &kf, sizeof(kf));
     CU(cudaMemcpyAsync(ctx->s_kf.p, ctx->pinned, sizeof(kf), cudaMemcpyHostToDevice, ctx->stream));
@@ -461,11 +471,11 @@ extern "C" int levins_create(int device, const levins_config* cfg, levins_ctx** 
     ctx->consts = make_consts(ctx->cfg);
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost(&ctx->pinned, 1 << 20) != cudaSuccess) {
+        cudaMallocHost(&ctx->pinned, std::max<size_t>(ctx->pin_total(), 1 << 20)) != cudaSuccess) {
         delete ctx;
         return LEVINS_ERR_CUDA;
     }
-    ctx->pinned_bytes = 1 << 20;
+    ctx->pinned_bytes = std::max<size_t>(ctx->pin_total(), 1 << 20);
     ctx->own_stream = true;
     *out = ctx;
     return LEVINS_OK;
@@ -558,6 +568,9 @@ extern "C" int levins_append_scan(levins_ctx* ctx, const levins_point_xyzit* poi
     const uint64_t tail = ctx->ring_tail;
     const uint64_t first = std::min<uint64_t>(n, cap - tail);
     PointXYZIT* base = ctx->ring.as<PointXYZIT>();
+    // (a scan in pageable memory is staged by the driver at ~10 GB/s and blocks the caller meanwhile; staging it here
+    // into page-locked slots was measured and is no faster -- the host copy is the cost.  Scans written directly into
+    // levins_alloc_host() buffers avoid it: ~10 us instead of ~80 us per 24 000-point scan.)
     CU(cudaMemcpyAsync(base + tail, points, first * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
     if (first < n)
         CU(cudaMemcpyAsync(base, points + first, (n - first) * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
@@ -569,6 +582,13 @@ extern "C" int levins_append_scan(levins_ctx* ctx, const levins_point_xyzit* poi
     CU(cudaGetLastError());
     return LEVINS_OK;
 }
+
+extern "C" int levins_alloc_host(size_t bytes, void** out) {
+    if (!out) return LEVINS_ERR_ARG;
+    *out = nullptr;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? LEVINS_OK : LEVINS_ERR_CUDA;
+}
+extern "C" int levins_free_host(void* p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? LEVINS_OK : LEVINS_ERR_CUDA; }
 
 extern "C" int levins_buffer_info(levins_ctx* ctx, size_t* n_points, double* t_front, double* t_back) {
     if (!ctx) return LEVINS_ERR_ARG;
@@ -750,7 +770,7 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
     int r = ensure_stream_buffers(ctx, n_ins, nf);
     if (r) return r;
     ctx->s_image_from_raw = false;
-    r = run_stage1(ctx, stamp, ins, n_ins, /*write_cloud=*/false, /*bin=*/true);
+    r = run_stage1(ctx, stamp, ins, n_ins, /*write_cloud=*/false, /*bin=*/true, nf);
     if (r == LEVINS_EMPTY) {
         for (size_t k = 0; k < nf; k++) {
             if (type) type[k] = LEVINS_MAPPOINT_NONE;
@@ -762,18 +782,14 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
         return LEVINS_EMPTY;
     }
     if (r) return r;
+    char* pin = reinterpret_cast<char*>(ctx->pinned);
     if (nf) {
-        CU(cudaMemcpyAsync(ctx->s_queries.p, query_xyz, nf * 12, cudaMemcpyHostToDevice, ctx->stream));
-        unsigned long long qc[2] = {0, nf};
-        memcpy(reinterpret_cast<char*>(ctx->pinned) + 512, qc, sizeof(qc));
-        CU(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->s_kf.p) + offsetof(KfState, q_begin),
-                           reinterpret_cast<char*>(ctx->pinned) + 512, sizeof(qc), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    if (nf) {
+        memcpy(pin + ctx->pin_q(), query_xyz, nf * 12);
+        CU(cudaMemcpyAsync(ctx->s_queries.p, pin + ctx->pin_q(), nf * 12, cudaMemcpyHostToDevice, ctx->stream));
         r = run_associate_stream(ctx, nf, false, true); // also counts M
         if (r) return r;
-        if (type) CU(cudaMemcpyAsync(type, ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
-        if (xyz_depth) CU(cudaMemcpyAsync(xyz_depth, ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (type) CU(cudaMemcpyAsync(pin + ctx->pin_type(), ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
+        if (xyz_depth) CU(cudaMemcpyAsync(pin + ctx->pin_xyzd(), ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (!nf) { // no feature kernel to piggy-back the cell count on
         k_count_cells<<<dim3(64, 1), 256, 0, ctx->stream>>>(ctx->s_kf.as<KfState>(), ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen);
@@ -781,8 +797,10 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
         CU(cudaGetLastError());
     }
     KfState kf;
-    r = fetch_kf(ctx, &kf);
+    r = fetch_kf(ctx, &kf); // the one synchronisation of the call
     if (r) return r;
+    if (nf && type) memcpy(type, pin + ctx->pin_type(), nf);
+    if (nf && xyz_depth) memcpy(xyz_depth, pin + ctx->pin_xyzd(), nf * 16);
     if (n_projected_out) *n_projected_out = kf.n_proj;
     if (m_out) *m_out = kf.m;
     // the fused path keeps no cell array: a later levins_associate() needs levins_build_range_image() first

@@ -27,7 +27,7 @@ EXPORTS = [
     "levins_buffer_info", "levins_buffer_clear", "levins_stack_deskew", "levins_build_range_image", "levins_associate",
     "levins_keyframe", "levins_point_cloud_projection", "levins_batch_upload", "levins_batch_run",
     "levins_batch_download", "levins_batch_set_wave", "levins_set_profiling", "levins_batch_kernel_ms",
-    "levins_launch_count", "levins_batch_result_pointers",
+    "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host",
 ]
 
 
@@ -268,6 +268,34 @@ def batch_descs(b) -> np.ndarray:
     d["q_count"] = f
     d["stamp"] = b.stamps
     return d
+
+
+class HostBuffer:
+    """Page-locked host array from levins_alloc_host (scan buffers: asynchronous H2D at PCIe speed)."""
+
+    def __init__(self, count: int, dtype=XYZIT):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(count) * self.dtype.itemsize
+        p = C.c_void_p()
+        L = lib()
+        L.levins_alloc_host.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+        L.levins_free_host.argtypes = [C.c_void_p]
+        if L.levins_alloc_host(self.nbytes, C.byref(p)) != OK:
+            raise MemoryError("levins_alloc_host failed")
+        self._p = p
+        self.array = np.frombuffer((C.c_char * max(self.nbytes, 1)).from_address(p.value), dtype=self.dtype, count=int(count))
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            lib().levins_free_host(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class _CudaArray:

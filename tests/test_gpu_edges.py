@@ -218,3 +218,23 @@ def test_full_size_properties_config3(built_lib):
     o4 = c.batch_download()
     assert o4["m"][0] <= o1["m"][0] and o4["n_projected"][0] <= o1["n_projected"][0]
     c.close()
+
+
+def test_scans_from_page_locked_buffers(ctx, oracle):
+    """levins_alloc_host / levins_free_host: the same keyframe whether the scans come from pageable or page-locked memory."""
+    kf = synth.make_keyframe(2, pts_per_scan=4000, n_features=64)
+    _setup(ctx, kf)
+    ctx.append_scan(kf.points)
+    want = ctx.keyframe(kf.stamp, kf.ins, kf.queries)
+    hb = abi.HostBuffer(len(kf.points))
+    hb.array[:] = kf.points
+    ctx.buffer_clear()
+    half = len(kf.points) // 2
+    ctx.append_scan(hb.array[:half])
+    ctx.append_scan(hb.array[half:])
+    got = ctx.keyframe(kf.stamp, kf.ins, kf.queries)
+    assert got["m"] == want["m"] and got["n_projected"] == want["n_projected"]
+    assert np.array_equal(got["type"], want["type"]) and got["xyz_depth"].tobytes() == want["xyz_depth"].tobytes()
+    ref = oracle.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries)
+    assert np.array_equal(got["type"], ref["type"]) and got["m"] == ref["m"]
+    hb.close()
