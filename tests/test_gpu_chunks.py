@@ -152,3 +152,54 @@ def test_many_undecided_cells_in_a_batch(oracle, built_lib):
         ref = oracle.range_image(ref1["cloud"][: ref1["n"]])
         assert out["n_projected"][k] == ref1["n"] and out["m"][k] == ref["m"], (k, out["m"][k], ref["m"])
     c.close()
+
+
+def test_ragged_batch_wave_sizes_and_keyframe_order(oracle, built_lib):
+    """Keyframes of different sizes (one empty, one smaller than a chunk), different feature counts: every wave size and
+    every keyframe order gives the same per-keyframe results, equal to the oracle's."""
+    shp = synth.Shape(**{**synth.shape(2).__dict__, "pts_per_scan": 3000})
+    b = synth.make_batch(2, 7, n_unique_scans=8, shp=shp)
+    F = b.queries.shape[1]
+    nq = [F, 5, 0, F, 17, F, 1]
+    pt_begin, pt_count = b.pt_begin.copy(), b.pt_count.copy()
+    pt_count[2] = 0            # empty keyframe
+    pt_count[4] = 100          # fewer points than one chunk (they are the oldest of its window)
+    pt_count[5] -= 777         # not a multiple of anything
+    q_begin = np.concatenate([[0], np.cumsum(nq)[:-1]])
+    queries = np.concatenate([b.queries[k][:nq[k]] for k in range(7)])
+
+    def run(order, wave):
+        d = np.zeros(7, abi.KF_DESC)
+        d["pt_begin"], d["pt_count"] = pt_begin[order], pt_count[order]
+        d["ins_begin"], d["ins_count"] = b.ins_begin[order], b.ins_count[order]
+        d["q_begin"], d["q_count"] = q_begin[order], np.asarray(nq)[order]
+        d["stamp"] = b.stamps[order]
+        c = abi.Context(0)
+        c.set_extrinsics(shp.rig.pose_b_c, shp.rig.pose_c_l, shp.rig.td_b_l)
+        c.batch_set_wave(wave)
+        c.batch_upload(b.points, b.ins, queries, d)
+        c.batch_run()
+        out = c.batch_download()
+        c.close()
+        return out
+
+    ident = np.arange(7)
+    base = run(ident, 256)
+    for wave in (1, 3):
+        o = run(ident, wave)
+        assert all(np.array_equal(base[k], o[k]) for k in base), wave
+    perm = np.array([3, 6, 0, 2, 5, 1, 4])
+    o = run(perm, 2)
+    assert np.array_equal(o["type"], base["type"]) and np.array_equal(o["xyz_depth"], base["xyz_depth"])  # results live at q_begin
+    assert np.array_equal(o["n_projected"], base["n_projected"][perm]) and np.array_equal(o["m"], base["m"][perm])
+    for k in range(7):
+        pts = b.points[pt_begin[k]: pt_begin[k] + pt_count[k]]
+        ins = b.ins[b.ins_begin[k]: b.ins_begin[k] + b.ins_count[k]]
+        q = queries[q_begin[k]: q_begin[k] + nq[k]]
+        if len(pts) == 0:
+            assert base["n_projected"][k] == 0 and base["m"][k] == 0 and np.all(base["type"][q_begin[k]: q_begin[k] + nq[k]] == -1)
+            continue
+        ref = oracle.keyframe(pts, b.stamps[k], ins, shp.rig.pose_b_c, shp.rig.pose_c_l, shp.rig.td_b_l,
+                              q if len(q) else np.zeros((0, 3), np.float32))
+        assert base["n_projected"][k] == ref["n_projected"] and base["m"][k] == ref["m"], k
+        assert np.array_equal(base["type"][q_begin[k]: q_begin[k] + nq[k]], ref["type"])
