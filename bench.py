@@ -235,16 +235,22 @@ def run_gpu(args):
     # results gathered across ranks at the end of every step (the path's only exchange step)
     nq = n_kf * F
     res_host = {"type": np.zeros(nq, np.int8), "xyz_depth": np.zeros((nq, 4), np.float32)}
-    gather_buf = None
+    pipe = None
     if world > 1:
+        from levins.shard import PipelinedGather
+
         dptr = ctx.batch_result_pointers()
         assert dptr["type"] == dptr["xyz_depth"] + 16 * nq  # one contiguous block: xyz_depth then type
         local = abi.device_tensor(torch, dptr["xyz_depth"], (17 * nq,), torch.uint8, local_rank)
-        gather_buf = (local, torch.empty((world * 17 * nq,), dtype=torch.uint8, device=dev))
+        pipe = PipelinedGather(torch, dist, local, world, dev)
 
     def gather():
-        if gather_buf is not None:  # one collective for depths + types of all ranks
-            dist.all_gather_into_tensor(gather_buf[1], gather_buf[0])
+        if pipe is not None:  # one collective for depths + types of all ranks, overlapped with the next step's kernels
+            pipe.submit()
+
+    def drain():
+        if pipe is not None:
+            pipe.drain()
 
     def barrier():
         if world > 1:
@@ -260,6 +266,7 @@ def run_gpu(args):
         ctx.batch_run()
         gather()
         ctx.batch_download(res_host)
+        drain()
 
     def timed(fn, steps):
         barrier()
@@ -268,6 +275,7 @@ def run_gpu(args):
         e0.record(stream)
         for _ in range(steps):
             fn()
+        drain()  # every step's gather has completed inside the timed region
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)

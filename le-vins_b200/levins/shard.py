@@ -42,6 +42,43 @@ def gather_results(local_type, local_xyzd, n_items_total: int, features_per_item
     return torch.cat(ts), torch.cat(xs)
 
 
+class PipelinedGather:
+    """The final gather of a stream of batches, overlapped with the next batch's kernels.
+
+    `local` is the rank's contiguous result block in library memory (xyz_depth then type, 17 B / feature,
+    levins_batch_result_pointers).  submit() snapshots it into one of two staging buffers (device-to-device on the compute
+    stream) and starts an asynchronous all-gather from there, so the library may overwrite its block while the collective
+    is still in flight; the gather issued two submits ago is waited for before its buffers are reused.  drain() waits for
+    everything outstanding (call it before reading `gathered` or stopping a clock)."""
+
+    def __init__(self, torch, dist, local, world: int, device):
+        self.torch, self.dist, self.local = torch, dist, local
+        n = local.numel()
+        self.stage = [torch.empty((n,), dtype=local.dtype, device=device) for _ in range(2)]
+        self.gathered = [torch.empty((world * n,), dtype=local.dtype, device=device) for _ in range(2)]
+        self.pending = [None, None]
+        self.k = 0
+
+    def submit(self):
+        j = self.k & 1
+        self.k += 1
+        if self.pending[j] is not None:
+            self.pending[j].wait()
+        self.stage[j].copy_(self.local, non_blocking=True)
+        self.pending[j] = self.dist.all_gather_into_tensor(self.gathered[j], self.stage[j], async_op=True)
+        return j
+
+    def drain(self):
+        for j in range(2):
+            if self.pending[j] is not None:
+                self.pending[j].wait()
+                self.pending[j] = None
+
+    def latest(self):
+        """The most recently gathered block (after drain())."""
+        return self.gathered[(self.k - 1) & 1]
+
+
 def split_batch(batch, world: int, rank: int):
     """The sub-batch of a synth.Batch that `rank` owns (descriptors re-based onto the rank's own pools)."""
     from . import synth

@@ -88,3 +88,38 @@ def test_split_batch_is_self_contained():
             k += 1
     with pytest.raises(ValueError):
         shard.split_batch(b, 8, 7)
+
+
+def _pipe_worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.join(ROOT, "le-vins_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n = 17 * 40
+    local = torch.zeros(n, dtype=torch.uint8)
+    pipe = shard.PipelinedGather(torch, dist, local, world, torch.device("cpu"))
+    seen = []
+    for step in range(5):  # the "library" overwrites its block every step; each gather must see that step's content
+        local.fill_(10 * step + rank)
+        j = pipe.submit()
+        local.fill_(255)  # overwritten right away, like the next batch_run would
+        if step >= 1:
+            pipe.pending[j ^ 1].wait()
+            seen.append(pipe.gathered[j ^ 1].clone())
+    pipe.drain()
+    seen.append(pipe.latest().clone())
+    ok = all(bool((g.view(world, n)[r] == 10 * s + r).all()) for s, g in enumerate(seen) for r in range(world))
+    np.save(os.path.join(out_dir, f"pipe_{rank}.npy"), np.array([ok, len(seen)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pipelined_gather_two_ranks(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_pipe_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        ok, n = np.load(tmp_path / f"pipe_{r}.npy")
+        assert ok == 1 and n == 5
