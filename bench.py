@@ -363,6 +363,7 @@ def run_gpu(args):
             "keyframes_per_s": world * n_kf * args.steps / (ms_total * 1e-3),
             "p50_keyframe_ms": p50["pageable"] if p50 else None,
             "p50_keyframe_ms_pinned_scans": p50["pinned"] if p50 else None,
+            "streaming": p50,
             "clocks": clocks.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps},
@@ -476,37 +477,62 @@ def load_traffic():
 
 def stream_latency(abi, synth, device, n_keyframes=40):
     """Config-2 streaming: one scan appended per 0.1 s of sensor time, one keyframe every 0.5 s.  Wall time from the
-    first append of a keyframe's new scans to its results on the host; p50 over the keyframes.  Twice: with the scans in
-    ordinary pageable memory (what the unmodified ROS converter hands over) and in page-locked buffers from
-    levins_alloc_host (INTEGRATION.md)."""
+    first append of a keyframe's new scans to its results on the host; p50 over the keyframes.  Four ways of handing the
+    scans over: PointXYZIT in ordinary pageable memory (what the unmodified ROS converter produces), PointXYZIT in
+    page-locked buffers from levins_alloc_host, and the driver's own Livox records (20 B / point, converted on the device
+    by levins_append_raw) from pageable and from page-locked memory."""
+    import oracle_py as orc
+    from levins import rawfmt
+
     shp = synth.shape(CFG)
     b = synth.make_batch(CFG, n_keyframes, n_unique_scans=12, seed=synth.BASE_SEED + 77)
     per = shp.pts_per_scan
+    n_scans = len(b.points) // per
+    week = 2334
+    recs, bases = [], []
+    for s in range(n_scans):
+        r, tb = rawfmt.livox_records(b.points[s * per:(s + 1) * per], week)
+        recs.append(rawfmt.as_bytes(r))
+        bases.append(tb)
+    raw_all = np.concatenate(recs)
+    step = per * rawfmt.LIVOX.itemsize
     out = {}
-    for kind in ("pageable", "pinned"):
-        pts, hb = b.points, None
-        if kind == "pinned":
-            hb = abi.HostBuffer(len(b.points))
-            hb.array[:] = b.points
-            pts = hb.array
+    for kind in ("pageable", "pinned", "livox_pageable", "livox_pinned"):
+        raw = kind.startswith("livox")
+        src, hb = (raw_all if raw else b.points), None
+        if kind.endswith("pinned"):
+            hb = abi.HostBuffer(len(src), src.dtype)
+            hb.array[:] = src
+            src = hb.array
         ctx = abi.Context(device)
         ctx.set_extrinsics(shp.rig.pose_b_c, shp.rig.pose_c_l, shp.rig.td_b_l)
-        n_scans = len(pts) // per
-        times = []
+        times, t_append = [], []
         scan = 0
         for k, stamp in enumerate(b.stamps):
             kf_ins = b.ins[b.ins_begin[k]: b.ins_begin[k] + b.ins_count[k]]
             t0 = time.perf_counter()
-            while scan < n_scans and pts["time"][scan * per] <= stamp + 1e-9:  # everything that started before the stamp
-                ctx.append_scan(pts[scan * per:(scan + 1) * per])
+            while scan < n_scans and b.points["time"][scan * per] <= stamp + 1e-9:  # everything that started before the stamp
+                ta = time.perf_counter()
+                if raw:
+                    ctx.append_raw(rawfmt.fmt_livox(), src[scan * step:(scan + 1) * step], per, timebase_ns=bases[scan], scan_line=6)
+                else:
+                    ctx.append_scan(src[scan * per:(scan + 1) * per])
+                t_append.append(1e6 * (time.perf_counter() - ta))
                 scan += 1
             ctx.keyframe(float(stamp), kf_ins, b.queries[k])
             times.append(1e3 * (time.perf_counter() - t0))
         ctx.close()
         if hb is not None:
-            pts = None
+            src = None
             hb.close()
         out[kind] = float(np.median(times[3:])) if len(times) > 3 else None
+        out[kind + "_append_us"] = float(np.median(t_append[5:])) if len(t_append) > 5 else None
+    # the host work levins_append_raw replaces: the converter loop on one scan (oracle restatement, one thread)
+    orc.build()
+    t0 = time.perf_counter()
+    for s in range(min(n_scans, 20)):
+        orc.convert_raw(rawfmt.fmt_livox(), recs[s], per, bases[s], 0.0, True, 6, 1.0, 200.0)
+    out["converter_cpu_us_per_scan"] = 1e6 * (time.perf_counter() - t0) / min(n_scans, 20)
     return out
 
 

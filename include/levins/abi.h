@@ -135,6 +135,28 @@ int levins_append_scan(levins_ctx *ctx, const levins_point_xyzit *points, size_t
  * write PointXYZIT records into them in turn. */
 int levins_alloc_host(size_t bytes, void **out);
 int levins_free_host(void *p);
+
+/* Driver records straight into the ring: LidarConverter::{livox,velodyne,ouster,hesai}PointCloudConvertion
+ * (ROS/lidar/lidar_converter.cc:35-256) + VINS::addNewPointCloud in one call.  The records are copied to the device as
+ * they are (Livox: 19-20 B instead of 32 B per point) and filtered, converted and compacted there, in record order:
+ *   kind 1  Livox CustomPoint: u32 offset_time, f32 x y z, u8 reflectivity, u8 tag, u8 line.  Kept iff line < scan_line and
+ *           (tag & 0x30) is 0x00 or 0x10 (:55); time = (double)(timebase_ns + offset_time) * 1e-9 (:245).
+ *   kind 2  PointCloud2-style record: f32 x y z intensity, ring, and a time field: time_kind 1 = f32 seconds added to
+ *           `stamp` (Velodyne :113), 2 = u32 nanoseconds added to `stamp` (Ouster :162), 3 = f64 unix seconds (Hesai :213).
+ * to_gps_time converts unix seconds to GPS seconds of week (le_vins/common/gpstime.h:36-41).  A record survives iff
+ * nearest^2 < |p|^2 < farthest^2 (:66-67).  point_filter_num_ is the constant 1 in the reference (lidar_converter.h:61).
+ * Outputs: the number of points appended and the converter's start / end times (over every considered record, :58-63).
+ * Fields may sit at any byte offset and the stride may be odd (the serialized 19-byte Livox record). */
+typedef struct levins_raw_format {
+    uint32_t kind, point_step;
+    uint32_t off_x, off_y, off_z, off_intensity, off_time, off_ring, off_tag;
+    uint32_t time_kind;  /* kind 2 only */
+    uint32_t ring_bytes; /* 1 or 2 (unused: every record is considered) */
+    uint32_t pad;
+} levins_raw_format;
+int levins_append_raw(levins_ctx *ctx, const levins_raw_format *fmt, const void *records, size_t n, uint64_t timebase_ns,
+                      double stamp, int to_gps_time, int scan_line, double nearest, double farthest, size_t *n_appended,
+                      double *t_start, double *t_end);
 /* current deque size and its front/back times (synchronises) */
 int levins_buffer_info(levins_ctx *ctx, size_t *n_points, double *t_front, double *t_back);
 int levins_buffer_clear(levins_ctx *ctx);

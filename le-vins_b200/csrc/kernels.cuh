@@ -67,7 +67,8 @@ __device__ __forceinline__ unsigned long long warp_search(unsigned long long cou
 // ring buffer append bookkeeping: VINS::addNewPointCloud eviction rule (le_vins.cc:156-159)
 // ------------------------------------------------------------------------------------------------
 __global__ void k_ring_append(RingState* ring, const PointXYZIT* __restrict__ pts, unsigned long long cap,
-                              unsigned long long n_new, double reserved_time) {
+                              unsigned long long n_new, double reserved_time, const unsigned long long* n_new_dev = nullptr) {
+    if (n_new_dev) n_new = *n_new_dev; // levins_append_raw: the number of records that survived is known on the device only
     const unsigned long long head = ring->head;
     const unsigned long long count = ring->count + n_new;
     if (count == 0) return;
@@ -79,6 +80,164 @@ __global__ void k_ring_append(RingState* ring, const PointXYZIT* __restrict__ pt
     if ((threadIdx.x & 31) == 0) {
         ring->head = wrap(head + pop, cap);
         ring->count = count - pop;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Driver records -> PointXYZIT straight into the ring (ROS/lidar/lidar_converter.cc:35-256,
+// le_vins/common/gpstime.h:36-41).  Three small kernels: per-block survivor counts + start/end, an exclusive scan over
+// the blocks, and the ordered scatter.  point_filter_num_ is the constant 1 in the reference (lidar_converter.h:61).
+// ------------------------------------------------------------------------------------------------
+struct RawFormat {
+    unsigned kind, point_step, off_x, off_y, off_z, off_intensity, off_time, off_ring, off_tag, time_kind, ring_bytes, pad;
+};
+struct RawResult {
+    unsigned long long count;
+    double start, end;
+};
+struct RawArgs {
+    const unsigned char* rec;
+    unsigned n;
+    RawFormat f;
+    unsigned long long timebase_ns;
+    double stamp; // PointCloud2 kinds with a header-relative time: already converted to GPS time by the host
+    int to_gps, scan_line;
+    double near2, far2;
+    unsigned* block_kept;       // [ceil(n / 256)] survivor counts, turned into exclusive offsets by k_raw_scan
+    unsigned long long* minmax; // ordered bit patterns of start (min) and end (max)
+    PointXYZIT* ring;
+    unsigned long long cap, tail;
+    RawResult* result;
+};
+constexpr int RAW_BLOCK = 256;
+
+__device__ __forceinline__ unsigned raw_u32(const unsigned char* p) { // little-endian, any alignment
+    return (unsigned) p[0] | ((unsigned) p[1] << 8) | ((unsigned) p[2] << 16) | ((unsigned) p[3] << 24);
+}
+__device__ __forceinline__ double unix2gps_sow(double unixs) { // gpstime.h:36-41, GPS_LEAP_SECOND = 18
+    const double seconds = unixs + 18 - 315964800;
+    const int week = (int) floor(seconds / 604800);
+    return seconds - week * 604800;
+}
+// doubles -> unsigned keys with the same order (for atomicMin / atomicMax)
+__device__ __forceinline__ unsigned long long ordered_key(double d) {
+    const unsigned long long b = (unsigned long long) __double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_value(unsigned long long k) {
+    return __longlong_as_double((long long) ((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+// one record: false if the converter skips it before looking at the range (Livox tag / line); `kept` = survives the range gate
+__device__ __forceinline__ bool raw_decode(const RawArgs& a, unsigned k, PointXYZIT& p, bool& kept) {
+    const unsigned char* r = a.rec + (size_t) k * a.f.point_step;
+    kept = false;
+    p.pad0 = 0.f;
+    p.pad1 = 0.f;
+    if (a.f.kind == 1) {
+        const unsigned line = r[a.f.off_ring], tag = r[a.f.off_tag];
+        if (!((int) line < a.scan_line && ((tag & 0x30u) == 0x00u || (tag & 0x30u) == 0x10u))) return false; // :55
+        p.intensity = (float) r[a.f.off_intensity];                                                          // :244
+        p.time = (double) (a.timebase_ns + (unsigned long long) raw_u32(r + a.f.off_time)) * 1.0e-9;         // :245
+        if (a.to_gps) p.time = unix2gps_sow(p.time);
+    } else {
+        p.intensity = __uint_as_float(raw_u32(r + a.f.off_intensity));
+        if (a.f.time_kind == 1) {
+            p.time = a.stamp + (double) __uint_as_float(raw_u32(r + a.f.off_time)); // :113
+        } else if (a.f.time_kind == 2) {
+            p.time = a.stamp + (double) raw_u32(r + a.f.off_time) * 1.0e-9; // :162
+        } else {
+            const unsigned long long b = (unsigned long long) raw_u32(r + a.f.off_time) | ((unsigned long long) raw_u32(r + a.f.off_time + 4) << 32);
+            p.time = __longlong_as_double((long long) b); // :213-221
+            if (a.to_gps) p.time = unix2gps_sow(p.time);
+        }
+    }
+    p.x = __uint_as_float(raw_u32(r + a.f.off_x));
+    p.y = __uint_as_float(raw_u32(r + a.f.off_y));
+    p.z = __uint_as_float(raw_u32(r + a.f.off_z));
+    const double sq = (double) v3f_sqnorm(p.x, p.y, p.z); // :66
+    kept = (sq > a.near2) && (sq < a.far2);               // :67
+    return true;
+}
+
+__global__ void __launch_bounds__(RAW_BLOCK) k_raw_count(const __grid_constant__ RawArgs a) {
+    const unsigned k = blockIdx.x * RAW_BLOCK + threadIdx.x;
+    PointXYZIT p;
+    bool kept = false, seen = false;
+    if (k < a.n) seen = raw_decode(a, k, p, kept);
+    const int c = __syncthreads_count(kept);
+    if (threadIdx.x == 0) a.block_kept[blockIdx.x] = (unsigned) c;
+    // start / end over every considered record, before the range gate (:58-63)
+    unsigned long long lo = seen ? ordered_key(p.time) : ~0ull, hi = seen ? ordered_key(p.time) : 0ull;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (lo != ~0ull) atomicMin(a.minmax, lo);
+        if (hi != 0ull) atomicMax(a.minmax + 1, hi);
+    }
+}
+
+// one block: exclusive scan of the per-block counts (in place) + the result record
+__global__ void __launch_bounds__(1024) k_raw_scan(unsigned* block_kept, unsigned nblocks, const unsigned long long* minmax, RawResult* result) {
+    __shared__ unsigned s_warp[32];
+    __shared__ unsigned s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (unsigned base = 0; base < nblocks; base += 1024) {
+        const unsigned i = base + threadIdx.x;
+        const unsigned v = i < nblocks ? block_kept[i] : 0u;
+        unsigned x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned w = s_warp[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            s_warp[threadIdx.x] = w; // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u;
+        const unsigned carry = s_carry;
+        if (i < nblocks) block_kept[i] = carry + warp_off + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + warp_off + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        result->count = s_carry;
+        result->start = ordered_value(minmax[0]);
+        result->end = ordered_value(minmax[1]);
+    }
+}
+
+__global__ void __launch_bounds__(RAW_BLOCK) k_raw_scatter(const __grid_constant__ RawArgs a) {
+    __shared__ unsigned s_warp[RAW_BLOCK / 32];
+    const unsigned k = blockIdx.x * RAW_BLOCK + threadIdx.x;
+    PointXYZIT p;
+    bool kept = false;
+    if (k < a.n) raw_decode(a, k, p, kept);
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, kept);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    unsigned off = a.block_kept[blockIdx.x]; // exclusive offset of this block (k_raw_scan)
+    for (unsigned w = 0; w < warp; w++) off += s_warp[w];
+    if (kept) {
+        const unsigned long long dst = wrap(a.tail + off + __popc(bal & ((1u << lane) - 1u)), a.cap);
+        float4* out = reinterpret_cast<float4*>(a.ring + dst);
+        out[0] = make_float4(p.x, p.y, p.z, 0.f);
+        reinterpret_cast<float2*>(out + 1)[0] = make_float2(p.intensity, 0.f);
+        reinterpret_cast<double*>(out + 1)[1] = p.time;
     }
 }
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cfloat>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -65,6 +66,7 @@ struct levins_ctx {
     uint64_t ring_count_ub = 0; // host's upper bound of the live point count
     DevBuf s_ins, s_table, s_tableF, s_kf, s_queries;
     DevBuf chunks; // ChunkDesc of the current k_deskew_bin launch (streaming and batch)
+    DevBuf raw_stage, raw_blocks, raw_misc; // levins_append_raw: records, per-block counts, {min, max, result}
     DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2, s_nn, s_nn_meta;
     DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
     DevBuf s_in_cloud; // explicit cloud uploaded by build_range_image
@@ -485,7 +487,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->chunks, &ctx->s_tableF, &ctx->b_tableF, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
+    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->chunks, &ctx->raw_stage, &ctx->raw_blocks, &ctx->raw_misc, &ctx->s_tableF, &ctx->b_tableF, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
@@ -580,6 +582,90 @@ extern "C" int levins_append_scan(levins_ctx* ctx, const levins_point_xyzit* poi
     k_ring_append<<<1, 32, 0, ctx->stream>>>(ctx->ring_state.as<RingState>(), base, cap, n, reserved);
     ctx->launches++;
     CU(cudaGetLastError());
+    return LEVINS_OK;
+}
+
+extern "C" int levins_append_raw(levins_ctx* ctx, const levins_raw_format* fmt, const void* records, size_t n, uint64_t timebase_ns,
+                                 double stamp, int to_gps_time, int scan_line, double nearest, double farthest, size_t* n_appended,
+                                 double* t_start, double* t_end) {
+    if (!ctx || !fmt || (!records && n)) return fail(ctx, LEVINS_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n_appended) *n_appended = 0;
+    if (t_start) *t_start = DBL_MAX; // lidar_converter.cc:50-51
+    if (t_end) *t_end = 0;
+    const uint32_t need = fmt->kind == 1 ? 4u : (fmt->time_kind == 3 ? 8u : 4u);
+    const uint32_t offs[] = {fmt->off_x + 4, fmt->off_y + 4, fmt->off_z + 4, fmt->off_intensity + (fmt->kind == 1 ? 1u : 4u),
+                             fmt->off_time + need, fmt->kind == 1 ? fmt->off_ring + 1 : 0u, fmt->kind == 1 ? fmt->off_tag + 1 : 0u};
+    if ((fmt->kind != 1 && fmt->kind != 2) || fmt->point_step == 0 || (fmt->kind == 2 && (fmt->time_kind < 1 || fmt->time_kind > 3)))
+        return fail(ctx, LEVINS_ERR_ARG, "unknown record format");
+    for (uint32_t o : offs)
+        if (o > fmt->point_step) return fail(ctx, LEVINS_ERR_ARG, "field beyond point_step");
+    if (n == 0) return LEVINS_OK;
+    if (n > 0x7fffffffull) return fail(ctx, LEVINS_ERR_ARG, "scan too large");
+    int r = ensure_ring(ctx);
+    if (r) return r;
+    const uint64_t cap = ctx->cfg.max_points;
+    if (ctx->ring_count_ub + n > cap) { // learn the exact live count before refusing
+        RingState st;
+        r = read_ring_state(ctx, &st);
+        if (r) return r;
+        if (st.count + n > cap) return fail(ctx, LEVINS_ERR_CAPACITY, "ring buffer full: raise config.max_points");
+    }
+    const size_t bytes = n * (size_t) fmt->point_step;
+    const unsigned nblocks = (unsigned) ((n + RAW_BLOCK - 1) / RAW_BLOCK);
+    CU(ctx->raw_stage.ensure(bytes));
+    CU(ctx->raw_blocks.ensure((size_t) nblocks * 4));
+    CU(ctx->raw_misc.ensure(64));
+    CU(cudaMemcpyAsync(ctx->raw_stage.p, records, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    RawArgs a{};
+    a.rec = ctx->raw_stage.as<unsigned char>();
+    a.n = (unsigned) n;
+    memcpy(&a.f, fmt, sizeof(RawFormat));
+    a.timebase_ns = timebase_ns;
+    a.stamp = stamp;
+    if (fmt->kind == 2 && fmt->time_kind != 3 && to_gps_time) { // lidar_converter.cc:92-98, 141-147 (host libm like the reference)
+        const double seconds = stamp + 18 - 315964800;
+        const int week = (int) floor(seconds / 604800);
+        a.stamp = seconds - week * 604800;
+    }
+    a.to_gps = to_gps_time ? 1 : 0;
+    a.scan_line = scan_line;
+    a.near2 = nearest * nearest; // :31-32
+    a.far2 = farthest * farthest;
+    a.block_kept = ctx->raw_blocks.as<unsigned>();
+    a.minmax = ctx->raw_misc.as<unsigned long long>();
+    a.result = reinterpret_cast<RawResult*>(ctx->raw_misc.as<unsigned char>() + 16);
+    a.ring = ctx->ring.as<PointXYZIT>();
+    a.cap = cap;
+    a.tail = ctx->ring_tail;
+    // start = DBL_MAX, end = 0 as ordered keys (positive doubles: sign bit set)
+    char* pin = reinterpret_cast<char*>(ctx->pinned);
+    const double init[2] = {DBL_MAX, 0.0};
+    unsigned long long keys[2];
+    for (int i = 0; i < 2; i++) {
+        unsigned long long b;
+        memcpy(&b, &init[i], 8);
+        keys[i] = b | 0x8000000000000000ull;
+    }
+    memcpy(pin + 512, keys, 16);
+    CU(cudaMemcpyAsync(ctx->raw_misc.p, pin + 512, 16, cudaMemcpyHostToDevice, ctx->stream));
+    k_raw_count<<<nblocks, RAW_BLOCK, 0, ctx->stream>>>(a);
+    k_raw_scan<<<1, 1024, 0, ctx->stream>>>(a.block_kept, nblocks, a.minmax, a.result);
+    k_raw_scatter<<<nblocks, RAW_BLOCK, 0, ctx->stream>>>(a);
+    const double reserved = ctx->cfg.reserved_buffer_length + ctx->cfg.stack_interval * 2; // le_vins.cc:156
+    k_ring_append<<<1, 32, 0, ctx->stream>>>(ctx->ring_state.as<RingState>(), a.ring, cap, 0, reserved, &a.result->count);
+    ctx->launches += 4;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pin + 640, a.result, sizeof(RawResult), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    RawResult res;
+    memcpy(&res, pin + 640, sizeof(res));
+    ctx->ring_tail = (ctx->ring_tail + res.count) % cap;
+    ctx->ring_count_ub += res.count;
+    if (n_appended) *n_appended = (size_t) res.count;
+    if (t_start) *t_start = res.start;
+    if (t_end) *t_end = res.end;
     return LEVINS_OK;
 }
 

@@ -27,7 +27,7 @@ EXPORTS = [
     "levins_buffer_info", "levins_buffer_clear", "levins_stack_deskew", "levins_build_range_image", "levins_associate",
     "levins_keyframe", "levins_point_cloud_projection", "levins_batch_upload", "levins_batch_run",
     "levins_batch_download", "levins_batch_set_wave", "levins_set_profiling", "levins_batch_kernel_ms",
-    "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host",
+    "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host", "levins_append_raw",
 ]
 
 
@@ -165,6 +165,21 @@ class Context:
     def append_scan(self, points):
         pts = np.ascontiguousarray(points, XYZIT)
         self._check(lib().levins_append_scan(self._h, _p(pts), len(pts)))
+
+    def append_raw(self, fmt, records, n, timebase_ns=0, stamp=0.0, to_gps_time=True, scan_line=128, nearest=1.0, farthest=200.0):
+        """levins_append_raw: driver records (flat uint8, n * point_step bytes) -> ring.  Returns (appended, start, end)."""
+        from .rawfmt import RAW_FORMAT
+
+        f = np.ascontiguousarray(fmt, RAW_FORMAT).reshape(1)
+        rec = records if (isinstance(records, np.ndarray) and records.dtype == np.uint8 and records.flags.c_contiguous) \
+            else np.ascontiguousarray(records, np.uint8)
+        m, a, b = C.c_size_t(0), C.c_double(0), C.c_double(0)
+        L = lib()
+        L.levins_append_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_double, C.c_int, C.c_int,
+                                        C.c_double, C.c_double, C.POINTER(C.c_size_t), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        self._check(L.levins_append_raw(self._h, _p(f), _p(rec), int(n), int(timebase_ns), float(stamp), int(bool(to_gps_time)),
+                                        int(scan_line), float(nearest), float(farthest), C.byref(m), C.byref(a), C.byref(b)))
+        return m.value, a.value, b.value
 
     def buffer_info(self):
         n, a, b = C.c_size_t(0), C.c_double(0), C.c_double(0)

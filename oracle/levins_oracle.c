@@ -1324,3 +1324,72 @@ size_t orc_keyframe(const orc_point_xyzit *buf, size_t n_buf, double stamp, doub
     free(cloud);
     return m;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * ROS/lidar/lidar_converter.cc (driver records -> PointXYZIT), le_vins/common/gpstime.h
+ * ------------------------------------------------------------------------------------------ */
+double orc_unix2gps_sow(double unixs) { /* gpstime.h:36-41, GPS_LEAP_SECOND = 18 (:27) */
+    double seconds = unixs + 18 - 315964800;
+    int week = (int) floor(seconds / 604800);
+    return seconds - week * 604800; /* int * int, then converted: like the reference */
+}
+
+static uint32_t rd_u32(const unsigned char *p) { return (uint32_t) p[0] | ((uint32_t) p[1] << 8) | ((uint32_t) p[2] << 16) | ((uint32_t) p[3] << 24); }
+static float rd_f32(const unsigned char *p) {
+    uint32_t u = rd_u32(p);
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static double rd_f64(const unsigned char *p) {
+    uint64_t u = (uint64_t) rd_u32(p) | ((uint64_t) rd_u32(p + 4) << 32);
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+}
+
+size_t orc_convert_raw(const orc_raw_format *fmt, const void *records, size_t n, uint64_t timebase_ns, double stamp,
+                       int to_gps_time, int scan_line, double nearest, double farthest, orc_point_xyzit *out, double *start,
+                       double *end) {
+    const unsigned char *base = (const unsigned char *) records;
+    const double near2 = nearest * nearest, far2 = farthest * farthest; /* lidar_converter.cc:31-32 */
+    double st = DBL_MAX, en = 0;                                          /* :50-51 */
+    size_t m = 0;
+    if (fmt->kind == 2 && fmt->time_kind != 3 && to_gps_time) stamp = orc_unix2gps_sow(stamp); /* :92-98, :141-147 */
+    for (size_t k = 0; k < n; k++) {
+        const unsigned char *r = base + k * (size_t) fmt->point_step;
+        orc_point_xyzit p;
+        memset(&p, 0, sizeof(p));
+        if (fmt->kind == 1) {
+            const unsigned line = r[fmt->off_ring], tag = r[fmt->off_tag];
+            if (!((int) line < scan_line && ((tag & 0x30) == 0x00 || (tag & 0x30) == 0x10))) continue; /* :55 */
+            p.x = rd_f32(r + fmt->off_x);
+            p.y = rd_f32(r + fmt->off_y);
+            p.z = rd_f32(r + fmt->off_z);
+            p.intensity = (float) r[fmt->off_intensity];                                       /* :244 */
+            p.time = (double) (timebase_ns + (uint64_t) rd_u32(r + fmt->off_time)) * 1.0e-9;  /* :245 */
+            if (to_gps_time) p.time = orc_unix2gps_sow(p.time);
+        } else {
+            /* point_counts[ring] % point_filter_num_ == 0 with point_filter_num_ == 1: always (:108) */
+            p.x = rd_f32(r + fmt->off_x);
+            p.y = rd_f32(r + fmt->off_y);
+            p.z = rd_f32(r + fmt->off_z);
+            p.intensity = rd_f32(r + fmt->off_intensity);
+            if (fmt->time_kind == 1)
+                p.time = stamp + rd_f32(r + fmt->off_time); /* :113 */
+            else if (fmt->time_kind == 2)
+                p.time = stamp + rd_u32(r + fmt->off_time) * 1.0e-9; /* :162 */
+            else {
+                p.time = rd_f64(r + fmt->off_time); /* :213-221 */
+                if (to_gps_time) p.time = orc_unix2gps_sow(p.time);
+            }
+        }
+        if (p.time < st) st = p.time; /* :58-63 */
+        if (p.time > en) en = p.time;
+        const double sq = (double) v3f_sqnorm(p.x, p.y, p.z); /* :66 Vector3f::squaredNorm() */
+        if (sq > near2 && sq < far2) out[m++] = p;               /* :67-69 */
+    }
+    *start = st;
+    *end = en;
+    return m;
+}

@@ -101,6 +101,10 @@ def lib():
         L.orc_keyframe.restype = sz
         L.orc_keyframe.argtypes = [vp, sz, dbl, dbl, vp, sz, vp, vp, dbl, vp, sz, i32, i32, vp, vp, vp]
         L.orc_max_threads.restype = i32
+        L.orc_unix2gps_sow.restype = dbl
+        L.orc_unix2gps_sow.argtypes = [dbl]
+        L.orc_convert_raw.restype = sz
+        L.orc_convert_raw.argtypes = [vp, vp, sz, C.c_uint64, dbl, i32, i32, dbl, dbl, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -372,3 +376,23 @@ def keyframe(points, stamp, ins, pose_b_c, pose_c_l, td_b_l, queries, stack_inte
                            _p(pc), float(td_b_l), _p(q), f, int(libm_mode), int(nthreads or max_threads()), _p(ty),
                            _p(xd), C.byref(npj))
     return {"m": int(m), "type": ty, "xyz_depth": xd, "n_projected": npj.value}
+
+
+RAW_FORMAT = np.dtype([(k, "<u4") for k in ("kind", "point_step", "off_x", "off_y", "off_z", "off_intensity", "off_time",
+                                             "off_ring", "off_tag", "time_kind", "ring_bytes", "pad")])
+
+
+def unix2gps_sow(unixs):
+    return float(lib().orc_unix2gps_sow(float(unixs)))
+
+
+def convert_raw(fmt, records, n, timebase_ns=0, stamp=0.0, to_gps_time=True, scan_line=128, nearest=1.0, farthest=200.0):
+    """ROS/lidar/lidar_converter.cc:35-256.  `fmt`: one RAW_FORMAT record; `records`: uint8 array of n * point_step bytes.
+    Returns (points XYZIT, start, end)."""
+    f = np.ascontiguousarray(fmt, RAW_FORMAT).reshape(1)
+    rec = np.ascontiguousarray(records, np.uint8)
+    out = np.zeros(max(int(n), 1), XYZIT)
+    st, en = C.c_double(0), C.c_double(0)
+    m = lib().orc_convert_raw(_p(f), _p(rec), int(n), int(timebase_ns), float(stamp), int(bool(to_gps_time)), int(scan_line),
+                              float(nearest), float(farthest), _p(out), C.byref(st), C.byref(en))
+    return out[:m], st.value, en.value
