@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
                 py[j] = xyz.y;
                 pz[j] = xyz.z;
                 tt[j] = tm + a.ext.td_b_l; // le_vins.cc:455
-                const float n2 = v3f_sqnorm(xyz.x, xyz.y, xyz.z);
+                const float n2 = v3f_sqnorm_t<FAST>(xyz.x, xyz.y, xyz.z);
                 kept[j] = (pi[j] < cnt) && !((n2 > a.c.n2_far) || (n2 < a.c.n2_near)); // le_vins.cc:447-451
                 any_kept |= kept[j];
             }
@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
             }
 #pragma unroll
             for (int j = 0; j < DESKEW_GROUP; j++) {
-                const float range = sqrtf(v3f_sqnorm(ox[j], oy[j], oz[j])); // tracking.cc:330
+                const float range = sqrtf(v3f_sqnorm_t<FAST>(ox[j], oy[j], oz[j])); // tracking.cc:330
                 if (!kept[j] || !(range < FLT_MAX)) cell[j] = -1;            // tracking.cc:332 against the FLT_MAX initial value
                 key[j] = key_make(a.gen, range, off + pi[j]);
             }
