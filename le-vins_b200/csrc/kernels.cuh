@@ -258,17 +258,16 @@ struct __align__(16) ChunkDesc {
 // idx + 1: the next interval, the fallback copy in slot nins after the last one, the first interval for a chunk that
 // starts before the window.  NC = false inside the kernel that has just written the table.
 template <bool NC>
-__device__ __forceinline__ ChunkDesc make_chunk_desc(unsigned c, unsigned n_proj, unsigned long long proj_begin, const PointXYZIT* __restrict__ pts,
-                                                     unsigned long long pts_cap, double td_b_l, const Interval* __restrict__ tab,
-                                                     unsigned long long table_begin, int nins, double t0, double t_last, double inv_mean_dt) {
+__device__ __forceinline__ ChunkDesc chunk_desc_from_time(unsigned c, unsigned n_proj, unsigned long long phys, double t_point, double td_b_l,
+                                                          const Interval* __restrict__ tab, unsigned long long table_begin, int nins,
+                                                          double t0, double t_last, double inv_mean_dt) {
     ChunkDesc d;
     d.phys = 0;
     d.ent0 = 0;
     d.cnt = 0;
     const unsigned off = c * CHUNK_PTS;
     if (off < n_proj) {
-        const unsigned long long phys = wrap(proj_begin + off, pts_cap);
-        const double t = pts[phys].time + td_b_l; // le_vins.cc:455
+        const double t = t_point + td_b_l; // le_vins.cc:455
         int idx = 0;
         if (!(nins < 2 || t0 > t || t_last <= t)) { // misc.cc:28-30
             int g = 1 + (int) ((t - t0) * inv_mean_dt);
@@ -288,6 +287,15 @@ __device__ __forceinline__ ChunkDesc make_chunk_desc(unsigned c, unsigned n_proj
         d.cnt = min((unsigned) CHUNK_PTS, n_proj - off);
     }
     return d;
+}
+template <bool NC>
+__device__ __forceinline__ ChunkDesc make_chunk_desc(unsigned c, unsigned n_proj, unsigned long long proj_begin, const PointXYZIT* __restrict__ pts,
+                                                     unsigned long long pts_cap, double td_b_l, const Interval* __restrict__ tab,
+                                                     unsigned long long table_begin, int nins, double t0, double t_last, double inv_mean_dt) {
+    const unsigned off = c * CHUNK_PTS;
+    const unsigned long long phys = off < n_proj ? wrap(proj_begin + off, pts_cap) : 0ull;
+    const double t_point = off < n_proj ? pts[phys].time : 0.0;
+    return chunk_desc_from_time<NC>(c, n_proj, phys, t_point, td_b_l, tab, table_begin, nins, t0, t_last, inv_mean_dt);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,9 +474,23 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
         const double inv_mean_dt = nins > 1 ? (double) (nins - 1) / (t_last - t_first) : 0.0;
         const unsigned long long table_begin = kf->table_begin;
         ChunkDesc* __restrict__ out = a.chunks + (size_t) blockIdx.x * a.chunks_per_kf;
-        for (unsigned c = threadIdx.x; c < a.chunks_per_kf; c += blockDim.x)
-            out[c] = make_chunk_desc<false>(c, n_proj, proj_begin, a.pts, a.pts_cap, a.ext.td_b_l, tab, table_begin, nins, t_first, t_last,
-                                            inv_mean_dt);
+        // all first-point times of this thread's chunks first (independent loads, one memory round trip), then the probes
+        constexpr int ROUNDS = 8; // the host fuses the descriptors only for chunks_per_kf <= 8 * 256
+        double tp[ROUNDS];
+        unsigned long long ph[ROUNDS];
+#pragma unroll
+        for (int i = 0; i < ROUNDS; i++) {
+            const unsigned off = (threadIdx.x + i * 256u) * CHUNK_PTS;
+            const bool live = threadIdx.x + i * 256u < a.chunks_per_kf && off < n_proj;
+            ph[i] = live ? wrap(proj_begin + off, a.pts_cap) : 0ull;
+            tp[i] = live ? a.pts[ph[i]].time : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < ROUNDS; i++) {
+            const unsigned c = threadIdx.x + i * 256u;
+            if (c < a.chunks_per_kf)
+                out[c] = chunk_desc_from_time<false>(c, n_proj, ph[i], tp[i], a.ext.td_b_l, tab, table_begin, nins, t_first, t_last, inv_mean_dt);
+        }
     }
 }
 
