@@ -144,6 +144,7 @@ public:
     bool empty() const { return points.empty(); }
     void clear() { points.clear(); }
     void resize(size_t n) { points.resize(n); }
+    void reserve(size_t n) { points.reserve(n); }
     void push_back(const PointT &p) { points.push_back(p); }
     PointT &operator[](size_t i) { return points[i]; }
     const PointT &operator[](size_t i) const { return points[i]; }

@@ -70,6 +70,13 @@ public:
         return true;
     }
 
+    // a scan that went to the device as driver records (LidarConverter::*PointCloudAppend): `newest_time` = the converter's `end`
+    void notifyAppended(size_t appended, double newest_time) {
+        if (!appended) return;
+        newest_point_time_.store(newest_time);
+        have_points_.store(true);
+    }
+
     bool lidarPointBufferEmpty() const { return !have_points_.load(); }
 
     // le_vins.cc:392-470.  frame_stamp = frame->stamp(); ins_window = ins_window_.

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "le_vins/vins_lidar.h"
+#include "ros/lidar_converter.h"
 #include "visual/tracking_depth.h"
 
 template <typename T> static std::vector<T> read_bin(const std::string &path) {
@@ -109,6 +110,34 @@ int main(int argc, char **argv) {
           << "\nassociated " << num_associated << "\nsingle_type " << single_type << "\nsingle " << single.x << " " << single.y << " "
           << single.z << " " << single.intensity << "\n";
         std::printf("host mirror: n=%zu M=%zu associated=%d\n", pointcloud.size(), tracking.unitSphereSize(), num_associated);
+
+        // the same scans once more as the driver's own Livox records: LidarConverter::livoxPointCloudAppend converts them on
+        // the device (ROS/fusion.cc:357-360 in one call), then the stacker runs again
+        {
+            std::ifstream probe(dir + "/raw_livox.bin");
+            if (probe) {
+                const auto recs = read_bin<livox_ros_driver::CustomPoint>(dir + "/raw_livox.bin");
+                const auto tb = read_bin<uint64_t>(dir + "/raw_timebase.bin"); // per scan: timebase, record count
+                levins_host::check(levins_buffer_clear(levins_host::context()), "buffer_clear");
+                LidarConverter converter(10.0, 6, 1.0, 200.0);
+                size_t o = 0, total = 0;
+                for (size_t sidx = 0; sidx + 1 < tb.size(); sidx += 2) {
+                    livox_ros_driver::CustomMsg msg;
+                    msg.timebase_ns = tb[sidx];
+                    msg.points.assign(recs.begin() + o, recs.begin() + o + tb[sidx + 1]);
+                    o += tb[sidx + 1];
+                    double start = 0, end = 0;
+                    const size_t n = converter.livoxPointCloudAppend(msg, start, end, true);
+                    vins.notifyAppended(n, end);
+                    total += n;
+                }
+                PointCloud from_records;
+                const bool ok = vins.pointcloudStackForVisualTracking(stamp, ins_window, from_records);
+                write_bin(dir + "/cloud_raw.bin", from_records.points);
+                std::ofstream s2(dir + "/summary_raw.txt");
+                s2 << "stacked " << ok << "\nappended " << total << "\nn " << from_records.size() << "\n";
+            }
+        }
         levins_destroy(levins_host::context());
     } catch (const std::exception &e) {
         std::fprintf(stderr, "test_host failed: %s\n", e.what());

@@ -49,8 +49,26 @@ def test_host_mirror_matches_oracle(oracle, built_lib, tmp_path):
     ok, frame_pose = oracle.get_pose_from_ins_window(kf.ins, kf.rig.pose_b_c, kf.stamp)
     n_scans = 8
     _dump(kf, str(tmp_path), frame_pose, n_scans)
+    # the same scans as Livox driver records for LidarConverter::livoxPointCloudAppend (device-side conversion)
+    from levins import rawfmt
+
+    rng = np.random.default_rng(12)
+    per = (len(kf.points) + n_scans - 1) // n_scans
+    recs, meta, conv = [], [], []
+    for b in range(0, len(kf.points), per):
+        rec, tb = rawfmt.livox_records(kf.points[b:b + per], 2334, rng=rng, bad_fraction=0.03)
+        recs.append(rec)
+        meta += [tb, len(rec)]
+        conv.append(oracle.convert_raw(rawfmt.fmt_livox(), rawfmt.as_bytes(rec), len(rec), tb, 0.0, True, 6, 1.0, 200.0)[0])
+    np.concatenate(recs).tofile(tmp_path / "raw_livox.bin")
+    np.array(meta, np.uint64).tofile(tmp_path / "raw_timebase.bin")
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    sraw = dict(line.split(" ", 1) for line in open(tmp_path / "summary_raw.txt").read().strip().split("\n"))
+    pts_conv = np.concatenate(conv)
+    ref_raw = oracle.stack_deskew(pts_conv, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, 0.5)
+    assert int(sraw["appended"]) == len(pts_conv) and int(sraw["n"]) == ref_raw["n"] > 0
+    assert np.fromfile(tmp_path / "cloud_raw.bin", dtype=synth.XYZI).tobytes() == ref_raw["cloud"].tobytes()
     summary = dict(line.split(" ", 1) for line in open(tmp_path / "summary.txt").read().strip().split("\n"))
     ref1 = oracle.stack_deskew(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, 0.5)
     ref2 = oracle.range_image(ref1["cloud"])
@@ -155,3 +173,41 @@ def test_host_mirror_cpu_functions_match_oracle(oracle, built_lib, tmp_path):
         assert np.array_equal(cam[k, 3:6], puc)
         assert np.array_equal(cam[k, 6:9], oracle.cam2world(puc, pose_list[k % len(pose_list)]))
         assert bool(cam[k, 9]) == oracle.is_good_depth(pts["z"][k], 1.0)
+
+
+def test_host_mirror_lidar_converter_matches_oracle(oracle, built_lib, tmp_path):
+    """LidarConverter (C++ mirror of ROS/lidar/lidar_converter.cc, CPU loops) on the four drivers' records against the oracle's
+    orc_convert_raw, bit for bit: two independent restatements of the same converter."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_raw_formats import _cases
+
+    from levins import rawfmt
+
+    _build()
+    exe = os.path.join(ROOT, "le-vins_b200", "host", "test_host_cpu")
+    # the driver needs its regular inputs too
+    kf = synth.make_keyframe(2, pts_per_scan=300, n_features=8)
+    d = str(tmp_path)
+    ins = np.concatenate([kf.ins["time"][:, None], kf.ins["state_time"][:, None], kf.ins["p"], kf.ins["q"]], axis=1)
+    ins.astype(np.float64).tofile(os.path.join(d, "ins.bin"))
+    kf.ins["time"][5:15].astype(np.float64).tofile(os.path.join(d, "times.bin"))
+    np.concatenate([kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.intr]).astype(np.float64).tofile(os.path.join(d, "ext.bin"))
+    np.zeros(10, synth.XYZI).tofile(os.path.join(d, "pts.bin"))
+    cases = {c[0]: c for c in _cases(seed=5, n=20_000)}
+    stamp = cases["velodyne"][4]
+    for to_gps in (True, False):
+        np.array([stamp, 1.0, 200.0, float(to_gps), 6, 128], np.float64).tofile(os.path.join(d, "raw_meta.bin"))
+        np.array([cases["livox"][3]], np.uint64).tofile(os.path.join(d, "raw_timebase.bin"))
+        for name in ("livox", "velodyne", "ouster", "hesai"):
+            cases[name][2].tofile(os.path.join(d, f"raw_{name}.bin"))
+        r = subprocess.run([exe, d], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        se = np.fromfile(os.path.join(d, "conv_se.bin"), np.float64).reshape(4, 2)
+        for i, name in enumerate(("livox", "velodyne", "ouster", "hesai")):
+            _, fmt, rec, tb, st, lines = cases[name]
+            want, wst, wen = oracle.convert_raw(fmt, rawfmt.as_bytes(rec), len(rec), tb, st, to_gps, 6 if name == "livox" else 128, 1.0, 200.0)
+            got = np.fromfile(os.path.join(d, f"conv_{name}.bin"), synth.XYZIT)
+            assert len(got) == len(want) > 0 and got.tobytes() == want.tobytes(), name
+            assert se[i, 0] == wst and se[i, 1] == wen, name
