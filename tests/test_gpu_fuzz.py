@@ -2,6 +2,8 @@
 jittered), time offsets, window lengths, point distributions (inside / outside the FOV, around the range gates, clustered
 on a few cells) and feature sets.  Every scenario checks window membership, range-gate decisions, coordinates, M and the
 per-feature decisions."""
+import os
+
 import numpy as np
 import pytest
 
@@ -85,7 +87,10 @@ def _scenario(seed):
     return dict(pts=pts, ins=ins, stamp=stamp, interval=interval, pose_b_c=pose_b_c, pose_c_l=pose_c_l, td=td, q=q)
 
 
-@pytest.mark.parametrize("seed", range(24))
+N_SEEDS = int(os.environ.get("LEVINS_FUZZ_SEEDS", "24"))  # e.g. LEVINS_FUZZ_SEEDS=400 for a soak run
+
+
+@pytest.mark.parametrize("seed", range(N_SEEDS))
 def test_fuzz_keyframe_against_oracle(oracle, built_lib, seed):
     s = _scenario(1000 + seed)
     c = abi.Context(0, stack_interval=s["interval"])
