@@ -23,7 +23,13 @@ namespace lv {
 #endif
 constexpr int DESKEW_THREADS = LV_THREADS;
 constexpr int FINALIZE_THREADS = 256;
-constexpr int ASSOC_WARPS = 4;
+#ifndef LV_ASSOC_WARPS
+#define LV_ASSOC_WARPS 2
+#endif
+#ifndef LV_ASSOC_MINBLK
+#define LV_ASSOC_MINBLK 12
+#endif
+constexpr int ASSOC_WARPS = LV_ASSOC_WARPS;
 constexpr int WIN_ROWS = 4; // |d row| <= 4, |d col| <= 6: every point within the acceptance radius 3*sin(0.3 deg)
 constexpr int WIN_COLS = 6; // of a query lies in this 9 x 13 window ("windowed k-NN is exact")
 constexpr int WIN_W = 2 * WIN_COLS + 1;
@@ -1089,7 +1095,7 @@ struct AssocArgs {
 };
 
 template <bool FUSED>
-__global__ void __launch_bounds__(ASSOC_WARPS * 32, 6) k_associate(const __grid_constant__ AssocArgs a) {
+__global__ void __launch_bounds__(ASSOC_WARPS * 32, LV_ASSOC_MINBLK) k_associate(const __grid_constant__ AssocArgs a) {
     KfState* __restrict__ kf = a.kfs + blockIdx.y;
     const int lane = threadIdx.x & 31;
     const unsigned f = blockIdx.x * ASSOC_WARPS + (threadIdx.x >> 5);
