@@ -19,7 +19,7 @@
 namespace lv {
 
 #ifndef LV_THREADS
-#define LV_THREADS 256
+#define LV_THREADS 512 // one 16-warp CTA per SM: 2 % faster than two 8-warp CTAs (profiles/r01_experiments.md)
 #endif
 constexpr int DESKEW_THREADS = LV_THREADS;
 constexpr int FINALIZE_THREADS = 256;
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
 #define LV_AMBQ 32
 #endif
 #ifndef LV_MINBLK
-#define LV_MINBLK 2
+#define LV_MINBLK 1
 #endif
 #ifndef LV_MINBLK_F // CTAs per SM of the single-precision instantiations (half the register state per point)
 #define LV_MINBLK_F LV_MINBLK
@@ -539,7 +539,7 @@ constexpr int WARP_BAR_OFF = DESKEW_STAGES * STAGE_BYTES;
 constexpr int WARP_Q_OFF = WARP_BAR_OFF + 32;
 constexpr int WARP_QKF_OFF = WARP_Q_OFF + AMBQ * 16;
 constexpr int WARP_SMEM = WARP_QKF_OFF + AMBQ * 4;
-constexpr int DESKEW_SMEM = DESKEW_WARPS * WARP_SMEM; // 113 280 B: two CTAs per SM
+constexpr int DESKEW_SMEM = DESKEW_WARPS * WARP_SMEM; // 16 warps x 14 160 B = 226 560 B: one CTA per SM
 constexpr int DESKEW_BLOCK = DESKEW_THREADS;
 static_assert(STAGE_BYTES % 16 == 0 && WARP_SMEM % 16 == 0 && WARP_Q_OFF % 16 == 0, "TMA / vector alignment");
 static_assert(LV_MINBLK * (DESKEW_SMEM + 1024) <= 228 * 1024 && LV_MINBLK_F * (DESKEW_SMEM + 1024) <= 228 * 1024, "CTAs per SM");

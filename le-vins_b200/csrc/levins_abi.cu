@@ -249,7 +249,7 @@ int launch_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_k
     return LEVINS_OK;
 }
 
-// k_deskew_bin is persistent: two CTAs per SM (111 KB of TMA staging each), every warp walking its own chunk list.
+// k_deskew_bin is persistent: one 16-warp CTA per SM (221 KB of TMA staging), every warp walking its own chunk list.
 // launch_chunks() must have filled a.chunks / a.chunks_per_kf.
 int launch_deskew(levins_ctx* ctx, DeskewArgs& a, bool write_cloud) {
     const unsigned total = a.n_kf * a.chunks_per_kf;
