@@ -1,14 +1,18 @@
-// kernels.cuh -- the four kernels of the LiDAR depth-enhancement path (sm_100a, hand-written, no libraries).
+// kernels.cuh -- the kernels of the LiDAR depth-enhancement path (sm_100a, hand-written, no libraries).
 //
-//   k_prepare      per keyframe: window search (le_vins.cc:413-437), keyframe pose (le_vins.cc:441-442) and the
-//                  per-INS-interval table that replaces the per-point pose interpolation (misc.cc:62-103)
+//   k_prepare      per keyframe: window search (le_vins.cc:413-437), keyframe pose (le_vins.cc:441-442), the
+//                  per-INS-interval table that replaces the per-point pose interpolation (misc.cc:62-103) and, in
+//                  batches, the chunk descriptors of k_deskew_bin (k_chunk_desc does those for the streaming path)
 //   k_deskew_bin   per point: range gate + deskew (le_vins.cc:445-464) fused with range-image binning
-//                  (tracking.cc:307-336) through a 64-bit atomicMin key (range bits | point index)
+//                  (tracking.cc:307-336) through a 64-bit atomicMin key (range bits | point index); persistent warps,
+//                  each with its own TMA ring
 //   k_associate    per feature (one warp): exact windowed 5-NN (tracking.cc:571);
 //                  in the fused path it also turns the z-buffer winners of its window into unit vectors + ranges
 //                  (tracking.cc:340-354) on the fly
 //   k_plane        per feature (one thread): threshold, QR plane fit, validity checks, depth (tracking.cc:573-631)
+//   k_count_cells  M per keyframe (side stream)
 //   k_finalize     stage-wise API only: per cell winner -> unit vector + range
+//   k_raw_count / k_raw_scan / k_raw_scatter   driver records -> PointXYZIT in the ring (lidar_converter.cc:35-256)
 // plus k_bin_cloud / k_compact / k_project / k_ring_append for the stage-wise ABI entry points.
 #pragma once
 
