@@ -4,10 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 One "step" is one pass of the whole hot path (window search + INS table, per-point deskew fused with range-image
-binning, cell finalisation, per-feature 5-NN + plane fit) over one batch of independent synthetic keyframes of
-BASELINE.json configs[1] (R3LIVE handheld shape: Livox-Avia-like 24 000 pts/scan at 10 Hz, 0.5 s stack window,
-1280x1024 camera, 300 features per keyframe).  Every rank processes its own batch (weak scaling); keyframes are
-independent, so the only exchange step is the final NCCL all-gather of the per-feature results.
+binning, per-feature 5-NN + plane fit) over one batch of independent synthetic keyframes of BASELINE.json configs[2],
+the largest single-GPU configuration (FusionPortableV2 vehicle shape: Ouster OS1-128, 131 072 pts/scan with per-point
+timestamps, 20-scan = 2.0 s stack window = 2.62 M points per keyframe, td_b_l = -0.48 s, 1440x1080 camera, 200 features
+per keyframe).  Every rank processes its own batch (weak scaling); keyframes are independent, so the only exchange step
+is the final gather of the per-feature results.
 
 Printed JSON (one line, rank 0):
   value      whole-job features/s with the batch already resident in HBM (CUDA events on the launching stream)
@@ -16,6 +17,7 @@ Printed JSON (one line, rank 0):
   roofline   dominant kernel (k_deskew_bin): algorithmic bytes (32 B per projected point) / its mean launch time
              measured live with CUDA events, against MEASURED_PEAKS.json's hbm_gbs
   cpu_baseline  the CPU oracle (a port of the reference's algorithm with its parallel structure) on a bounded sample
+  parity     the GPU results of the timed batch against the oracle's on the keyframes the cpu_baseline leg computed
 `--impl reference` times that CPU port alone on the box's host cores (the reference itself cannot be built here).
 """
 from __future__ import annotations
@@ -36,9 +38,11 @@ for p in (os.path.join(ROOT, "le-vins_b200"), os.path.join(ROOT, "oracle")):
 
 METRIC = "features_depth_associated_per_s"
 UNIT = "features/s"
-CFG = 2  # BASELINE.json configs[1]
-DEFAULT_KEYFRAMES = 256
-UNIQUE_SCANS = 48
+CFG = 3  # BASELINE.json configs[2]: the largest single-GPU configuration (the metric names no configuration)
+DEFAULT_KEYFRAMES = 32
+UNIQUE_SCANS = 20  # one stack window of ray-cast scans, repeated with advancing timestamps (every keyframe has its own poses)
+INS_SPAN = 3.5  # seconds of INS before the stamp: the 2.0 s window shifted by td_b_l = -0.48 s
+STREAM_CFG = 2  # p50 keyframe latency: BASELINE.json configs[1], the streaming single-GPU shape
 
 
 def load_peaks():
@@ -50,7 +54,41 @@ def load_peaks():
 
 
 def workload_name(n_kf):
-    return f"cfg2_r3live_avia_24kpts_x5scans_1280x1024_F300_batch{n_kf}_independent_keyframes"
+    return f"cfg3_fusionportable_os1_128_x20scans_1440x1080_F200_batch{n_kf}_independent_keyframes"
+
+
+def cached_batch(synth, key, make):
+    """Synthetic batches are deterministic in their arguments; LEVINS_BATCH_CACHE=<dir> keeps them on disk so that several
+    bench.py processes on one box (A/B timing of kernel variants, the two arms) ray-cast each batch once."""
+    cache = os.environ.get("LEVINS_BATCH_CACHE")
+    if not cache:
+        return make()
+    os.makedirs(cache, exist_ok=True)
+    path = os.path.join(cache, key + ".npz")
+    fields = ("points", "ins", "stamps", "pt_begin", "pt_count", "ins_begin", "ins_count", "queries")
+    if os.path.exists(path):
+        z = np.load(path)
+        return synth.Batch(synth.shape(int(z["cfg"])), *[z[f] for f in fields])
+    b = make()
+    tmp = path + f".{os.getpid()}.tmp.npz"
+    np.savez(tmp, cfg=np.int64(int(key.split("_")[0][3:])), **{f: getattr(b, f) for f in fields})
+    os.replace(tmp, path)
+    return b
+
+
+def make_workload(synth, n_kf, rank=0):
+    seed = synth.BASE_SEED + 3 + 1000 * rank
+    return cached_batch(synth, f"cfg{CFG}_k{n_kf}_s{seed}_u{UNIQUE_SCANS}",
+                        lambda: synth.make_batch(CFG, n_kf, seed=seed, n_unique_scans=UNIQUE_SCANS, ins_span=INS_SPAN))
+
+
+def workload_config(batch, n_kf):
+    """The `config` object of the JSON line: identical keys and values in both arms."""
+    return {"workload": workload_name(n_kf), "keyframes_per_gpu": int(n_kf),
+            "scans_per_keyframe": int(round(batch.shape.stack_interval / batch.shape.scan_period)),
+            "points_per_scan": int(batch.shape.pts_per_scan), "features_per_keyframe": int(batch.queries.shape[1]),
+            "stack_interval_s": float(batch.shape.stack_interval), "td_b_l_s": float(batch.shape.rig.td_b_l),
+            "resolution": list(batch.shape.rig.resolution)}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -125,27 +163,56 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def cpu_keyframes(batch, ks, nthreads, budget_s=None):
-    """Oracle port on keyframes `ks` (cycled until `budget_s` seconds of CPU work when given).  Returns
-    (seconds, features, points, keyframes)."""
+def cpu_keyframes(batch, ks, nthreads, budget_s=None, results=None):
+    """Oracle port on keyframes `ks` (stopping after `budget_s` seconds of CPU work when given).  Returns
+    (seconds, features, points, keyframes); `results` (a dict) receives the oracle's result per keyframe index."""
     import oracle_py as orc
     from levins import synth
 
     t0 = time.perf_counter()
     nf = npts = nk = 0
-    ks = list(ks)
-    while True:
-        for k in ks:
-            kf = synth.batch_keyframe(batch, k)
-            r = orc.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries,
-                             kf.shape.stack_interval, nthreads=nthreads)
-            nf += len(kf.queries)
-            npts += r["n_projected"]
-            nk += 1
-            if budget_s is not None and time.perf_counter() - t0 >= budget_s:
-                return time.perf_counter() - t0, nf, npts, nk
-        if budget_s is None:
-            return time.perf_counter() - t0, nf, npts, nk
+    for k in ks:
+        kf = synth.batch_keyframe(batch, k)
+        r = orc.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries,
+                         kf.shape.stack_interval, nthreads=nthreads)
+        if results is not None:
+            results[k] = r
+        nf += len(kf.queries)
+        npts += r["n_projected"]
+        nk += 1
+        if budget_s is not None and time.perf_counter() - t0 >= budget_s:
+            break
+    return time.perf_counter() - t0, nf, npts, nk
+
+
+def parity_report(gpu, oracle_results, F):
+    """GPU results of the timed batch against the oracle's, keyframe by keyframe (bars: north_star)."""
+    if not oracle_results:
+        return None
+    ks = sorted(oracle_results)
+    type_eq = depth_ok = depth_n = depth_same = 0
+    m_eq = np_eq = 0
+    max_rel = 0.0
+    for k in ks:
+        r = oracle_results[k]
+        gt, gx = gpu["type"][k * F:(k + 1) * F], gpu["xyz_depth"][k * F:(k + 1) * F]
+        type_eq += int(np.sum(gt == r["type"]))
+        both = (gt == 1) & (r["type"] == 1)
+        d0 = r["xyz_depth"][both, 3].astype(np.float64)
+        d1 = gx[both, 3].astype(np.float64)
+        rel = np.abs(d1 - d0) / np.abs(d0) if both.any() else np.zeros(0)
+        depth_ok += int(np.sum(rel <= 1e-4))
+        depth_same += int(np.sum(d0 == d1))
+        depth_n += int(both.sum())
+        max_rel = max(max_rel, float(rel.max()) if rel.size else 0.0)
+        m_eq += int(gpu["m"][k] == r["m"])
+        np_eq += int(gpu["n_projected"][k] == r["n_projected"])
+    n = len(ks)
+    return {"keyframes_checked": n, "features_checked": n * F, "type_agreement": type_eq / (n * F),
+            "depth_within_1e-4": (depth_ok / depth_n) if depth_n else 1.0,
+            "depth_bit_identical": (depth_same / depth_n) if depth_n else 1.0, "depth_compared": depth_n,
+            "max_depth_rel_err": max_rel, "m_equal": m_eq / n, "n_projected_equal": np_eq / n,
+            "against": "oracle port (oracle/levins_oracle.c) on the same keyframes of the timed batch"}
 
 
 def run_reference(args):
@@ -158,10 +225,10 @@ def run_reference(args):
     from levins import synth
 
     orc.build()
-    n_sample = 8
-    batch = synth.make_batch(CFG, n_sample, n_unique_scans=UNIQUE_SCANS)
+    n_sample = 4  # keyframes per step (~0.2 s of host work each on 8+ threads): the default 20 steps end well within a minute
+    batch = make_workload(synth, n_sample)
     cores = host_cores()
-    for _ in range(args.warmup):
+    for _ in range(max(1, min(args.warmup, 2))):
         cpu_keyframes(batch, range(n_sample), cores)
     t_total, nf_total, np_total = 0.0, 0, 0
     for _ in range(args.steps):
@@ -170,12 +237,14 @@ def run_reference(args):
         nf_total += nf
         np_total += npts
     value = nf_total / t_total
-    sample = f"{n_sample} keyframes of the workload per step ({n_sample * 300} features, {np_total // args.steps} points)"
+    F = batch.queries.shape[1]
+    sample = (f"{n_sample} keyframes of the workload per step ({n_sample * F} features, {np_total // args.steps} points); "
+              f"stage 1 on {cores} threads, stages 2-3 serial + KD-tree like the reference")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(DEFAULT_KEYFRAMES), "sample_keyframes_per_step": n_sample},
+        "config": workload_config(batch, args.keyframes),
         "lidar_pts_per_s": np_total / t_total, "keyframes_per_s": n_sample * args.steps / t_total,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,6 +266,15 @@ def pinned_copy(torch, arr):
     return t, v.view(arr.dtype).reshape(arr.shape)
 
 
+def world_from_env(args):
+    """World size comes from the launcher (torchrun exports WORLD_SIZE); --gpus must agree with it."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world:
+        raise SystemExit(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}: launch N ranks with "
+                         f"`python -m torch.distributed.run --nproc-per-node N bench.py --gpus N`")
+    return world
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -205,7 +283,7 @@ def run_gpu(args):
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    world = world_from_env(args)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
@@ -215,7 +293,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
 
     n_kf = args.keyframes
-    batch = synth.make_batch(CFG, n_kf, seed=synth.BASE_SEED + 5 + 1000 * rank, n_unique_scans=UNIQUE_SCANS)
+    batch = make_workload(synth, n_kf, rank)
     descs = abi.batch_descs(batch)
     F = batch.queries.shape[1]
     q_flat = np.ascontiguousarray(batch.queries.reshape(-1, 3))
@@ -225,7 +303,7 @@ def run_gpu(args):
     t_q, q = pinned_copy(torch, q_flat)
     keep += [t_pts, t_ins, t_q]
 
-    ctx = abi.Context(local_rank, deskew_precision=args.precision)
+    ctx = abi.Context(local_rank, stack_interval=batch.shape.stack_interval)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.set_extrinsics(batch.shape.rig.pose_b_c, batch.shape.rig.pose_c_l, batch.shape.rig.td_b_l)
@@ -326,31 +404,28 @@ def run_gpu(args):
     if rank == 0 and not args.no_stream:
         p50 = stream_latency(abi, synth, local_rank)
 
-    # ---- secondary workload: BASELINE configs[2], Ouster OS1-128, 20-scan (2.0 s) window, td_b_l = -0.48 s ----
+    # ---- secondary workload: BASELINE configs[1] as a resident batch (round 1's headline), for continuity ----
     also = None
-    if rank == 0 and world == 1 and not args.no_cfg3:
-        also = bench_cfg3(torch, abi, synth, local_rank, stream, peak)
+    if rank == 0 and world == 1 and not args.no_also:
+        also = bench_cfg2(torch, abi, synth, local_rank, stream, peak)
 
-    # ---- the opt-in single-precision deskew (levins_config.deskew_precision = 1) on the same batch, and how far its
-    #      results are from the default mode's (which equals the reference bit for bit in tests/) ----
-    f32_mode = None
-    if rank == 0 and world == 1 and not args.no_f32 and args.precision == 0:
-        f32_mode = bench_f32_mode(torch, abi, args, local_rank, stream, batch, (pts, ins, q, descs), out, peak, n_proj_total)
-
-    # ---- CPU baseline on a bounded sample (rank 0 only) ----
-    cpu = None
+    # ---- CPU baseline on a bounded sample (rank 0 only), and the parity of the timed batch's results against it ----
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle_py as orc
 
         orc.build()
         cores = host_cores()
-        cpu_keyframes(batch, range(2), cores)
-        t, nf, npts, nk = cpu_keyframes(batch, range(n_kf), cores, budget_s=args.cpu_seconds)
+        oracle_results = {}
+        t, nf, npts, nk = cpu_keyframes(batch, range(n_kf), cores, budget_s=args.cpu_seconds, results=oracle_results)
+        parity = parity_report(out, oracle_results, F)
         # the host work levins_append_raw replaces: LidarConverter's loop on one 24 000-point Livox scan (one thread, like
         # the ROS callback)
         from levins import rawfmt
 
-        rec, tb = rawfmt.livox_records(batch.points[:batch.shape.pts_per_scan], 2334)
+        shp2 = synth.shape(STREAM_CFG)
+        kf2 = synth.make_keyframe(STREAM_CFG)
+        rec, tb = rawfmt.livox_records(kf2.points[:shp2.pts_per_scan], 2334)
         raw = rawfmt.as_bytes(rec)
         t0c = time.perf_counter()
         for _ in range(20):
@@ -366,9 +441,10 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(n_kf), "keyframes_per_gpu": n_kf, "points_per_keyframe": int(n_proj_total / n_kf),
-                       "features_per_keyframe": F, "wave": args.wave,
-                       "l2": f"inputs larger than L2: {pts.nbytes / 1e6:.0f} MB of points per GPU per step"},
+            "config": workload_config(batch, n_kf),
+            "run": {"points_per_keyframe": int(n_proj_total / n_kf), "wave": args.wave,
+                    "cells_per_keyframe": int(out["m"].mean()), "associated_fraction": float((out["type"] == 1).mean()),
+                    "l2": f"inputs larger than L2: {pts.nbytes / 1e6:.0f} MB of points per GPU per step"},
             "lidar_pts_per_s": world * pts_per_step * args.steps / (ms_total * 1e-3),
             "keyframes_per_s": world * n_kf * args.steps / (ms_total * 1e-3),
             "p50_keyframe_ms": p50["pageable"] if p50 else None,
@@ -386,8 +462,8 @@ def run_gpu(args):
                                                "k_associate": share[3]},
                          "whole_step_frac": (32.0 * n_proj_total / (ms_per_step * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
+            "parity": parity,
             "also": also,
-            "single_precision_mode": f32_mode,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -396,56 +472,12 @@ def run_gpu(args):
     ctx.close()
 
 
-def bench_f32_mode(torch, abi, args, device, stream, batch, arrays, exact, peak, n_proj_total):
-    """Same batch, deskew_precision = 1: step time, k_deskew_bin roofline fraction, agreement with the default mode."""
-    pts, ins, q, descs = arrays
-    ctx = abi.Context(device, deskew_precision=1)
-    ctx.set_stream(stream.cuda_stream)
-    ctx.set_extrinsics(batch.shape.rig.pose_b_c, batch.shape.rig.pose_c_l, batch.shape.rig.td_b_l)
-    ctx.batch_set_wave(args.wave)
-    ctx.batch_upload(pts, ins, q, descs)
-    for _ in range(3):
-        ctx.batch_run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        ctx.batch_run()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    ctx.set_profiling(True)
-    prof_ms, prof_n = np.zeros(4), np.zeros(4)
-    for _ in range(3):
-        ctx.batch_run()
-        m, n = ctx.batch_kernel_ms()
-        prof_ms += m
-        prof_n += n
-    ctx.set_profiling(False)
-    got = ctx.batch_download()
-    ctx.close()
-    launch_ms = prof_ms[1] / max(prof_n[1], 1)
-    both = (got["type"] == 1) & (exact["type"] == 1)
-    d0, d1 = exact["xyz_depth"][both, 3].astype(np.float64), got["xyz_depth"][both, 3].astype(np.float64)
-    rel = np.abs(d1 - d0) / np.abs(d0) if both.any() else np.zeros(1)
-    nq = len(got["type"])
-    return {
-        "ms_per_step": ms, "features_per_s": nq / (ms * 1e-3), "lidar_pts_per_s": n_proj_total / (ms * 1e-3),
-        "k_deskew_bin_launch_ms": launch_ms,
-        "k_deskew_bin_hbm_frac": 32.0 * n_proj_total / (launch_ms * 1e-3) / 1e9 / peak,
-        "validity_agreement": float(np.mean(got["type"] == exact["type"])),
-        "depth_within_1e-4": float(np.mean(rel <= 1e-4)),
-        "depth_identical": float(np.mean(d0 == d1)),
-        "max_depth_rel_diff": float(rel.max()),
-        "cells_m_equal": float(np.mean(got["m"] == exact["m"])),
-        "note": "agreement is against the default (f64) mode of this library on the same batch",
-    }
-
-
-def bench_cfg3(torch, abi, synth, device, stream, peak, n_kf=6, steps=10):
-    """Device-resident throughput of the FusionPortableV2 vehicle shape (2.62 M points per keyframe)."""
-    b = synth.make_batch(3, n_kf, n_unique_scans=20, seed=synth.BASE_SEED + 3, ins_span=3.5)
-    ctx = abi.Context(device, stack_interval=b.shape.stack_interval)
+def bench_cfg2(torch, abi, synth, device, stream, peak, n_kf=256, steps=10):
+    """Device-resident throughput of round 1's headline workload (R3LIVE handheld shape, 256 keyframes x 120 001 points x
+    300 features: every point lies inside the camera's field of view)."""
+    b = cached_batch(synth, f"cfg2_k{n_kf}_s{synth.BASE_SEED + 5}_u48",
+                     lambda: synth.make_batch(2, n_kf, seed=synth.BASE_SEED + 5, n_unique_scans=48))
+    ctx = abi.Context(device)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_extrinsics(b.shape.rig.pose_b_c, b.shape.rig.pose_c_l, b.shape.rig.td_b_l)
     ctx.batch_upload(b.points, b.ins, b.queries.reshape(-1, 3), abi.batch_descs(b))
@@ -465,12 +497,14 @@ def bench_cfg3(torch, abi, synth, device, stream, peak, n_kf=6, steps=10):
     ctx.batch_run()
     kms, kn = ctx.batch_kernel_ms()
     ctx.close()
-    return {"workload": f"cfg3_fusionportable_os1_128_x20scans_1440x1080_F{b.queries.shape[1]}_batch{n_kf}",
+    return {"workload": f"cfg2_r3live_avia_24kpts_x5scans_1280x1024_F{b.queries.shape[1]}_batch{n_kf}_independent_keyframes",
             "ms_per_step": ms, "lidar_pts_per_s": npts / (ms * 1e-3), "keyframes_per_s": n_kf / (ms * 1e-3),
             "features_per_s": n_kf * b.queries.shape[1] / (ms * 1e-3), "points_per_keyframe": npts // n_kf,
             "cells_per_keyframe": int(out["m"].mean()), "associated_fraction": float((out["type"] == 1).mean()),
             "whole_step_hbm_frac": 32.0 * npts / (ms * 1e-3) / 1e9 / peak,
-            "k_deskew_bin_hbm_frac": 32.0 * npts / (float(kms[1]) * 1e-3) / 1e9 / peak}
+            "k_deskew_bin_hbm_frac": 32.0 * npts / (float(kms[1]) * 1e-3) / 1e9 / peak,
+            "kernel_ms": {"k_prepare": float(kms[0]), "k_deskew_bin": float(kms[1]), "k_plane": float(kms[2]),
+                          "k_associate": float(kms[3])}}
 
 
 def load_traffic():
@@ -493,8 +527,8 @@ def stream_latency(abi, synth, device, n_keyframes=40):
     by levins_append_raw) from pageable and from page-locked memory."""
     from levins import rawfmt
 
-    shp = synth.shape(CFG)
-    b = synth.make_batch(CFG, n_keyframes, n_unique_scans=12, seed=synth.BASE_SEED + 77)
+    shp = synth.shape(STREAM_CFG)
+    b = synth.make_batch(STREAM_CFG, n_keyframes, n_unique_scans=12, seed=synth.BASE_SEED + 77)
     per = shp.pts_per_scan
     n_scans = len(b.points) // per
     week = 2334
@@ -546,13 +580,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--keyframes", type=int, default=DEFAULT_KEYFRAMES, help="keyframes per GPU per step")
-    ap.add_argument("--wave", type=int, default=256)
+    ap.add_argument("--wave", type=int, default=0, help="keyframes per wave of launches (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
-    ap.add_argument("--no-cfg3", action="store_true", help="skip the secondary Ouster OS1-128 x 20-scan measurement")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary measurement (configs[1] as a resident batch)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--precision", type=int, default=0, choices=[0, 1], help="levins_config.deskew_precision of the measured context")
-    ap.add_argument("--no-f32", action="store_true", help="skip the secondary measurement of the single-precision deskew mode")
     ap.add_argument("--no-stream", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

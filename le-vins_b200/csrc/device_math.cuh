@@ -47,36 +47,23 @@ struct __align__(16) Interval {
     double c0[3];        // R0^T (p0 - t0)
     double c1[3];        // R0^T (p1 - p0)
     double fast;         // != 0: entry_brackets() may be used on (t_lo, t_hi) and theta is in sin_omc_small()'s range
+    // Certified frustum cull (k_deskew_bin): the whole deskew of this interval frozen at mid-interval, in f32:
+    //   p~ = M p_lidar + m,   |p~ - p_c0| <= ca |p_lidar| + cb   for every time the entry brackets
+    // (rotation and translation left over within the interval + every rounding, all rounded up).  A point whose p~ lies
+    // outside the 90-degree image cone by more than that bound is rejected by tracking.cc:311-314 whatever its exact
+    // coordinates are, so the f64 algebra is skipped for it.  ca < 0 marks "no cull" (bound not finite).
+    float M[9]; // row-major
+    float m[3];
+    float ca, cb;
+    float pad[2];
 };
-static_assert(sizeof(Interval) == 192, "interval entry");
+static_assert(sizeof(Interval) == 256, "interval entry");
 
 // fixed extrinsics (class VINS: pose_c_l_, pose_b_c_, td_b_l_), R column-major like Eigen
 struct Extrinsics {
     double Rcl[9], tcl[3];
     double Rbc[9], tbc[3];
     double td_b_l;
-};
-
-// ---- single-precision mode (levins_config.deskew_precision = 1) ----
-// The same interval entry with the rotation / translation terms in f32 (times stay f64: 1e5 s with ns resolution).
-// Coordinates come out within ~1e-6 relative of the reference (bar: 1e-4); they are no longer bit-identical, so a
-// point next to a cell boundary may land in the neighbouring cell (measured agreement in tests/ and bench.py).
-struct __align__(16) IntervalF {
-    double t_lo, t_hi; // as in Interval (entry_brackets)
-    double ts0;
-    float inv_dts;
-    float fast; // != 0: bracket test usable and theta small (as Interval::fast)
-    float A[9];
-    float k[3];
-    float theta;
-    float c0[3];
-    float c1[3];
-    float pad;
-};
-static_assert(sizeof(IntervalF) == 112, "f32 interval entry");
-struct ExtrinsicsF {
-    float Rcl[9], tcl[3];
-    float Rbc[9], tbc[3];
 };
 
 // constants evaluated on the host with the reference's own double expressions (tracking.h:119-135)
@@ -758,46 +745,6 @@ __device__ __forceinline__ void deskew_core(float x, float y, float z, double t,
     ox = LV_D2F(fma(e.A2, wz, fma(e.A1, wy, fma(e.A0, wx, fma(s, e.c1x, e.c0x)))));
     oy = LV_D2F(fma(e.A5, wz, fma(e.A4, wy, fma(e.A3, wx, fma(s, e.c1y, e.c0y)))));
     oz = LV_D2F(fma(e.A8, wz, fma(e.A7, wy, fma(e.A6, wx, fma(s, e.c1z, e.c0z)))));
-}
-
-// ---- single-precision mode: the same formula in f32 (only the time difference is formed in f64) ----
-struct EntryRegsF {
-    double ts0;
-    float inv_dts;
-    float A0, A1, A2, A3, A4, A5, A6, A7, A8;
-    float kx, ky, kz, theta;
-    float c0x, c0y, c0z, c1x, c1y, c1z;
-};
-__device__ __forceinline__ void load_entry_f(const IntervalF* it, EntryRegsF& e) {
-    const float4* p = reinterpret_cast<const float4*>(it);
-    const double2 v1 = *reinterpret_cast<const double2*>(p + 1); // ts0 | inv_dts, fast
-    const float4 v2 = p[2], v3 = p[3], v4 = p[4], v5 = p[5], v6 = p[6];
-    e.ts0 = v1.x;
-    e.inv_dts = __int_as_float(__double2loint(v1.y));
-    e.A0 = v2.x; e.A1 = v2.y; e.A2 = v2.z; e.A3 = v2.w; e.A4 = v3.x; e.A5 = v3.y; e.A6 = v3.z; e.A7 = v3.w; e.A8 = v4.x;
-    e.kx = v4.y; e.ky = v4.z; e.kz = v4.w; e.theta = v5.x;
-    e.c0x = v5.y; e.c0y = v5.z; e.c0z = v5.w; e.c1x = v6.x; e.c1y = v6.y; e.c1z = v6.z;
-}
-__device__ __forceinline__ void deskew_core_f32(float x, float y, float z, double t, const EntryRegsF& e, const ExtrinsicsF& ex,
-                                                float& ox, float& oy, float& oz) {
-    const float p1x = fmaf(ex.Rcl[6], z, fmaf(ex.Rcl[3], y, fmaf(ex.Rcl[0], x, ex.tcl[0])));
-    const float p1y = fmaf(ex.Rcl[7], z, fmaf(ex.Rcl[4], y, fmaf(ex.Rcl[1], x, ex.tcl[1])));
-    const float p1z = fmaf(ex.Rcl[8], z, fmaf(ex.Rcl[5], y, fmaf(ex.Rcl[2], x, ex.tcl[2])));
-    const float ux = fmaf(ex.Rbc[6], p1z, fmaf(ex.Rbc[3], p1y, fmaf(ex.Rbc[0], p1x, ex.tbc[0])));
-    const float uy = fmaf(ex.Rbc[7], p1z, fmaf(ex.Rbc[4], p1y, fmaf(ex.Rbc[1], p1x, ex.tbc[1])));
-    const float uz = fmaf(ex.Rbc[8], p1z, fmaf(ex.Rbc[5], p1y, fmaf(ex.Rbc[2], p1x, ex.tbc[2])));
-    const float s = (float) (t - e.ts0) * e.inv_dts; // the difference is exact in f64 and at most one interval long
-    const float phi = -s * e.theta, p2 = phi * phi;  // |phi| < 2^-6 (Interval::fast)
-    const float sn = fmaf(phi * p2, fmaf(p2, 1.0f / 120.0f, -1.0f / 6.0f), phi);
-    const float omc = p2 * fmaf(p2, -1.0f / 24.0f, 0.5f);
-    const float cx = fmaf(e.ky, uz, -(e.kz * uy)), cy = fmaf(e.kz, ux, -(e.kx * uz)), cz = fmaf(e.kx, uy, -(e.ky * ux));
-    const float dx = fmaf(e.ky, cz, -(e.kz * cy)), dy = fmaf(e.kz, cx, -(e.kx * cz)), dz = fmaf(e.kx, cy, -(e.ky * cx));
-    const float wx = fmaf(omc, dx, fmaf(sn, cx, ux));
-    const float wy = fmaf(omc, dy, fmaf(sn, cy, uy));
-    const float wz = fmaf(omc, dz, fmaf(sn, cz, uz));
-    ox = fmaf(e.A2, wz, fmaf(e.A1, wy, fmaf(e.A0, wx, fmaf(s, e.c1x, e.c0x))));
-    oy = fmaf(e.A5, wz, fmaf(e.A4, wy, fmaf(e.A3, wx, fmaf(s, e.c1y, e.c0y))));
-    oz = fmaf(e.A8, wz, fmaf(e.A7, wy, fmaf(e.A6, wx, fmaf(s, e.c1z, e.c0z))));
 }
 
 // Range gate (le_vins.cc:447-451) on the squared norm (see Consts) + entry lookup + deskew.  false for gated points.

@@ -317,13 +317,87 @@ struct PrepareArgs {
     unsigned long long pts_cap; // ring capacity (ULLONG_MAX for linear pools)
     const InsSample* ins;
     Interval* table;
-    IntervalF* tableF; // the same entries in f32 (single-precision mode), same indexing
     ChunkDesc* chunks; // batch: [gridDim.x][chunks_per_kf], written here; streaming (null): k_chunk_desc does it
     unsigned chunks_per_kf;
     RingState* ring; // streaming: the keyframe's buffer is the ring (le_vins.cc:410-437), and is popped
     Extrinsics ext;
     Consts c;
 };
+
+// The certified-cull record of an interval entry (see Interval): the deskew frozen at the middle of the entry's own range
+// of s = (t - ts0) * inv_dts, and a bound on everything that was dropped.  With Rod(k, phi) = I + sin(phi) K + (1 - cos(phi)) K^2:
+//   p_c0(s) = A Rod(k, -s theta) (R_bc (R_cl p + t_cl) + t_bc) + c0 + s c1
+//   |Rod(k, a) - Rod(k, b)| <= |a - b| (|k| + |k|^2)                      (operator norm; |k| = 1 for a proper axis)
+// so |p_c0(s) - p_c0(s_mid)| <= h (|A| theta kk (|R_bc| (|R_cl| |p| + |t_cl|) + |t_bc|) + |c1|),  h = max |s - s_mid|,
+// with Frobenius norms standing in for operator norms.  On top of that come the f32 evaluation of M p + m (4 roundings per
+// row, M and m themselves rounded), the intermediate f32 rounding of pointcloud.cc:68 and the f64 round-off of the real path:
+// all far below the 1e-5 (|M| |p| + |m|) that is added for them.
+__device__ __forceinline__ void fill_cull_record(Interval& e, const Extrinsics& ex, bool fallback) {
+    double s_mid = 0.0, h = 0.0;
+    if (!fallback) {
+        const double s_lo = (e.t_lo - e.ts0) * e.inv_dts, s_hi = (e.t_hi - e.ts0) * e.inv_dts;
+        s_mid = 0.5 * (s_lo + s_hi);
+        h = 0.5 * fabs(s_hi - s_lo) * 1.001 + 1e-9;
+    }
+    double sn, omc;
+    sin_omc(-s_mid * e.theta, sn, omc);
+    const double kx = e.k[0], ky = e.k[1], kz = e.k[2];
+    // Rod = I + sn K + omc K^2, row-major
+    const double K[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
+    double Rod[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double k2 = (K[3 * r] * K[c] + K[3 * r + 1] * K[3 + c]) + K[3 * r + 2] * K[6 + c];
+            Rod[3 * r + c] = (r == c ? 1.0 : 0.0) + sn * K[3 * r + c] + omc * k2;
+        }
+    double AR[9], ARb[9], Md[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) AR[3 * r + c] = (e.A[3 * r] * Rod[c] + e.A[3 * r + 1] * Rod[3 + c]) + e.A[3 * r + 2] * Rod[6 + c];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) // R_bc is column-major: element (i, c) = Rbc[3 * c + i]
+            ARb[3 * r + c] = (AR[3 * r] * ex.Rbc[3 * c] + AR[3 * r + 1] * ex.Rbc[3 * c + 1]) + AR[3 * r + 2] * ex.Rbc[3 * c + 2];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            Md[3 * r + c] = (ARb[3 * r] * ex.Rcl[3 * c] + ARb[3 * r + 1] * ex.Rcl[3 * c + 1]) + ARb[3 * r + 2] * ex.Rcl[3 * c + 2];
+    double md[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        md[r] = ((ARb[3 * r] * ex.tcl[0] + ARb[3 * r + 1] * ex.tcl[1]) + ARb[3 * r + 2] * ex.tcl[2]) +
+                ((AR[3 * r] * ex.tbc[0] + AR[3 * r + 1] * ex.tbc[1]) + AR[3 * r + 2] * ex.tbc[2]) + (e.c0[r] + s_mid * e.c1[r]);
+    auto fro = [](const double* m, int n) {
+        double s = 0;
+        for (int i = 0; i < n; i++) s += m[i] * m[i];
+        return sqrt(s);
+    };
+    const double nA = fro(e.A, 9), nRbc = fro(ex.Rbc, 9), nRcl = fro(ex.Rcl, 9), nk = fro(e.k, 3);
+    const double rot = nA * h * fabs(e.theta) * (nk + nk * nk);
+    double ca = rot * nRbc * nRcl + 1e-5 * fro(Md, 9);
+    double cb = rot * (nRbc * fro(ex.tcl, 3) + fro(ex.tbc, 3)) + h * fro(e.c1, 3) + 1e-5 * fro(md, 3) + 1e-6;
+    ca *= 1.01;
+    cb *= 1.01;
+    bool ok = (ca == ca) && (cb == cb) && ca < 0.05 && cb < 1e6;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        e.M[i] = (float) Md[i];
+        ok = ok && (fabs(Md[i]) < 1e6);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        e.m[i] = (float) md[i];
+        ok = ok && (fabs(md[i]) < 1e9);
+    }
+    e.ca = ok ? (float) ca * 1.000001f : -1.0f; // (float) rounds to nearest: push it up again
+    e.cb = ok ? (float) cb * 1.000001f : 0.0f;
+    e.pad[0] = e.pad[1] = 0.f;
+}
 
 __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ PrepareArgs a) {
     KfState* kf = a.kfs + blockIdx.x;
@@ -449,29 +523,9 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
         // the one-compare bracket test needs positive, increasing times; the straight-line deskew a small angle
         const bool ordered = j == 0 ? (e.t_hi > 0 && e.t_lo > e.t_hi) : (e.t_lo > 0 && e.t_hi > e.t_lo);
         e.fast = (ordered && e.theta * e.theta < 2.44140625e-4) ? 1.0 : 0.0;
+        fill_cull_record(e, a.ext, j == 0);
         tab[j] = e;
         if (j == 0) tab[nins] = e; // slot nins: the fallback again, as the successor of the last interval (k_chunk_desc)
-        {
-            IntervalF f;
-            f.t_lo = e.t_lo;
-            f.t_hi = e.t_hi;
-            f.ts0 = e.ts0;
-            f.inv_dts = (float) e.inv_dts;
-            f.fast = (float) e.fast;
-#pragma unroll
-            for (int i = 0; i < 9; i++) f.A[i] = (float) e.A[i];
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                f.k[i] = (float) e.k[i];
-                f.c0[i] = (float) e.c0[i];
-                f.c1[i] = (float) e.c1[i];
-            }
-            f.theta = (float) e.theta;
-            f.pad = 0.f;
-            IntervalF* __restrict__ tabF = a.tableF + kf->table_begin;
-            tabF[j] = f;
-            if (j == 0) tabF[nins] = f;
-        }
     }
     // batch mode: the chunk descriptors of this keyframe (k_deskew_bin's work list), while the table is hot in L1/L2
     if (a.chunks) {
@@ -525,8 +579,8 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
 #ifndef LV_MINBLK
 #define LV_MINBLK 1
 #endif
-#ifndef LV_MINBLK_F // CTAs per SM of the single-precision instantiations (half the register state per point)
-#define LV_MINBLK_F LV_MINBLK
+#ifndef LV_CULL // 0: never try the certified frustum cull (A/B timing)
+#define LV_CULL 1
 #endif
 #ifndef LV_KO // knock-out experiments (timing only, results are wrong): 1 no RED, 2 no deskew math, 4 no cell math, 8 loads only
 #define LV_KO 0
@@ -535,18 +589,19 @@ constexpr int DESKEW_GROUP = LV_GROUP; // of which this many are in flight toget
 constexpr int DESKEW_WARPS = DESKEW_THREADS / 32;
 constexpr int CHUNK_BYTES = CHUNK_PTS * 32;
 constexpr int DESKEW_STAGES = LV_STAGES;
-constexpr int STAGE_ENT_OFF = CHUNK_BYTES;                        // two interval entries (2 x 192 B)
-constexpr int STAGE_HDR_OFF = STAGE_ENT_OFF + 2 * (int) sizeof(Interval); // {cnt}
-constexpr int STAGE_BYTES = STAGE_HDR_OFF + 16;
+constexpr int STAGE_ENT_OFF = CHUNK_BYTES;                               // two interval entries (2 x 256 B)
+constexpr int STAGE_BYTES = STAGE_ENT_OFF + 2 * (int) sizeof(Interval);
 constexpr int AMBQ = LV_AMBQ; // undecided cell ids queued per warp
-constexpr int WARP_BAR_OFF = DESKEW_STAGES * STAGE_BYTES;
-constexpr int WARP_Q_OFF = WARP_BAR_OFF + 32;
+constexpr int WARP_BAR_OFF = DESKEW_STAGES * STAGE_BYTES; // one mbarrier per stage
+constexpr int WARP_HDR_OFF = WARP_BAR_OFF + 32;           // points in the chunk of each stage
+constexpr int WARP_Q_OFF = WARP_HDR_OFF + 16;
 constexpr int WARP_QKF_OFF = WARP_Q_OFF + AMBQ * 16;
 constexpr int WARP_SMEM = WARP_QKF_OFF + AMBQ * 4;
-constexpr int DESKEW_SMEM = DESKEW_WARPS * WARP_SMEM; // 16 warps x 14 160 B = 226 560 B: one CTA per SM
+constexpr int DESKEW_SMEM = DESKEW_WARPS * WARP_SMEM; // 16 warps x 14 512 B = 232 192 B: one CTA per SM
 constexpr int DESKEW_BLOCK = DESKEW_THREADS;
+static_assert(DESKEW_STAGES <= 4, "barrier / header slots");
 static_assert(STAGE_BYTES % 16 == 0 && WARP_SMEM % 16 == 0 && WARP_Q_OFF % 16 == 0, "TMA / vector alignment");
-static_assert(LV_MINBLK * (DESKEW_SMEM + 1024) <= 228 * 1024 && LV_MINBLK_F * (DESKEW_SMEM + 1024) <= 228 * 1024, "CTAs per SM");
+static_assert(LV_MINBLK * DESKEW_SMEM <= 227 * 1024, "CTAs per SM");
 
 struct DeskewArgs {
     KfState* kfs; // first keyframe of this launch
@@ -555,13 +610,11 @@ struct DeskewArgs {
     const PointXYZIT* pts;
     unsigned long long pts_cap;
     const Interval* table;
-    const IntervalF* tableF;  // single-precision mode
     ChunkDesc* chunks;        // [n_kf][chunks_per_kf]
     unsigned long long* zbuf; // [n_kf][CELLS]
     PointXYZI* cloud_out;     // streaming only (n_kf == 1), nullable
     unsigned gen;             // z-buffer generation of this launch
     Extrinsics ext;
-    ExtrinsicsF extf; // single-precision mode
     Consts c;
 };
 
@@ -608,6 +661,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// the same with an L2 eviction-priority hint: the point stream is read exactly once, so it should not push the
+// z-buffers (re-used by every chunk of the keyframe and again by k_associate) out of L2
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_bulk_g2s_hint(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar,
+                                                  unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
 
 __device__ __forceinline__ KfView kf_view(const KfState* __restrict__ kf, const Interval* table) {
     KfView kv;
@@ -634,24 +701,21 @@ __device__ __forceinline__ int cell_id(float x, float y, float z, const Consts& 
 }
 
 // lane 0: start the copies of one chunk into a stage of the warp's ring
-template <bool FAST>
-__device__ __forceinline__ void issue_chunk(const DeskewArgs& a, const ChunkDesc& d, unsigned char* stage, unsigned long long* bar) {
+__device__ __forceinline__ void issue_chunk(const DeskewArgs& a, const ChunkDesc& d, unsigned char* stage, unsigned* hdr,
+                                            unsigned long long* bar, unsigned long long policy) {
     const unsigned cnt = d.cnt;
-    *reinterpret_cast<unsigned*>(stage + STAGE_HDR_OFF) = cnt;
+    *hdr = cnt;
     if (cnt == 0) {
         mbar_arrive(bar); // release: the header is visible to whoever passes the barrier
         return;
     }
-    constexpr unsigned ENT = 2u * (unsigned) (FAST ? sizeof(IntervalF) : sizeof(Interval)); // entries ent0, ent0 + 1
+    constexpr unsigned ENT = 2u * (unsigned) sizeof(Interval); // entries ent0, ent0 + 1
     mbar_arrive_expect_tx(bar, cnt * 32u + ENT);
-    if (FAST)
-        tma_bulk_g2s(stage + STAGE_ENT_OFF, a.tableF + d.ent0, ENT, bar);
-    else
-        tma_bulk_g2s(stage + STAGE_ENT_OFF, a.table + d.ent0, ENT, bar);
+    tma_bulk_g2s(stage + STAGE_ENT_OFF, a.table + d.ent0, ENT, bar);
     const unsigned long long room = a.pts_cap - d.phys; // ring: the chunk may wrap around the end
     const unsigned first = room < cnt ? (unsigned) room : cnt;
-    tma_bulk_g2s(stage, a.pts + d.phys, first * 32u, bar);
-    if (first < cnt) tma_bulk_g2s(stage + first * 32u, a.pts, (cnt - first) * 32u, bar);
+    tma_bulk_g2s_hint(stage, a.pts + d.phys, first * 32u, bar, policy);
+    if (first < cnt) tma_bulk_g2s_hint(stage + first * 32u, a.pts, (cnt - first) * 32u, bar, policy);
 }
 
 // settle the queued cell ids of a warp with the exact path (all lanes busy instead of one lane per rare case)
@@ -669,21 +733,41 @@ __device__ __noinline__ void flush_undecided(const float4* q, const unsigned* qk
     __syncwarp();
 }
 
-template <int LIBM_MODE, bool WRITE_CLOUD, bool FAST>
-__global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
+// Certified frustum cull (see Interval / fill_cull_record): true when the point is rejected by the FOV gate of
+// tracking.cc:311-314 for certain, i.e. whatever its exact deskewed coordinates (X, Y, Z) are, given |(X,Y,Z) - p~| <= d:
+//   z~ < -d                        =>  Z < 0
+//   max(|x~|, |y~|) - |z~| > 2 d   =>  max(|X|, |Y|) > |Z|  =>  Z < 0 or fl32(|X| / |Z|) >= 1 > tan(45 deg) (0x1.fffffffffffffp-1)
+// Any NaN makes both comparisons false (not culled).
+struct CullRegs {
+    float4 r0, r1, r2, r3; // M0..M3 | M4..M7 | M8 m0 m1 m2 | ca cb - -
+};
+__device__ __forceinline__ bool certainly_outside(const CullRegs& q, float x, float y, float z, float n2) {
+    const float xt = fmaf(q.r0.z, z, fmaf(q.r0.y, y, fmaf(q.r0.x, x, q.r2.y)));
+    const float yt = fmaf(q.r1.y, z, fmaf(q.r1.x, y, fmaf(q.r0.w, x, q.r2.z)));
+    const float zt = fmaf(q.r2.x, z, fmaf(q.r1.w, y, fmaf(q.r1.z, x, q.r2.w)));
+    float n;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(n2)); // 2^-22 relative: covered by the 1 % the bound was inflated by
+    const float d = fmaf(q.r3.x, n, q.r3.y);
+    return (zt < -d) | (fmaxf(fabsf(xt), fabsf(yt)) - fabsf(zt) > 2.001f * d);
+}
+
+template <int LIBM_MODE, bool WRITE_CLOUD>
+__global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = smem_raw + warp * WARP_SMEM;
     unsigned long long* full = reinterpret_cast<unsigned long long*>(wbase + WARP_BAR_OFF);
+    unsigned* hdr = reinterpret_cast<unsigned*>(wbase + WARP_HDR_OFF);
     float4* q_pt = reinterpret_cast<float4*>(wbase + WARP_Q_OFF);
     unsigned* q_kf = reinterpret_cast<unsigned*>(wbase + WARP_QKF_OFF);
 
-    const unsigned W = gridDim.x * DESKEW_WARPS; // the 8 warps of a CTA take 8 neighbouring chunks (32 KB of one keyframe)
+    const unsigned W = gridDim.x * DESKEW_WARPS; // the warps of a CTA take neighbouring chunks of one keyframe
     const unsigned cpk = a.chunks_per_kf, total = a.n_kf * cpk;
     unsigned c = blockIdx.x * DESKEW_WARPS + warp;
     if (c >= total) return;
     unsigned kfi = c / cpk, rem = c - kfi * cpk; // keyframe and chunk-in-keyframe of chunk c, advanced incrementally
     const unsigned Wq = W / cpk, Wr = W - Wq * cpk;
+    const unsigned long long policy = l2_policy_evict_first();
 
     if (lane == 0) {
 #pragma unroll
@@ -698,7 +782,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
                 d.phys = (unsigned long long) r.x | ((unsigned long long) r.y << 32);
                 d.ent0 = r.z;
                 d.cnt = r.w;
-                issue_chunk<FAST>(a, d, wbase + i * STAGE_BYTES, full + i);
+                issue_chunk(a, d, wbase + i * STAGE_BYTES, hdr + i, full + i, policy);
             }
         }
     }
@@ -707,7 +791,11 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
     if (c + (DESKEW_STAGES - 1) * W < total) dn = __ldg(reinterpret_cast<const uint4*>(a.chunks + c + (DESKEW_STAGES - 1) * W));
 
     unsigned s = 0, ph = 0, s_fill = DESKEW_STAGES - 1, qn = 0;
-    for (; c < total; c += W) {
+    // The cull only pays where whole warps fall outside the image cone (a 360-degree scanner: three quarters of the
+    // chunks); a sensor that looks where the camera looks never culls anything.  After 8 chunks without a single culled
+    // point the warp tries only every 16th chunk.
+    unsigned cull_miss = 0, iter = 0;
+    for (; c < total; c += W, iter++) {
         // stage s_fill was read during the previous iteration: every lane is past those reads here
         __syncwarp();
         if (lane == 0 && c + (DESKEW_STAGES - 1) * W < total) {
@@ -715,16 +803,18 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
             d.phys = (unsigned long long) dn.x | ((unsigned long long) dn.y << 32);
             d.ent0 = dn.z;
             d.cnt = dn.w;
-            issue_chunk<FAST>(a, d, wbase + s_fill * STAGE_BYTES, full + s_fill);
+            issue_chunk(a, d, wbase + s_fill * STAGE_BYTES, hdr + s_fill, full + s_fill, policy);
         }
         if (c + DESKEW_STAGES * W < total) dn = __ldg(reinterpret_cast<const uint4*>(a.chunks + c + DESKEW_STAGES * W));
         const unsigned char* st = wbase + s * STAGE_BYTES;
         mbar_wait(full + s, ph);
-        const unsigned cnt = *reinterpret_cast<const unsigned*>(st + STAGE_HDR_OFF);
+        const unsigned cnt = hdr[s];
 
         if (cnt) {
             const float4* __restrict__ sp = reinterpret_cast<const float4*>(st);
             const unsigned off = rem * CHUNK_PTS;
+            const bool cull_try = LV_CULL && !WRITE_CLOUD && (cull_miss < 8 || (iter & 15) == 0);
+            bool culled_any = false;
             // 4 consecutive points per thread (they almost always share one INS interval).  Lane l visits them in the order
             // (j + l) & 3: with the plain order all lanes of a quarter-warp would hit the same 4 banks (128-byte lane stride,
             // 8-way conflict on every LDS.128); rotated, the conflict is 2-way.
@@ -734,7 +824,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
             unsigned pi[DESKEW_GROUP];
 #pragma unroll
             for (int j = 0; j < DESKEW_GROUP; j++) pi[j] = i0 + ((g0 + j + lane) & (DESKEW_PPT - 1));
-            float px[DESKEW_GROUP], py[DESKEW_GROUP], pz[DESKEW_GROUP];
+            float px[DESKEW_GROUP], py[DESKEW_GROUP], pz[DESKEW_GROUP], pn2[DESKEW_GROUP];
             double tt[DESKEW_GROUP];
             bool kept[DESKEW_GROUP];
             bool any_kept = false;
@@ -746,8 +836,8 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
                 py[j] = xyz.y;
                 pz[j] = xyz.z;
                 tt[j] = tm + a.ext.td_b_l; // le_vins.cc:455
-                const float n2 = v3f_sqnorm_t<FAST>(xyz.x, xyz.y, xyz.z);
-                kept[j] = (pi[j] < cnt) && !((n2 > a.c.n2_far) || (n2 < a.c.n2_near)); // le_vins.cc:447-451
+                pn2[j] = v3f_sqnorm(xyz.x, xyz.y, xyz.z);
+                kept[j] = (pi[j] < cnt) && !((pn2[j] > a.c.n2_far) || (pn2[j] < a.c.n2_near)); // le_vins.cc:447-451
                 any_kept |= kept[j];
             }
             float ox[DESKEW_GROUP], oy[DESKEW_GROUP], oz[DESKEW_GROUP];
@@ -772,12 +862,9 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
             if (any_kept) {
 #endif
                 // which of the two staged entries brackets every kept point of this thread (checked, not assumed)
-                constexpr unsigned ENT_SZ = FAST ? sizeof(IntervalF) : sizeof(Interval);
                 const unsigned char* E0 = st + STAGE_ENT_OFF;
-                const unsigned char* E1 = E0 + ENT_SZ;
-                auto usable = [](const unsigned char* e) { // Interval::fast / IntervalF::fast
-                    return FAST ? reinterpret_cast<const IntervalF*>(e)->fast != 0.f : reinterpret_cast<const Interval*>(e)->fast != 0.0;
-                };
+                const unsigned char* E1 = E0 + sizeof(Interval);
+                auto usable = [](const unsigned char* e) { return reinterpret_cast<const Interval*>(e)->fast != 0.0; };
                 const double2 T0 = *reinterpret_cast<const double2*>(E0);
                 const unsigned long long lo0 = (unsigned long long) __double_as_longlong(T0.x);
                 const unsigned long long w0 = usable(E0) ? (unsigned long long) __double_as_longlong(T0.y) - lo0 : 0ull;
@@ -798,13 +885,27 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
                     fast = in1;
                 }
                 if (fast) {
-                    // common case: one entry for the group, straight-line code, the points interleave
-                    if constexpr (FAST) {
-                        EntryRegsF e;
-                        load_entry_f(reinterpret_cast<const IntervalF*>(ep), e);
+                    if (cull_try) {
+                        // points that cannot land inside the image cone need no coordinates (and leave no trace)
+                        const float4* cr = reinterpret_cast<const float4*>(ep + offsetof(Interval, M));
+                        CullRegs q;
+                        q.r3 = cr[3];
+                        if (q.r3.x >= 0.f) {
+                            q.r0 = cr[0];
+                            q.r1 = cr[1];
+                            q.r2 = cr[2];
+                            any_kept = false;
 #pragma unroll
-                        for (int j = 0; j < DESKEW_GROUP; j++) deskew_core_f32(px[j], py[j], pz[j], tt[j], e, a.extf, ox[j], oy[j], oz[j]);
-                    } else {
+                            for (int j = 0; j < DESKEW_GROUP; j++) {
+                                const bool out = kept[j] && certainly_outside(q, px[j], py[j], pz[j], pn2[j]);
+                                culled_any |= out;
+                                kept[j] = kept[j] && !out;
+                                any_kept |= kept[j];
+                            }
+                        }
+                    }
+                    if (any_kept) {
+                        // common case: one entry for the group, straight-line code, the points interleave
                         EntryRegs e;
                         load_entry_shared(reinterpret_cast<const Interval*>(ep), e);
 #pragma unroll
@@ -817,17 +918,11 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
                     for (int j = 0; j < DESKEW_GROUP; j++)
                         if (kept[j]) {
                             const unsigned char* es = key_brackets(lo0, w0, tt[j]) ? E0 : key_brackets(lo1, w1, tt[j]) ? E1 : nullptr;
+                            const Interval* epj = es ? reinterpret_cast<const Interval*>(es) : find_entry_global(a.kfs + kfi, a.table, tt[j]);
+                            EntryRegs e;
+                            load_entry_shared(epj, e); // generic pointer: shared or global
                             float x, y, z;
-                            if (FAST && es) {
-                                EntryRegsF e;
-                                load_entry_f(reinterpret_cast<const IntervalF*>(es), e);
-                                deskew_core_f32(px[j], py[j], pz[j], tt[j], e, a.extf, x, y, z);
-                            } else { // (in single-precision mode too: the rare cases take the f64 formula)
-                                const Interval* epj = (!FAST && es) ? reinterpret_cast<const Interval*>(es) : find_entry_global(a.kfs + kfi, a.table, tt[j]);
-                                EntryRegs e;
-                                load_entry_shared(epj, e); // generic pointer: shared or global
-                                deskew_core<false>(px[j], py[j], pz[j], tt[j], e, a.ext, x, y, z);
-                            }
+                            deskew_core<false>(px[j], py[j], pz[j], tt[j], e, a.ext, x, y, z);
                             ox[j] = x;
                             oy[j] = y;
                             oz[j] = z;
@@ -843,6 +938,8 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
                         out[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
             }
+            // nothing left in this warp (every point gated or culled): no cell ids, no keys
+            if (!__any_sync(0xffffffffu, any_kept)) continue;
             // stage 2: cell ids (a default point lands at col = -150 and is dropped at tracking.cc:326-328)
             unsigned long long key[DESKEW_GROUP];
             int cell[DESKEW_GROUP];
@@ -861,8 +958,8 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
             }
 #pragma unroll
             for (int j = 0; j < DESKEW_GROUP; j++) {
-                const float range = sqrtf(v3f_sqnorm_t<FAST>(ox[j], oy[j], oz[j])); // tracking.cc:330
-                if (!kept[j] || !(range < FLT_MAX)) cell[j] = -1;            // tracking.cc:332 against the FLT_MAX initial value
+                const float range = sqrtf(v3f_sqnorm(ox[j], oy[j], oz[j])); // tracking.cc:330
+                if (!kept[j] || !(range < FLT_MAX)) cell[j] = -1;          // tracking.cc:332 against the FLT_MAX initial value
                 key[j] = key_make(a.gen, range, off + pi[j]);
             }
             // z-buffer: fire-and-forget RED.MIN.64, one per in-grid point (no probe: a probe costs the L1/L2 path as much
@@ -896,6 +993,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, FAST ? LV_MINBLK_F : LV_MINBLK) 
                 }
             }
             } // group
+            if (cull_try) cull_miss = __any_sync(0xffffffffu, culled_any) ? 0u : cull_miss + 1u;
         }
         s_fill = s;
         if (++s == DESKEW_STAGES) {

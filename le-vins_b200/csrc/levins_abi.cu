@@ -47,7 +47,6 @@ struct levins_ctx {
     levins_config cfg{};
     Consts consts{};
     Extrinsics ext{};
-    ExtrinsicsF extf{}; // the same, rounded to f32 (single-precision mode)
     bool have_ext = false;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -64,7 +63,7 @@ struct levins_ctx {
     DevBuf ring_state; // RingState
     uint64_t ring_tail = 0;     // physical index one past the newest point
     uint64_t ring_count_ub = 0; // host's upper bound of the live point count
-    DevBuf s_ins, s_table, s_tableF, s_kf, s_queries;
+    DevBuf s_ins, s_table, s_kf, s_queries;
     DevBuf chunks; // ChunkDesc of the current k_deskew_bin launch (streaming and batch)
     DevBuf raw_stage, raw_blocks, raw_misc; // levins_append_raw: records, per-block counts, {min, max, result}
     DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2, s_nn, s_nn_meta;
@@ -89,11 +88,7 @@ struct levins_ctx {
     size_t pin_total() const { return pin_xyzd() + cfg.max_features * 16 + 256; }
 
     // ---- batch state ----
-    DevBuf b_pts, b_ins, b_table, b_tableF, b_queries, b_kfs;
-    // the f32 twin of an interval-table pool (same indexing)
-    const IntervalF* tableF_of(const Interval* t) const {
-        return t == static_cast<const Interval*>(s_table.p) ? static_cast<const IntervalF*>(s_tableF.p) : static_cast<const IntervalF*>(b_tableF.p);
-    }
+    DevBuf b_pts, b_ins, b_table, b_queries, b_kfs;
     DevBuf b_results; // xyz_depth (16 B / query) immediately followed by type (1 B / query): one contiguous block, so that an
                       // exchange step can move both with a single collective
     size_t b_results_nq = 0;
@@ -194,7 +189,6 @@ int next_gen(levins_ctx* ctx, unsigned long long* z, size_t n, unsigned* gen) {
 int ensure_stream_buffers(levins_ctx* ctx, size_t n_ins, size_t n_feat) {
     CU(ctx->s_ins.ensure(std::max<size_t>(n_ins, 1) * sizeof(InsSample)));
     CU(ctx->s_table.ensure((std::max<size_t>(n_ins, 1) + 1) * sizeof(Interval))); // + the fallback copy
-    CU(ctx->s_tableF.ensure((std::max<size_t>(n_ins, 1) + 1) * sizeof(IntervalF)));
     CU(ctx->s_kf.ensure(sizeof(KfState)));
     CU(ctx->s_queries.ensure(std::max<size_t>(n_feat, 1) * 3 * sizeof(float)));
     CU(ctx->s_type.ensure(std::max<size_t>(n_feat, 1)));
@@ -255,20 +249,14 @@ int launch_deskew(levins_ctx* ctx, DeskewArgs& a, bool write_cloud) {
     const unsigned total = a.n_kf * a.chunks_per_kf;
     if (total == 0) return LEVINS_OK;
     using Kernel = void (*)(DeskewArgs);
-    static const Kernel kernels[2][2][2] = {
-        {{k_deskew_bin<0, false, false>, k_deskew_bin<0, false, true>}, {k_deskew_bin<0, true, false>, k_deskew_bin<0, true, true>}},
-        {{k_deskew_bin<1, false, false>, k_deskew_bin<1, false, true>}, {k_deskew_bin<1, true, false>, k_deskew_bin<1, true, true>}}};
+    static const Kernel kernels[2][2] = {{k_deskew_bin<0, false>, k_deskew_bin<0, true>}, {k_deskew_bin<1, false>, k_deskew_bin<1, true>}};
     if (!ctx->deskew_attr_set) {
-        for (int i = 0; i < 8; i++)
-            CU(cudaFuncSetAttribute(kernels[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
+        for (int i = 0; i < 4; i++)
+            CU(cudaFuncSetAttribute(kernels[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
         ctx->deskew_attr_set = true;
     }
-    const bool fast = ctx->cfg.deskew_precision == 1;
-    const unsigned grid = std::min<unsigned>((total + DESKEW_WARPS - 1) / DESKEW_WARPS,
-                                             (unsigned) (fast ? LV_MINBLK_F : LV_MINBLK) * (unsigned) ctx->num_sms);
-    a.tableF = fast ? ctx->tableF_of(a.table) : nullptr;
-    a.extf = ctx->extf;
-    kernels[ctx->consts.libm_mode ? 1 : 0][write_cloud ? 1 : 0][fast ? 1 : 0]<<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
+    const unsigned grid = std::min<unsigned>((total + DESKEW_WARPS - 1) / DESKEW_WARPS, (unsigned) LV_MINBLK * (unsigned) ctx->num_sms);
+    kernels[ctx->consts.libm_mode ? 1 : 0][write_cloud ? 1 : 0]<<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
     return LEVINS_OK;
@@ -308,7 +296,6 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     pa.pts_cap = ctx->cfg.max_points;
     pa.ins = ctx->s_ins.as<InsSample>();
     pa.table = ctx->s_table.as<Interval>();
-    pa.tableF = ctx->s_tableF.as<IntervalF>();
     pa.ring = ctx->ring_state.as<RingState>();
     pa.ext = ctx->ext;
     pa.c = ctx->consts;
@@ -465,8 +452,7 @@ extern "C" int levins_create(int device, const levins_config* cfg, levins_ctx** 
         memcpy(&ctx->cfg, cfg, n);
         ctx->cfg.struct_size = sizeof(levins_config);
     }
-    if (ctx->cfg.max_points == 0 || ctx->cfg.max_ins == 0 || ctx->cfg.stack_interval <= 0 || ctx->cfg.deskew_precision < 0 ||
-        ctx->cfg.deskew_precision > 1) {
+    if (ctx->cfg.max_points == 0 || ctx->cfg.max_ins == 0 || ctx->cfg.stack_interval <= 0 || ctx->cfg.deskew_precision != 0) {
         delete ctx;
         return LEVINS_ERR_ARG;
     }
@@ -487,7 +473,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->chunks, &ctx->raw_stage, &ctx->raw_blocks, &ctx->raw_misc, &ctx->s_tableF, &ctx->b_tableF, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
+    for (DevBuf* b : {&ctx->ring, &ctx->ring_state, &ctx->chunks, &ctx->raw_stage, &ctx->raw_blocks, &ctx->raw_misc, &ctx->s_ins, &ctx->s_table, &ctx->s_kf, &ctx->s_queries, &ctx->s_type,
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
@@ -530,14 +516,6 @@ extern "C" int levins_set_extrinsics(levins_ctx* ctx, const levins_pose* pose_b_
     memcpy(ctx->ext.Rcl, pose_c_l->R, sizeof(double) * 9);
     memcpy(ctx->ext.tcl, pose_c_l->t, sizeof(double) * 3);
     ctx->ext.td_b_l = td_b_l;
-    for (int i = 0; i < 9; i++) {
-        ctx->extf.Rcl[i] = (float) ctx->ext.Rcl[i];
-        ctx->extf.Rbc[i] = (float) ctx->ext.Rbc[i];
-    }
-    for (int i = 0; i < 3; i++) {
-        ctx->extf.tcl[i] = (float) ctx->ext.tcl[i];
-        ctx->extf.tbc[i] = (float) ctx->ext.tbc[i];
-    }
     ctx->have_ext = true;
     return LEVINS_OK;
 }
@@ -955,7 +933,6 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
     CU(ctx->b_pts.ensure(std::max<size_t>(n_points, 1) * sizeof(PointXYZIT)));
     CU(ctx->b_ins.ensure(n_ins * sizeof(InsSample)));
     CU(ctx->b_table.ensure(table_entries * sizeof(Interval)));
-    CU(ctx->b_tableF.ensure(table_entries * sizeof(IntervalF)));
     CU(ctx->b_queries.ensure(std::max<size_t>(n_queries, 1) * 12));
     CU(ctx->b_kfs.ensure(n_kf * sizeof(KfState)));
     CU(ctx->b_results.ensure(std::max<size_t>(n_queries, 1) * 17));
@@ -1022,7 +999,6 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
     pa.pts_cap = ~0ull;
     pa.ins = ctx->b_ins.as<InsSample>();
     pa.table = ctx->b_table.as<Interval>();
-    pa.tableF = ctx->b_tableF.as<IntervalF>();
     pa.ring = nullptr;
     pa.ext = ctx->ext;
     pa.c = ctx->consts;
@@ -1034,6 +1010,9 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             max_pts = std::max<uint64_t>(max_pts, ctx->b_descs[k0 + i].pt_count);
             max_q = std::max<uint64_t>(max_q, ctx->b_descs[k0 + i].q_count);
         }
+        // The slots are about to be reused (and, once every 254 generations, cleared): the previous wave's k_count_cells on
+        // the side stream must be done with them first, whether or not this wave launches a deskew kernel.
+        if (k0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_counted, 0));
         // every wave is a new z-buffer generation: the slots are reused without being cleared
         int r = next_gen(ctx, ctx->b_zbuf.as<unsigned long long>(), (size_t) ctx->b_wave_alloc * CELLS, &ctx->b_gen);
         if (r) return r;
@@ -1067,7 +1046,6 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         }
         mark(0, false);
         if (max_pts) {
-            if (k0) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_counted, 0)); // the slots are about to be reused
             mark(1, true);
             r = launch_deskew(ctx, da, false);
             mark(1, false);

@@ -238,3 +238,82 @@ def test_scans_from_page_locked_buffers(ctx, oracle):
     ref = oracle.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries)
     assert np.array_equal(got["type"], ref["type"]) and got["m"] == ref["m"]
     hb.close()
+
+
+def test_more_than_254_waves(oracle, built_lib):
+    """z-buffer slots are recycled by generation and cleared for real once every 254 uses: a batch with more waves than
+    that (wave = 1, some keyframes without features, so that no feature kernel separates one wave's cell count from the
+    next wave's clear) must still report every keyframe's M."""
+    shp = synth.Shape(**{**synth.shape(2).__dict__, "pts_per_scan": 600, "n_features": 4})
+    b = synth.make_batch(2, 300, n_unique_scans=9, shp=shp)
+    descs = abi.batch_descs(b)
+    descs["q_count"][::3] = 0  # every third keyframe has no features
+    c = abi.Context(0)
+    c.set_extrinsics(b.shape.rig.pose_b_c, b.shape.rig.pose_c_l, b.shape.rig.td_b_l)
+    c.batch_set_wave(1)
+    c.batch_upload(b.points, b.ins, b.queries.reshape(-1, 3), descs)
+    want_m = None
+    for rep in range(2):  # the second run starts in the middle of a generation cycle
+        c.batch_run()
+        out = c.batch_download()
+        if want_m is None:
+            want_m = np.zeros(b.n_keyframes, np.uint32)
+            for k in range(b.n_keyframes):
+                kf = synth.batch_keyframe(b, k)
+                r1 = oracle.stack_deskew(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, 0.5)
+                want_m[k] = oracle.range_image(r1["cloud"])["m"]
+        assert np.array_equal(out["m"], want_m), np.nonzero(out["m"] != want_m)[0][:10]
+    c.close()
+
+
+def _edge_band_scenario(seed, n=6000):
+    """Points aimed at the border of the 90-degree image cone (|x| / z or |y| / z = 1 +- 1e-7 .. 1e-1), every one at its own
+    border cell, seen from a slowly moving rig: the certified frustum cull of k_deskew_bin must drop exactly the points the
+    reference's FOV gate (tracking.cc:311-314) drops."""
+    rng = np.random.default_rng(seed)
+    t0 = float(rng.uniform(1e3, 6e5))
+    stamp = t0 + 2.0
+    times = np.sort(rng.uniform(stamp - 0.5, stamp, n))
+    side = rng.integers(0, 4, n)
+    along = np.tan(np.deg2rad(rng.uniform(-44.9, 44.9, n)))
+    off = 1.0 + rng.choice([-1.0, 1.0], n) * 10.0 ** rng.uniform(-7, -1, n)
+    x = np.where(side == 0, off, np.where(side == 1, -off, along))
+    y = np.where(side == 2, off, np.where(side == 3, -off, along))
+    d = np.stack([x, y, np.ones(n)], axis=1)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = rng.uniform(2.0, 150.0, n)
+    R_lc = np.eye(3)
+    pts = np.zeros(n, synth.XYZIT)
+    p = d * r[:, None]
+    pts["x"], pts["y"], pts["z"] = p[:, 0].astype(np.float32), p[:, 1].astype(np.float32), p[:, 2].astype(np.float32)
+    pts["time"] = times
+    rate = float(rng.choice([50.0, 200.0]))
+    tt = np.arange(stamp - 0.7, stamp + 0.1, 1.0 / rate)
+    ins = np.zeros(len(tt), synth.INS)
+    ins["time"] = tt
+    ins["state_time"] = tt
+    w = rng.normal(size=3) * rng.choice([0.0, 0.02, 0.3])
+    v = rng.normal(size=3) * rng.choice([0.0, 0.1, 3.0])
+    ang = np.linalg.norm(w) * (tt - stamp)
+    ax = w / max(np.linalg.norm(w), 1e-12)
+    ins["q"][:, :3] = np.sin(0.5 * ang)[:, None] * ax
+    ins["q"][:, 3] = np.cos(0.5 * ang)
+    ins["p"] = v[None, :] * (tt - stamp)[:, None]
+    eye = synth.pose_to_abi(R_lc, np.zeros(3))
+    return dict(pts=pts, ins=ins, stamp=stamp, pose_b_c=eye, pose_c_l=eye)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_frustum_cull_is_exact_on_the_fov_border(oracle, built_lib, seed):
+    s = _edge_band_scenario(100 + seed)
+    c = abi.Context(0)
+    c.set_extrinsics(s["pose_b_c"], s["pose_c_l"], 0.0)
+    c.append_scan(s["pts"])
+    q = np.array([[0.0, 0.0, 1.0]], np.float32)
+    got = c.keyframe(s["stamp"], s["ins"], q)
+    ref1 = oracle.stack_deskew(s["pts"], s["stamp"], s["ins"], s["pose_b_c"], s["pose_c_l"], 0.0, 0.5)
+    ref2 = oracle.range_image(ref1["cloud"])
+    assert got["n_projected"] == ref1["n"]
+    assert 200 < ref2["m"] < len(s["pts"])  # both sides of the border are populated
+    assert got["m"] == ref2["m"], (got["m"], ref2["m"])
+    c.close()

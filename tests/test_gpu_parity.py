@@ -42,15 +42,37 @@ def make_ctx_for(ctx, kf):
 CASES = [
     pytest.param(dict(cfg=1), id="cfg1_avia_240k"),
     pytest.param(dict(cfg=2, pts_per_scan=6000), id="cfg2_avia_small"),
+    pytest.param(dict(cfg=2), id="cfg2_avia_24k_full"),
+    pytest.param(dict(cfg=3), id="cfg3_ouster_x20_full"),  # 2.62 M points in the window, td_b_l = -0.48 s
     pytest.param(dict(cfg=4), id="cfg4_vlp16"),
 ]
+
+_KF_CACHE = {}
+
+
+def make_keyframe(**case):
+    """synth.make_keyframe, cached per case (the full-size Ouster case ray-casts 3 M points)."""
+    key = tuple(sorted(case.items()))
+    if key not in _KF_CACHE:
+        _KF_CACHE[key] = synth.make_keyframe(**case)
+    return _KF_CACHE[key]
+
+
+_REF1_CACHE = {}
+
+
+def cached_stage1(orc, case, kf):
+    key = tuple(sorted(case.items()))
+    if key not in _REF1_CACHE:
+        _REF1_CACHE[key] = oracle_stage1(orc, kf)
+    return _REF1_CACHE[key]
 
 
 @pytest.mark.parametrize("case", CASES)
 def test_stage1_deskew(ctx, oracle, case):
-    kf = synth.make_keyframe(**case)
+    kf = make_keyframe(**case)
     ctx = make_ctx_for(ctx, kf)
-    ref = oracle_stage1(oracle, kf)
+    ref = cached_stage1(oracle, case, kf)
     ctx.append_scan(kf.points)
     n_before = ctx.buffer_info()[0]
     assert n_before == len(kf.points)
@@ -77,8 +99,8 @@ def test_stage1_deskew(ctx, oracle, case):
 
 @pytest.mark.parametrize("case", CASES)
 def test_stage2_range_image_on_oracle_cloud(ctx, oracle, case):
-    kf = synth.make_keyframe(**case)
-    ref1 = oracle_stage1(oracle, kf)
+    kf = make_keyframe(**case)
+    ref1 = cached_stage1(oracle, case, kf)
     ref2 = oracle.range_image(ref1["cloud"])
     st, m, unit, winner = ctx.build_range_image(ref1["cloud"])
     assert st == abi.OK
@@ -101,8 +123,8 @@ def test_stage2_double_libm_mode(oracle, built_lib):
 
 @pytest.mark.parametrize("case", CASES)
 def test_stage3_associate_on_oracle_image(ctx, oracle, case):
-    kf = synth.make_keyframe(**case)
-    ref1 = oracle_stage1(oracle, kf)
+    kf = make_keyframe(**case)
+    ref1 = cached_stage1(oracle, case, kf)
     ref2 = oracle.range_image(ref1["cloud"])
     ref3 = oracle.associate(ref2["unit_sphere"], kf.queries)
     st, m, unit, _ = ctx.build_range_image(ref1["cloud"])
@@ -136,7 +158,7 @@ def test_stage3_associate_on_oracle_image(ctx, oracle, case):
 
 @pytest.mark.parametrize("case", CASES)
 def test_keyframe_end_to_end(ctx, oracle, case):
-    kf = synth.make_keyframe(**case)
+    kf = make_keyframe(**case)
     ctx = make_ctx_for(ctx, kf)
     ref = oracle.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries,
                           kf.shape.stack_interval)
