@@ -120,6 +120,21 @@ int levins_synchronize(levins_ctx *ctx);
 int levins_set_extrinsics(levins_ctx *ctx, const levins_pose *pose_b_c, const levins_pose *pose_c_l, double td_b_l);
 
 /* ------------------------------------------------------------------------------------------------
+ * single-shot pose lookups on the host (no GPU involved): what the estimator itself asks MISC for once per frame
+ * (le_vins.cc:364).  The per-point use of the same functions inside the deskew loop (le_vins.cc:455) is what the kernels
+ * replace; these four share their arithmetic (one source, compiled for host and device).
+ * ------------------------------------------------------------------------------------------------ */
+/* MISC::getInsWindowIndex (misc.cc:25-60): i with time[i-1] <= t < time[i]; 0 when the window is empty, t < time[0] or
+ * t >= time[n-1], or when no bracketing pair exists. */
+size_t levins_ins_window_index(const levins_ins_sample *window, size_t n, double time);
+/* MISC::statePoseInterpolation (misc.cc:80-95): out->{state_time, p, q} between two samples; out->time = midtime. */
+void levins_state_interpolate(const levins_ins_sample *s0, const levins_ins_sample *s1, double midtime, levins_ins_sample *out);
+/* MISC::stateToPoseWithExtrinsic (misc.cc:97-103) */
+void levins_state_to_pose(const levins_ins_sample *state, const levins_pose *pose_ext, levins_pose *out);
+/* MISC::getPoseFromInsWindow (misc.cc:62-78): returns 1 when interpolated, 0 when the newest state was used. */
+int levins_pose_at(const levins_ins_sample *window, size_t n, const levins_pose *pose_ext, double time, levins_pose *out);
+
+/* ------------------------------------------------------------------------------------------------
  * streaming API -- one keyframe at a time, host buffers in and out
  * ------------------------------------------------------------------------------------------------ */
 
@@ -134,6 +149,13 @@ int levins_append_scan(levins_ctx *ctx, const levins_point_xyzit *points, size_t
  * costs ~80 us per 24 000 points.  Typical use: allocate two or three scan-sized buffers once and let the converter
  * write PointXYZIT records into them in turn. */
 int levins_alloc_host(size_t bytes, void **out);
+/* levins_append_scan returns before the device has read the caller's buffer when that buffer is page-locked (the copy is
+ * ordered on the context's stream behind whatever is queued there).  A buffer may be overwritten again once
+ * levins_append_wait() has returned (it waits for the copies of the most recent levins_append_scan), or after any call that
+ * synchronises the context (levins_keyframe, levins_stack_deskew, levins_synchronize).  Rotating two or three buffers and
+ * waiting before re-filling the oldest keeps the converter and the copy overlapped.  Scans in pageable memory are staged by
+ * the driver before the call returns and need no wait. */
+int levins_append_wait(levins_ctx *ctx);
 int levins_free_host(void *p);
 
 /* Driver records straight into the ring: LidarConverter::{livox,velodyne,ouster,hesai}PointCloudConvertion

@@ -104,30 +104,30 @@ static_assert(sizeof(KfState) % 16 == 0 && sizeof(KfState) <= 128, "KfState is c
 // ------------------------------------------------------------------------------------------------
 // small algebra (column-major 3x3 like Eigen), mirrored summation order ((a0 b0 + a1 b1) + a2 b2)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void m3_mul_v(const double* R, const double* x, double* y) {
+__host__ __device__ __forceinline__ void m3_mul_v(const double* R, const double* x, double* y) {
 #pragma unroll
     for (int i = 0; i < 3; i++) y[i] = (R[i] * x[0] + R[3 + i] * x[1]) + R[6 + i] * x[2];
 }
-__device__ __forceinline__ void m3t_mul_v(const double* R, const double* x, double* y) {
+__host__ __device__ __forceinline__ void m3t_mul_v(const double* R, const double* x, double* y) {
 #pragma unroll
     for (int i = 0; i < 3; i++) y[i] = (R[3 * i] * x[0] + R[3 * i + 1] * x[1]) + R[3 * i + 2] * x[2];
 }
-__device__ __forceinline__ void m3_mul_m(const double* A, const double* B, double* C) {
+__host__ __device__ __forceinline__ void m3_mul_m(const double* A, const double* B, double* C) {
 #pragma unroll
     for (int j = 0; j < 3; j++)
 #pragma unroll
         for (int i = 0; i < 3; i++) C[3 * j + i] = (A[i] * B[3 * j] + A[3 + i] * B[3 * j + 1]) + A[6 + i] * B[3 * j + 2];
 }
-__device__ __forceinline__ void m3t_mul_m(const double* A, const double* B, double* C) {
+__host__ __device__ __forceinline__ void m3t_mul_m(const double* A, const double* B, double* C) {
 #pragma unroll
     for (int j = 0; j < 3; j++)
 #pragma unroll
         for (int i = 0; i < 3; i++)
             C[3 * j + i] = (A[3 * i] * B[3 * j] + A[3 * i + 1] * B[3 * j + 1]) + A[3 * i + 2] * B[3 * j + 2];
 }
-__device__ __forceinline__ double v3_dot(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+__host__ __device__ __forceinline__ double v3_dot(const double* a, const double* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
 
-__device__ __forceinline__ void quat_mul(const double* a, const double* b, double* r) {
+__host__ __device__ __forceinline__ void quat_mul(const double* a, const double* b, double* r) {
     const double ax = a[0], ay = a[1], az = a[2], aw = a[3];
     const double bx = b[0], by = b[1], bz = b[2], bw = b[3];
     r[3] = aw * bw - ax * bx - ay * by - az * bz;
@@ -135,8 +135,8 @@ __device__ __forceinline__ void quat_mul(const double* a, const double* b, doubl
     r[1] = aw * by + ay * bw + az * bx - ax * bz;
     r[2] = aw * bz + az * bw + ax * by - ay * bx;
 }
-__device__ __forceinline__ double quat_sqnorm(const double* q) { return ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]; }
-__device__ __forceinline__ void quat_inverse(const double* q, double* r) {
+__host__ __device__ __forceinline__ double quat_sqnorm(const double* q) { return ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3]; }
+__host__ __device__ __forceinline__ void quat_inverse(const double* q, double* r) {
     const double n2 = quat_sqnorm(q);
     if (n2 > 0) {
         r[0] = -q[0] / n2;
@@ -147,7 +147,7 @@ __device__ __forceinline__ void quat_inverse(const double* q, double* r) {
         r[0] = r[1] = r[2] = r[3] = 0;
     }
 }
-__device__ __forceinline__ void quat_normalize(double* q) {
+__host__ __device__ __forceinline__ void quat_normalize(double* q) {
     const double z = quat_sqnorm(q);
     if (z > 0) {
         const double s = sqrt(z);
@@ -158,7 +158,7 @@ __device__ __forceinline__ void quat_normalize(double* q) {
     }
 }
 // Eigen toRotationMatrix, column-major output
-__device__ __forceinline__ void quat_to_matrix(const double* q, double* R) {
+__host__ __device__ __forceinline__ void quat_to_matrix(const double* q, double* R) {
     const double x = q[0], y = q[1], z = q[2], w = q[3];
     const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
     const double twx = tx * w, twy = ty * w, twz = tz * w;
@@ -176,7 +176,7 @@ __device__ __forceinline__ void quat_to_matrix(const double* q, double* R) {
 }
 
 // Eigen::AngleAxisd(quaternion) (rotation.cc:65-68): angle and unit axis
-__device__ __forceinline__ void quat_to_angle_axis(const double* q, double& angle, double* axis) {
+__host__ __device__ __forceinline__ void quat_to_angle_axis(const double* q, double& angle, double* axis) {
     double n = sqrt(v3_dot(q, q));
     if (n < DBL_EPSILON) {
         const double m = fmax(fabs(q[0]), fmax(fabs(q[1]), fabs(q[2])));
@@ -202,7 +202,7 @@ __device__ __forceinline__ void quat_to_angle_axis(const double* q, double& angl
 }
 
 // rotation.cc:59-63
-__device__ __forceinline__ void rotvec_to_quat(const double* rvec, double* q) {
+__host__ __device__ __forceinline__ void rotvec_to_quat(const double* rvec, double* q) {
     const double z = v3_dot(rvec, rvec);
     const double angle = sqrt(z);
     double vec[3] = {rvec[0], rvec[1], rvec[2]};
@@ -221,9 +221,8 @@ __device__ __forceinline__ void rotvec_to_quat(const double* rvec, double* q) {
     q[2] = sn * vec[2];
 }
 
-// misc.cc:80-95 then 97-103, reference operation order (used once per keyframe for the pose at `stamp`)
-__device__ inline void interpolate_pose(const InsSample& s0, const InsSample& s1, double midtime, const double* Rbc,
-                                        const double* tbc, double* R, double* t) {
+// misc.cc:80-95: interpolated state (p, q) between two samples, reference operation order
+__host__ __device__ inline void interpolate_state(const InsSample& s0, const InsSample& s1, double midtime, double* p, double* q) {
     double dp[3] = {s1.p[0] - s0.p[0], s1.p[1] - s0.p[1], s1.p[2] - s0.p[2]};
     double q1inv[4], dq[4], rvec[3], axis[3], angle;
     quat_inverse(s1.q, q1inv);
@@ -237,27 +236,34 @@ __device__ inline void interpolate_pose(const InsSample& s0, const InsSample& s1
     rvec[1] = rvec[1] * scale;
     rvec[2] = rvec[2] * scale;
     rotvec_to_quat(rvec, dq);
-    double p[3] = {s0.p[0] + dp[0] * scale, s0.p[1] + dp[1] * scale, s0.p[2] + dp[2] * scale};
-    double dqinv[4], q[4];
+    p[0] = s0.p[0] + dp[0] * scale;
+    p[1] = s0.p[1] + dp[1] * scale;
+    p[2] = s0.p[2] + dp[2] * scale;
+    double dqinv[4];
     quat_inverse(dq, dqinv);
     quat_mul(s0.q, dqinv, q);
     quat_normalize(q);
+}
+// misc.cc:97-103: pose of the sensor `ext` rides on the body state (p, q)
+__host__ __device__ inline void pose_with_extrinsic(const double* p, const double* q, const double* Rext, const double* text, double* R,
+                                                    double* t) {
     double Rq[9], Rt[3];
     quat_to_matrix(q, Rq);
-    m3_mul_v(Rq, tbc, Rt);
+    m3_mul_v(Rq, text, Rt);
     t[0] = p[0] + Rt[0];
     t[1] = p[1] + Rt[1];
     t[2] = p[2] + Rt[2];
-    m3_mul_m(Rq, Rbc, R);
+    m3_mul_m(Rq, Rext, R);
 }
-__device__ inline void state_pose(const InsSample& s, const double* Rbc, const double* tbc, double* R, double* t) {
-    double Rq[9], Rt[3];
-    quat_to_matrix(s.q, Rq);
-    m3_mul_v(Rq, tbc, Rt);
-    t[0] = s.p[0] + Rt[0];
-    t[1] = s.p[1] + Rt[1];
-    t[2] = s.p[2] + Rt[2];
-    m3_mul_m(Rq, Rbc, R);
+// misc.cc:80-95 then 97-103 (used once per keyframe for the pose at `stamp`)
+__host__ __device__ inline void interpolate_pose(const InsSample& s0, const InsSample& s1, double midtime, const double* Rbc,
+                                        const double* tbc, double* R, double* t) {
+    double p[3], q[4];
+    interpolate_state(s0, s1, midtime, p, q);
+    pose_with_extrinsic(p, q, Rbc, tbc, R, t);
+}
+__host__ __device__ inline void state_pose(const InsSample& s, const double* Rbc, const double* tbc, double* R, double* t) {
+    pose_with_extrinsic(s.p, s.q, Rbc, tbc, R, t);
 }
 
 // ------------------------------------------------------------------------------------------------

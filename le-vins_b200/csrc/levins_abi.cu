@@ -57,6 +57,7 @@ struct levins_ctx {
     bool deskew_attr_set = false;
     cudaStream_t side = nullptr; // k_count_cells runs here, overlapped with the latency-bound k_associate
     cudaEvent_t ev_binned = nullptr, ev_counted = nullptr;
+    cudaEvent_t ev_append = nullptr; // recorded after the host->device copies of the latest levins_append_scan / levins_append_raw
 
     // ---- streaming state ----
     DevBuf ring;      // PointXYZIT x cfg.max_points
@@ -277,6 +278,15 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     if (!ins || n_ins == 0) return fail(ctx, LEVINS_ERR_ARG, "empty INS window");
     if (n_ins > ctx->cfg.max_ins) return fail(ctx, LEVINS_ERR_CAPACITY, "INS window larger than config.max_ins");
     if (!ctx->ring.p || ctx->ring_count_ub == 0) return LEVINS_EMPTY; // le_vins.cc:378: lidar_point_buffer_.empty()
+    // everything that can refuse the call comes before k_prepare, which pops the ring (shared state)
+    const size_t n_ub = ctx->ring_count_ub;
+    if (n_ub >= MAX_POINTS_PER_KEYFRAME) return fail(ctx, LEVINS_ERR_CAPACITY, "more than 2^25 points in one keyframe window");
+    if (write_cloud) CU(ctx->s_cloud.ensure(n_ub * sizeof(PointXYZI)));
+    DeskewArgs da{};
+    {
+        int r = size_chunks(ctx, da, n_ub, 1);
+        if (r) return r;
+    }
     char* pin = reinterpret_cast<char*>(ctx->pinned);
     memcpy(pin + ctx->pin_ins(), ins, n_ins * sizeof(InsSample));
     CU(cudaMemcpyAsync(ctx->s_ins.p, pin + ctx->pin_ins(), n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
@@ -303,14 +313,10 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     ctx->launches++;
     CU(cudaGetLastError());
 
-    const size_t n_ub = ctx->ring_count_ub;
-    if (n_ub >= MAX_POINTS_PER_KEYFRAME) return fail(ctx, LEVINS_ERR_CAPACITY, "more than 2^25 points in one keyframe window");
-    if (write_cloud) CU(ctx->s_cloud.ensure(n_ub * sizeof(PointXYZI)));
     {
         int r = next_gen(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS, &ctx->s_gen);
         if (r) return r;
     }
-    DeskewArgs da{};
     da.kfs = ctx->s_kf.as<KfState>();
     da.pts = ctx->ring.as<PointXYZIT>();
     da.pts_cap = ctx->cfg.max_points;
@@ -483,6 +489,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev_binned) cudaEventDestroy(ctx->ev_binned);
     if (ctx->ev_counted) cudaEventDestroy(ctx->ev_counted);
+    if (ctx->ev_append) cudaEventDestroy(ctx->ev_append);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -529,6 +536,56 @@ extern "C" int levins_set_profiling(levins_ctx* ctx, int enabled) {
 extern "C" uint64_t levins_launch_count(const levins_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 // =================================================================================================
+// single-shot pose lookups (host): the same functions k_prepare runs on the device (device_math.cuh)
+// =================================================================================================
+extern "C" size_t levins_ins_window_index(const levins_ins_sample* w, size_t n, double time) {
+    if (!w || n < 2 || w[0].time > time || w[n - 1].time <= time) return 0; // misc.cc:28-30
+    // near-uniform sampling: guess from the mean spacing, fix up by bisection over what is left
+    size_t lo = 1, hi = n - 1;
+    size_t g = 1 + (size_t) ((time - w[0].time) * ((double) (n - 1) / (w[n - 1].time - w[0].time)));
+    g = std::min(std::max(g, lo), hi);
+    for (int it = 0; it < 80 && lo <= hi; it++) {
+        if (time < w[g - 1].time) {
+            hi = g - 1;
+            g = it < 2 ? g - 1 : (lo + hi) / 2;
+        } else if (time >= w[g].time) {
+            lo = g + 1;
+            g = it < 2 ? g + 1 : (lo + hi) / 2;
+        } else {
+            return g;
+        }
+        if (lo > hi) break;
+        g = std::min(std::max(g, lo), hi);
+    }
+    return 0;
+}
+
+extern "C" void levins_state_interpolate(const levins_ins_sample* s0, const levins_ins_sample* s1, double midtime, levins_ins_sample* out) {
+    if (!s0 || !s1 || !out) return;
+    static_assert(sizeof(levins_ins_sample) == sizeof(InsSample), "INS sample layout");
+    interpolate_state(*reinterpret_cast<const InsSample*>(s0), *reinterpret_cast<const InsSample*>(s1), midtime, out->p, out->q);
+    out->time = midtime;
+    out->state_time = midtime;
+}
+
+extern "C" void levins_state_to_pose(const levins_ins_sample* state, const levins_pose* ext, levins_pose* out) {
+    if (!state || !ext || !out) return;
+    pose_with_extrinsic(state->p, state->q, ext->R, ext->t, out->R, out->t);
+}
+
+extern "C" int levins_pose_at(const levins_ins_sample* w, size_t n, const levins_pose* ext, double time, levins_pose* out) {
+    if (!w || !n || !ext || !out) return 0;
+    const size_t i = levins_ins_window_index(w, n, time);
+    if (i > 0) {
+        interpolate_pose(*reinterpret_cast<const InsSample*>(w + i - 1), *reinterpret_cast<const InsSample*>(w + i), time, ext->R, ext->t,
+                         out->R, out->t);
+        return 1;
+    }
+    state_pose(*reinterpret_cast<const InsSample*>(w + n - 1), ext->R, ext->t, out->R, out->t); // misc.cc:74-77
+    return 0;
+}
+
+// =================================================================================================
 // streaming API
 // =================================================================================================
 extern "C" int levins_append_scan(levins_ctx* ctx, const levins_point_xyzit* points, size_t n) {
@@ -554,6 +611,8 @@ extern "C" int levins_append_scan(levins_ctx* ctx, const levins_point_xyzit* poi
     CU(cudaMemcpyAsync(base + tail, points, first * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
     if (first < n)
         CU(cudaMemcpyAsync(base, points + first, (n - first) * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->ev_append) CU(cudaEventCreateWithFlags(&ctx->ev_append, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_append, ctx->stream)); // levins_append_wait(): the caller's buffer has been read
     ctx->ring_tail = (tail + n) % cap;
     ctx->ring_count_ub += n;
     const double reserved = ctx->cfg.reserved_buffer_length + ctx->cfg.stack_interval * 2; // le_vins.cc:156
@@ -572,13 +631,14 @@ extern "C" int levins_append_raw(levins_ctx* ctx, const levins_raw_format* fmt, 
     if (n_appended) *n_appended = 0;
     if (t_start) *t_start = DBL_MAX; // lidar_converter.cc:50-51
     if (t_end) *t_end = 0;
-    const uint32_t need = fmt->kind == 1 ? 4u : (fmt->time_kind == 3 ? 8u : 4u);
-    const uint32_t offs[] = {fmt->off_x + 4, fmt->off_y + 4, fmt->off_z + 4, fmt->off_intensity + (fmt->kind == 1 ? 1u : 4u),
-                             fmt->off_time + need, fmt->kind == 1 ? fmt->off_ring + 1 : 0u, fmt->kind == 1 ? fmt->off_tag + 1 : 0u};
     if ((fmt->kind != 1 && fmt->kind != 2) || fmt->point_step == 0 || (fmt->kind == 2 && (fmt->time_kind < 1 || fmt->time_kind > 3)))
         return fail(ctx, LEVINS_ERR_ARG, "unknown record format");
-    for (uint32_t o : offs)
-        if (o > fmt->point_step) return fail(ctx, LEVINS_ERR_ARG, "field beyond point_step");
+    const uint64_t need = fmt->kind == 1 ? 4u : (fmt->time_kind == 3 ? 8u : 4u);
+    const uint64_t ends[] = {(uint64_t) fmt->off_x + 4, (uint64_t) fmt->off_y + 4, (uint64_t) fmt->off_z + 4,
+                             (uint64_t) fmt->off_intensity + (fmt->kind == 1 ? 1u : 4u), (uint64_t) fmt->off_time + need,
+                             fmt->kind == 1 ? (uint64_t) fmt->off_ring + 1 : 0u, fmt->kind == 1 ? (uint64_t) fmt->off_tag + 1 : 0u};
+    for (uint64_t e : ends) // 64-bit sums: an offset near UINT32_MAX must not wrap past the check
+        if (e > fmt->point_step) return fail(ctx, LEVINS_ERR_ARG, "field beyond point_step");
     if (n == 0) return LEVINS_OK;
     if (n > 0x7fffffffull) return fail(ctx, LEVINS_ERR_ARG, "scan too large");
     int r = ensure_ring(ctx);
@@ -644,6 +704,19 @@ extern "C" int levins_append_raw(levins_ctx* ctx, const levins_raw_format* fmt, 
     if (n_appended) *n_appended = (size_t) res.count;
     if (t_start) *t_start = res.start;
     if (t_end) *t_end = res.end;
+    return LEVINS_OK;
+}
+
+extern "C" int levins_append_wait(levins_ctx* ctx) {
+    if (!ctx) return LEVINS_ERR_ARG;
+    cudaEvent_t ev;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ev = ctx->ev_append;
+    }
+    if (!ev) return LEVINS_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ev));
     return LEVINS_OK;
 }
 

@@ -1,96 +1,82 @@
-// MISC pose lookup of the reference (le_vins/common/misc.h:35-41, misc.cc:25-103) and the two Rotation helpers it uses
-// (rotation.cc:59-68).  Same names, signatures and semantics.  These are the estimator's single-shot host calls
-// (e.g. le_vins.cc:364); the per-point use inside the deskew loop (le_vins.cc:455) is what k_deskew_bin replaces.
+// MISC pose lookup of the reference (le_vins/common/misc.h:35-41): same names, signatures and return conventions, bodies in
+// liblevins_b200.so.  These are the estimator's single-shot host calls (e.g. le_vins.cc:364); the library evaluates them with
+// the same source its kernels use for the per-point case (csrc/device_math.cuh: interpolate_state / pose_with_extrinsic,
+// compiled for host and device), so the frame pose the estimator sees and the keyframe pose inside k_prepare are one
+// function.  Nothing is computed in this header.
 #ifndef LEVINS_HOST_MISC_H
 #define LEVINS_HOST_MISC_H
 
-#include <cfloat>
-#include <cmath>
+#include <cstring>
 #include <deque>
 #include <utility>
+#include <vector>
 
 #include "common/types.h"
+#include "levins/abi.h"
 
-class Rotation {
-public:
-    static Quaterniond rotvec2quaternion(const Vector3d &rotvec) { // rotation.cc:59-63
-        const double angle = rotvec.norm();
-        const Vector3d vec = rotvec.normalized();
-        const double ha = 0.5 * angle;
-        const double s = std::sin(ha);
-        return Quaterniond(std::cos(ha), s * vec[0], s * vec[1], s * vec[2]);
-    }
-    static Vector3d quaternion2vector(const Quaterniond &q) { // rotation.cc:65-68 (Eigen::AngleAxisd(q))
-        Vector3d v(q.x(), q.y(), q.z());
-        double n = v.norm();
-        if (n < DBL_EPSILON) {
-            const double m = std::fmax(std::fabs(v[0]), std::fmax(std::fabs(v[1]), std::fabs(v[2])));
-            n = m > 0 ? m * Vector3d(v[0] / m, v[1] / m, v[2] / m).norm() : 0.0;
-        }
-        if (n != 0) {
-            const double angle = 2 * std::atan2(n, std::fabs(q.w()));
-            if (q.w() < 0) n = -n;
-            return Vector3d(v[0] / n, v[1] / n, v[2] / n) * angle;
-        }
-        return Vector3d(0, 0, 0);
-    }
-};
+namespace levins_host {
+
+inline void to_abi(const Pose &pose, levins_pose &out) {
+    std::memcpy(out.R, pose.R.data(), sizeof(out.R));
+    std::memcpy(out.t, pose.t.data(), sizeof(out.t));
+}
+inline Pose from_abi(const levins_pose &in) {
+    Pose pose;
+    std::memcpy(pose.R.data(), in.R, sizeof(in.R));
+    std::memcpy(pose.t.data(), in.t, sizeof(in.t));
+    return pose;
+}
+inline void to_abi(const IMU &imu, const IntegrationState &state, levins_ins_sample &s) {
+    s.time = imu.time;
+    s.state_time = state.time;
+    std::memcpy(s.p, state.p.data(), sizeof(s.p));
+    std::memcpy(s.q, state.q.coeffs(), sizeof(s.q));
+}
+inline void to_abi(const std::deque<std::pair<IMU, IntegrationState>> &window, std::vector<levins_ins_sample> &out) {
+    out.resize(window.size());
+    for (size_t i = 0; i < window.size(); i++) to_abi(window[i].first, window[i].second, out[i]);
+}
+
+} // namespace levins_host
 
 class MISC {
 public:
     typedef std::deque<std::pair<IMU, IntegrationState>> InsWindow;
 
-    static size_t getInsWindowIndex(const InsWindow &window, double time) { // misc.cc:25-60
-        if (window.empty() || (window.front().first.time > time) || (window.back().first.time <= time)) return 0;
-        size_t index = 0, sta = 0, end = window.size();
-        int counts = 0;
-        while (true) {
-            const size_t mid = (sta + end) / 2;
-            const double first = window[mid - 1].first.time, second = window[mid].first.time;
-            if ((first <= time) && (time < second)) {
-                index = mid;
-                break;
-            } else if (first > time) {
-                end = mid;
-            } else if (second <= time) {
-                sta = mid;
-            }
-            if (counts++ > 15) break;
-        }
-        return index;
+    static size_t getInsWindowIndex(const InsWindow &window, double time) {
+        std::vector<levins_ins_sample> w;
+        levins_host::to_abi(window, w);
+        return levins_ins_window_index(w.data(), w.size(), time);
     }
 
     static void statePoseInterpolation(const IntegrationState &state0, const IntegrationState &state1, double midtime,
-                                       IntegrationState &state) { // misc.cc:80-95
-        const Vector3d dp = state1.p - state0.p;
-        Quaterniond dq = state1.q.inverse() * state0.q;
-        Vector3d rvec = Rotation::quaternion2vector(dq);
-        const double scale = (midtime - state0.time) / (state1.time - state0.time);
-        rvec = rvec * scale;
-        dq = Rotation::rotvec2quaternion(rvec);
-        state.time = midtime;
-        state.p = state0.p + dp * scale;
-        state.q = state0.q * dq.inverse();
-        state.q.normalize();
+                                       IntegrationState &state) {
+        levins_ins_sample s0, s1, out;
+        levins_host::to_abi(IMU(), state0, s0);
+        levins_host::to_abi(IMU(), state1, s1);
+        levins_state_interpolate(&s0, &s1, midtime, &out);
+        state.time = out.state_time;
+        state.p = Vector3d(out.p[0], out.p[1], out.p[2]);
+        state.q = Quaterniond(out.q);
     }
 
-    static Pose stateToPoseWithExtrinsic(const IntegrationState &state, const Pose &pose_ext) { // misc.cc:97-103
-        Pose pose;
-        pose.t = state.p + state.q.toRotationMatrix() * pose_ext.t;
-        pose.R = state.q.toRotationMatrix() * pose_ext.R;
-        return pose;
+    static Pose stateToPoseWithExtrinsic(const IntegrationState &state, const Pose &pose_ext) {
+        levins_ins_sample s;
+        levins_pose ext, out;
+        levins_host::to_abi(IMU(), state, s);
+        levins_host::to_abi(pose_ext, ext);
+        levins_state_to_pose(&s, &ext, &out);
+        return levins_host::from_abi(out);
     }
 
-    static bool getPoseFromInsWindow(const InsWindow &window, const Pose &pose_ext, double time, Pose &pose) { // misc.cc:62-78
-        const size_t index = getInsWindowIndex(window, time);
-        IntegrationState state;
-        if (index > 0) {
-            statePoseInterpolation(window[index - 1].second, window[index].second, time, state);
-            pose = stateToPoseWithExtrinsic(state, pose_ext);
-            return true;
-        }
-        pose = stateToPoseWithExtrinsic(window.back().second, pose_ext);
-        return false;
+    static bool getPoseFromInsWindow(const InsWindow &window, const Pose &pose_ext, double time, Pose &pose) {
+        std::vector<levins_ins_sample> w;
+        levins_host::to_abi(window, w);
+        levins_pose ext, out;
+        levins_host::to_abi(pose_ext, ext);
+        const int interpolated = levins_pose_at(w.data(), w.size(), &ext, time, &out);
+        pose = levins_host::from_abi(out);
+        return interpolated != 0;
     }
 };
 

@@ -31,22 +31,6 @@ inline ResidentCloud &resident_cloud() {
     return r;
 }
 
-inline void to_abi(const Pose &pose, levins_pose &out) {
-    std::memcpy(out.R, pose.R.data(), sizeof(out.R));
-    std::memcpy(out.t, pose.t.data(), sizeof(out.t));
-}
-
-inline void to_abi(const MISC::InsWindow &window, std::vector<levins_ins_sample> &out) {
-    out.resize(window.size());
-    for (size_t i = 0; i < window.size(); i++) {
-        levins_ins_sample &s = out[i];
-        s.time = window[i].first.time;
-        s.state_time = window[i].second.time;
-        std::memcpy(s.p, window[i].second.p.data(), sizeof(s.p));
-        std::memcpy(s.q, window[i].second.q.coeffs(), sizeof(s.q));
-    }
-}
-
 class VinsLidarPath {
 public:
     static constexpr double LIDAR_DEPTH_POINT_STACK_INTERVAL = 0.5; // le_vins.h:130

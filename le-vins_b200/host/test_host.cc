@@ -83,6 +83,31 @@ int main(int argc, char **argv) {
                 num_associated = tracking.depthAssociationReference(camera, px, std::vector<uint8_t>(), frame_pose, associated);
             }
         }
+        // the drivers' skip branches: features whose reference frame is not frame_ref_ (tracking.cc:401-404) and map points
+        // that are already depth associated (tracking.cc:513-516) are not evaluated
+        if (projected) {
+            std::vector<visual::Point2f> px(pixels.size() / 2);
+            for (size_t k = 0; k < px.size(); k++) px[k] = {pixels[2 * k], pixels[2 * k + 1]};
+            std::vector<uint8_t> not_current_ref(px.size()), already(px.size());
+            for (size_t k = 0; k < px.size(); k++) {
+                not_current_ref[k] = (k % 3 == 0);
+                already[k] = (k % 4 == 1);
+            }
+            auto dump = [&](const char *name, const std::vector<visual::DepthAssociated> &list, int count) {
+                std::vector<double> o{(double) count};
+                for (const auto &a : list) {
+                    o.push_back((double) a.index);
+                    o.push_back(a.depth);
+                    o.push_back((double) a.type);
+                }
+                write_bin(dir + "/" + name, o);
+            };
+            std::vector<visual::DepthAssociated> a_ref, a_map;
+            const int n_ref = tracking.depthAssociationReference(camera, px, not_current_ref, frame_pose, a_ref);
+            dump("assoc_ref_skip.bin", a_ref, n_ref);
+            const int n_map = tracking.depthAssociationMapPoint(camera, px, already, frame_pose, a_map);
+            dump("assoc_map_skip.bin", a_map, n_map);
+        }
         // single-query form on the first pixel (in-place semantics of tracking.cc:626-629)
         PointType single;
         int single_type = -1;
@@ -136,6 +161,30 @@ int main(int argc, char **argv) {
                 write_bin(dir + "/cloud_raw.bin", from_records.points);
                 std::ofstream s2(dir + "/summary_raw.txt");
                 s2 << "stacked " << ok << "\nappended " << total << "\nn " << from_records.size() << "\n";
+            }
+        }
+        // the three PointCloud2 drivers through LidarConverter::*PointCloudAppend (conversion on the device)
+        {
+            std::ifstream probe(dir + "/raw_meta.bin");
+            if (probe) {
+                const auto rm = read_bin<double>(dir + "/raw_meta.bin"); // stamp, nearest, farthest, to_gps, ring lines
+                LidarConverter ring(10.0, (int) rm[4], rm[1], rm[2]);
+                std::vector<double> res;
+                auto run = [&](auto fn) {
+                    levins_host::check(levins_buffer_clear(levins_host::context()), "buffer_clear");
+                    double start = 0, end = 0;
+                    const size_t n = fn(start, end);
+                    size_t in_ring = 0;
+                    levins_host::check(levins_buffer_info(levins_host::context(), &in_ring, nullptr, nullptr), "buffer_info");
+                    res.insert(res.end(), {(double) n, (double) in_ring, start, end});
+                };
+                const auto vel = read_bin<VelodynePoint>(dir + "/raw_velodyne.bin");
+                run([&](double &s0, double &e0) { return ring.velodynePointCloudAppend(vel, rm[0], s0, e0, rm[3] != 0); });
+                const auto ous = read_bin<OusterPoint>(dir + "/raw_ouster.bin");
+                run([&](double &s0, double &e0) { return ring.ousterPointCloudAppend(ous, rm[0], s0, e0, rm[3] != 0); });
+                const auto hes = read_bin<HesaiPoint>(dir + "/raw_hesai.bin");
+                run([&](double &s0, double &e0) { return ring.hesaiPointCloudAppend(hes, rm[0], s0, e0, rm[3] != 0); });
+                write_bin(dir + "/append_drivers.bin", res);
             }
         }
         levins_destroy(levins_host::context());

@@ -1,4 +1,4 @@
-// CPU-only driver for the header-only part of the host mirror (no GPU needed): MISC pose lookup, the single-point
+// CPU-only driver for the part of the host mirror that needs no GPU: MISC pose lookup (host exports of the library), the single-point
 // PointCloudCommon statics, planeEstimation, pointToPlaneStd, Camera.  tests/test_host_mirror.py feeds it binary vectors
 // and compares every output with the oracle.
 //   test_host_cpu <dir>   reads ins.bin times.bin ext.bin pts.bin   writes poses.bin proj.bin plane.bin std.bin cam.bin
@@ -9,7 +9,6 @@
 
 #include "common/misc.h"
 #include "lidar/pointcloud.h"
-#include "ros/lidar_converter.h"
 #include "visual/camera.h"
 #include "visual/visual_mappoint.h"
 
@@ -113,38 +112,5 @@ int main(int argc, char **argv) {
     }
     write_bin(dir + "/cam.bin", cam);
 
-    // LidarConverter (ROS/lidar/lidar_converter.cc): the four drivers' records -> PointXYZIT, on the CPU
-    {
-        std::ifstream probe(dir + "/raw_meta.bin");
-        if (probe) {
-            const auto rm = read_bin<double>(dir + "/raw_meta.bin"); // stamp, nearest, farthest, to_gps, livox lines, ring lines
-            const auto tb = read_bin<uint64_t>(dir + "/raw_timebase.bin");
-            const bool gps = rm[3] != 0;
-            std::vector<double> se;
-            auto run = [&](const char *name, auto fn) {
-                PointCloudCustomPtr cloud(new PointCloudCustom);
-                double start = 0, end = 0;
-                fn(cloud, start, end);
-                write_bin(dir + "/conv_" + name + ".bin", cloud->points);
-                se.push_back(start);
-                se.push_back(end);
-            };
-            LidarConverter livox(10.0, (int) rm[4], rm[1], rm[2]), ring(10.0, (int) rm[5], rm[1], rm[2]);
-            livox_ros_driver::CustomMsg msg;
-            msg.timebase_ns = tb[0];
-            msg.points = read_bin<livox_ros_driver::CustomPoint>(dir + "/raw_livox.bin");
-            run("livox", [&](PointCloudCustomPtr &c, double &s0, double &e0) {
-                PointCloudCustomPtr ds(new PointCloudCustom);
-                livox.livoxPointCloudConvertion(msg, c, ds, s0, e0, gps);
-            });
-            const auto vel = read_bin<VelodynePoint>(dir + "/raw_velodyne.bin");
-            run("velodyne", [&](PointCloudCustomPtr &c, double &s0, double &e0) { ring.velodynePointCloudConvertion(vel, rm[0], c, s0, e0, gps); });
-            const auto ous = read_bin<OusterPoint>(dir + "/raw_ouster.bin");
-            run("ouster", [&](PointCloudCustomPtr &c, double &s0, double &e0) { ring.ousterPointCloudConvertion(ous, rm[0], c, s0, e0, gps); });
-            const auto hes = read_bin<HesaiPoint>(dir + "/raw_hesai.bin");
-            run("hesai", [&](PointCloudCustomPtr &c, double &s0, double &e0) { ring.hesaiPointCloudConvertion(hes, rm[0], c, s0, e0, gps); });
-            write_bin(dir + "/conv_se.bin", se);
-        }
-    }
     return 0;
 }

@@ -28,6 +28,7 @@ EXPORTS = [
     "levins_keyframe", "levins_point_cloud_projection", "levins_batch_upload", "levins_batch_run",
     "levins_batch_download", "levins_batch_set_wave", "levins_set_profiling", "levins_batch_kernel_ms",
     "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host", "levins_append_raw",
+    "levins_append_wait", "levins_ins_window_index", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
 ]
 
 
@@ -68,6 +69,7 @@ def lib():
         for name, args in {
             "levins_set_stream": [vp, vp],
             "levins_synchronize": [vp],
+            "levins_append_wait": [vp],
             "levins_set_extrinsics": [vp, vp, vp, dbl],
             "levins_append_scan": [vp, vp, sz],
             "levins_buffer_info": [vp, vp, vp, vp],
@@ -180,6 +182,9 @@ class Context:
         self._check(L.levins_append_raw(self._h, _p(f), _p(rec), int(n), int(timebase_ns), float(stamp), int(bool(to_gps_time)),
                                         int(scan_line), float(nearest), float(farthest), C.byref(m), C.byref(a), C.byref(b)))
         return m.value, a.value, b.value
+
+    def append_wait(self):
+        self._check(lib().levins_append_wait(self._h))
 
     def buffer_info(self):
         n, a, b = C.c_size_t(0), C.c_double(0), C.c_double(0)

@@ -62,8 +62,24 @@ def test_host_mirror_matches_oracle(oracle, built_lib, tmp_path):
         conv.append(oracle.convert_raw(rawfmt.fmt_livox(), rawfmt.as_bytes(rec), len(rec), tb, 0.0, True, 6, 1.0, 200.0)[0])
     np.concatenate(recs).tofile(tmp_path / "raw_livox.bin")
     np.array(meta, np.uint64).tofile(tmp_path / "raw_timebase.bin")
+    # the three PointCloud2 drivers' records for LidarConverter::{velodyne,ouster,hesai}PointCloudAppend
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_raw_formats import _cases
+
+    cases = {c[0]: c for c in _cases(seed=5, n=20_000)}
+    drv_stamp = cases["velodyne"][4]
+    np.array([drv_stamp, 1.0, 200.0, 1.0, 128], np.float64).tofile(tmp_path / "raw_meta.bin")
+    for name in ("velodyne", "ouster", "hesai"):
+        cases[name][2].tofile(tmp_path / f"raw_{name}.bin")
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    drv = np.fromfile(tmp_path / "append_drivers.bin", np.float64).reshape(3, 4)
+    for i, name in enumerate(("velodyne", "ouster", "hesai")):
+        _, fmt, rec, tb, st, lines = cases[name]
+        want, wst, wen = oracle.convert_raw(fmt, rawfmt.as_bytes(rec), len(rec), tb, st, True, 128, 1.0, 200.0)
+        assert int(drv[i, 0]) == len(want) == int(drv[i, 1]) > 0 and drv[i, 2] == wst and drv[i, 3] == wen, name
     sraw = dict(line.split(" ", 1) for line in open(tmp_path / "summary_raw.txt").read().strip().split("\n"))
     pts_conv = np.concatenate(conv)
     ref_raw = oracle.stack_deskew(pts_conv, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, 0.5)
@@ -85,13 +101,22 @@ def test_host_mirror_matches_oracle(oracle, built_lib, tmp_path):
     R, t = frame_pose[:9].reshape(3, 3).T, frame_pose[9:]
     pw = ref3["xyz_depth"][good, :3].astype(np.float64) @ R.T + t  # cam2world (camera.cc:149-151)
     assert np.allclose(assoc[:, 1:4], pw, rtol=0, atol=1e-9)
+    # skip branches of the two drivers (tracking.cc:401-404, 513-516): skipped features are not evaluated, the rest unchanged
+    idx = np.arange(len(good))
+    for name, skipped in (("assoc_ref_skip.bin", idx % 3 == 0), ("assoc_map_skip.bin", idx % 4 == 1)):
+        o = np.fromfile(tmp_path / name, np.float64)
+        lst = o[1:].reshape(-1, 3)
+        want_idx = np.nonzero(good & ~skipped)[0]
+        assert int(o[0]) == len(want_idx) == len(lst) and 0 < len(want_idx) < int(good.sum()), name
+        assert np.array_equal(lst[:, 0].astype(int), want_idx)
+        assert np.array_equal(lst[:, 1].astype(np.float32), ref3["xyz_depth"][want_idx, 3]) and np.all(lst[:, 2] == 1)
     assert int(summary["single_type"]) == int(ref3["type"][0])
     single = np.array(summary["single"].split(), dtype=np.float32)
     assert np.allclose(single, ref3["xyz_depth"][0], rtol=1e-6)
 
 
 def test_host_mirror_cpu_functions_match_oracle(oracle, built_lib, tmp_path):
-    """Header-only part of the C++ mirror (no GPU): MISC pose lookup, PointCloudCommon single-point statics,
+    """The part of the C++ mirror that needs no GPU: MISC pose lookup (host exports of the library), PointCloudCommon single-point statics,
     planeEstimation, pointToPlaneStd, Camera -- bit-for-bit against the oracle (same operation order, -ffp-contract=off),
     pointToPlaneStd also against an independent numpy restatement."""
     _build()
@@ -173,41 +198,3 @@ def test_host_mirror_cpu_functions_match_oracle(oracle, built_lib, tmp_path):
         assert np.array_equal(cam[k, 3:6], puc)
         assert np.array_equal(cam[k, 6:9], oracle.cam2world(puc, pose_list[k % len(pose_list)]))
         assert bool(cam[k, 9]) == oracle.is_good_depth(pts["z"][k], 1.0)
-
-
-def test_host_mirror_lidar_converter_matches_oracle(oracle, built_lib, tmp_path):
-    """LidarConverter (C++ mirror of ROS/lidar/lidar_converter.cc, CPU loops) on the four drivers' records against the oracle's
-    orc_convert_raw, bit for bit: two independent restatements of the same converter."""
-    import sys
-
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from test_raw_formats import _cases
-
-    from levins import rawfmt
-
-    _build()
-    exe = os.path.join(ROOT, "le-vins_b200", "host", "test_host_cpu")
-    # the driver needs its regular inputs too
-    kf = synth.make_keyframe(2, pts_per_scan=300, n_features=8)
-    d = str(tmp_path)
-    ins = np.concatenate([kf.ins["time"][:, None], kf.ins["state_time"][:, None], kf.ins["p"], kf.ins["q"]], axis=1)
-    ins.astype(np.float64).tofile(os.path.join(d, "ins.bin"))
-    kf.ins["time"][5:15].astype(np.float64).tofile(os.path.join(d, "times.bin"))
-    np.concatenate([kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.intr]).astype(np.float64).tofile(os.path.join(d, "ext.bin"))
-    np.zeros(10, synth.XYZI).tofile(os.path.join(d, "pts.bin"))
-    cases = {c[0]: c for c in _cases(seed=5, n=20_000)}
-    stamp = cases["velodyne"][4]
-    for to_gps in (True, False):
-        np.array([stamp, 1.0, 200.0, float(to_gps), 6, 128], np.float64).tofile(os.path.join(d, "raw_meta.bin"))
-        np.array([cases["livox"][3]], np.uint64).tofile(os.path.join(d, "raw_timebase.bin"))
-        for name in ("livox", "velodyne", "ouster", "hesai"):
-            cases[name][2].tofile(os.path.join(d, f"raw_{name}.bin"))
-        r = subprocess.run([exe, d], capture_output=True, text=True)
-        assert r.returncode == 0, r.stderr
-        se = np.fromfile(os.path.join(d, "conv_se.bin"), np.float64).reshape(4, 2)
-        for i, name in enumerate(("livox", "velodyne", "ouster", "hesai")):
-            _, fmt, rec, tb, st, lines = cases[name]
-            want, wst, wen = oracle.convert_raw(fmt, rawfmt.as_bytes(rec), len(rec), tb, st, to_gps, 6 if name == "livox" else 128, 1.0, 200.0)
-            got = np.fromfile(os.path.join(d, f"conv_{name}.bin"), synth.XYZIT)
-            assert len(got) == len(want) > 0 and got.tobytes() == want.tobytes(), name
-            assert se[i, 0] == wst and se[i, 1] == wen, name
