@@ -266,6 +266,29 @@ def pinned_copy(torch, arr):
     return t, v.view(arr.dtype).reshape(arr.shape)
 
 
+def bind_near_gpu(index):
+    """Pin this process to the cores of the GPU's NUMA node, so that the page-locked host pools it allocates (first touch) and
+    the thread that feeds the copies are local to the GPU's PCIe root.  Does nothing when the topology is not exposed."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
+
+
 def world_from_env(args):
     """World size comes from the launcher (torchrun exports WORLD_SIZE); --gpus must agree with it."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -293,12 +316,19 @@ def run_gpu(args):
     dev = torch.device("cuda", local_rank)
 
     n_kf = args.keyframes
+    bind_near_gpu(local_rank)  # before the page-locked pools are allocated (first touch decides their NUMA node)
     batch = make_workload(synth, n_kf, rank)
     descs = abi.batch_descs(batch)
     F = batch.queries.shape[1]
     q_flat = np.ascontiguousarray(batch.queries.reshape(-1, 3))
+    # The host-side form of the points: packed 16-byte records (x, y, z, u32 nanoseconds after the scan's stamp -- the driver's
+    # own time field).  batch.points becomes what the device reconstructs from them (times = stamp + dt * 1e-9), so the
+    # resident measurement, the e2e measurement and the CPU oracle all see the same values.
+    per = batch.shape.pts_per_scan
+    packed_np, scans, batch.points = abi.pack_points(batch.points, np.arange(len(batch.points) // per) * per, batch.points["time"][::per])
     keep = []
-    t_pts, pts = pinned_copy(torch, batch.points)
+    t_pts, pts = pinned_copy(torch, packed_np)
+    del packed_np
     t_ins, ins = pinned_copy(torch, batch.ins)
     t_q, q = pinned_copy(torch, q_flat)
     keep += [t_pts, t_ins, t_q]
@@ -308,27 +338,35 @@ def run_gpu(args):
     ctx.set_stream(stream.cuda_stream)
     ctx.set_extrinsics(batch.shape.rig.pose_b_c, batch.shape.rig.pose_c_l, batch.shape.rig.td_b_l)
     ctx.batch_set_wave(args.wave)
-    ctx.batch_upload(pts, ins, q, descs)
+    ctx.batch_upload_packed(pts, scans, ins, q, descs)
 
-    # results gathered across ranks at the end of every step (the path's only exchange step)
+    # The path's only exchange step: every rank ends up with the per-feature results of all ranks, through the C ABI.
+    #   peer (default): k_plane stores its results straight into every rank's gathered block over NVLink (CUDA IPC peer
+    #                   memory) and publishes a step counter; no collective is launched
+    #   nccl:           one ncclAllGather per step (levins_gather) on the context's stream
+    # torch.distributed only carries the 64-byte IPC handles / the 128-byte NCCL id between the ranks.
     nq = n_kf * F
     res_host = {"type": np.zeros(nq, np.int8), "xyz_depth": np.zeros((nq, 4), np.float32)}
-    pipe = None
+    comm = None
     if world > 1:
-        from levins.shard import PipelinedGather
-
-        dptr = ctx.batch_result_pointers()
-        assert dptr["type"] == dptr["xyz_depth"] + 16 * nq  # one contiguous block: xyz_depth then type
-        local = abi.device_tensor(torch, dptr["xyz_depth"], (17 * nq,), torch.uint8, local_rank)
-        pipe = PipelinedGather(torch, dist, local, world, dev)
+        if args.gather == "peer":
+            mine = torch.from_numpy(ctx.peer_export(world, nq)).to(dev)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.peer_attach(rank, world, torch.stack(allh).cpu().numpy())
+        else:
+            uid = torch.from_numpy(abi.Context.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(dev)
+            dist.broadcast(uid, 0)
+            comm = ctx.comm_init(uid.cpu().numpy(), world, rank)
+        dist.barrier()
 
     def gather():
-        if pipe is not None:  # one collective for depths + types of all ranks, overlapped with the next step's kernels
-            pipe.submit()
+        if comm is not None:
+            ctx.gather(comm, world)
 
-    def drain():
-        if pipe is not None:
-            pipe.drain()
+    def drain():  # device-side: the stream does not pass this point before every rank's results of the latest step are here
+        if world > 1 and comm is None:
+            ctx.peer_wait()
 
     def barrier():
         if world > 1:
@@ -340,11 +378,11 @@ def run_gpu(args):
         gather()
 
     def step_e2e():
-        ctx.batch_upload(pts, ins, q, descs)
+        ctx.batch_upload_packed(pts, scans, ins, q, descs)
         ctx.batch_run()
         gather()
-        ctx.batch_download(res_host)
         drain()
+        ctx.batch_download(res_host)
 
     def timed(fn, steps):
         barrier()
@@ -365,6 +403,7 @@ def run_gpu(args):
     # ---- device-resident throughput ----
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    drain()
     with ClockSampler(local_rank) as clocks:
         ms_total, launches = timed(step_resident, args.steps)
         # keep the sampler alive over the e2e region too so that short runs still collect samples
@@ -379,7 +418,7 @@ def run_gpu(args):
     n_proj_total = int(out["n_projected"].astype(np.int64).sum())
     pts_per_step = n_proj_total  # per rank
     e2e_value = total_features * e2e_steps / (ms_e2e * 1e-3)
-    h2d = int(pts.nbytes + ins.nbytes + q.nbytes + descs.nbytes)
+    h2d = int(pts.nbytes + scans.nbytes + ins.nbytes + q.nbytes + descs.nbytes)
     d2h = int(res_host["type"].nbytes + res_host["xyz_depth"].nbytes)
 
     # ---- per-kernel time, live, with CUDA events on the launching stream ----
@@ -444,7 +483,9 @@ def run_gpu(args):
             "config": workload_config(batch, n_kf),
             "run": {"points_per_keyframe": int(n_proj_total / n_kf), "wave": args.wave,
                     "cells_per_keyframe": int(out["m"].mean()), "associated_fraction": float((out["type"] == 1).mean()),
-                    "l2": f"inputs larger than L2: {pts.nbytes / 1e6:.0f} MB of points per GPU per step"},
+                    "gather": (args.gather if world > 1 else None),
+                    "l2": f"inputs larger than L2: {batch.points.nbytes / 1e6:.0f} MB of points per GPU per step",
+                    "e2e_input": "packed 16-byte records (x, y, z, u32 ns after the scan stamp), expanded to PointXYZIT on the device"},
             "lidar_pts_per_s": world * pts_per_step * args.steps / (ms_total * 1e-3),
             "keyframes_per_s": world * n_kf * args.steps / (ms_total * 1e-3),
             "p50_keyframe_ms": p50["pageable"] if p50 else None,
@@ -467,6 +508,11 @@ def run_gpu(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
+        if comm is not None:
+            abi.Context.comm_destroy(comm)
+        else:
+            ctx.peer_detach()
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
@@ -585,6 +631,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurement (configs[1] as a resident batch)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="exchange step at N > 1 (both through the C ABI)")
     ap.add_argument("--no-stream", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

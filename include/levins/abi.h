@@ -236,10 +236,28 @@ typedef struct levins_keyframe_desc {
     double stamp;
 } levins_keyframe_desc;
 
-/* Copy the pools and descriptors to the device (host -> device).  Replaces any previous batch. */
+/* Copy the pools and descriptors to the device (host -> device).  Replaces any previous batch.  Asynchronous: the caller's
+ * arrays must stay untouched until the next call that synchronises the context (levins_batch_download, levins_synchronize). */
 int levins_batch_upload(levins_ctx *ctx, const levins_point_xyzit *points, size_t n_points,
                         const levins_ins_sample *ins, size_t n_ins, const float *query_xyz, size_t n_queries,
                         const levins_keyframe_desc *descs, size_t n_keyframes);
+/* The same with the points as packed 16-byte records: x, y, z and the point's time as the LiDAR drivers deliver it, a u32
+ * count of nanoseconds after its scan's stamp (Ouster `t`, Livox `offset_time`; ROS/lidar/lidar_converter.cc:162, :245:
+ * time = stamp + t * 1e-9).  These are the fields of a driver record this path reads (intensity is never used), so the upload
+ * moves half the bytes of PointXYZIT records; the records are expanded to PointXYZIT on the device.  `scans` tile the pool
+ * in order (scan i covers points [first, first + count)); `stamp` is the scan's header stamp already in the estimator's time
+ * base (GPS seconds of week).  Keyframe descriptors index the pool exactly as in levins_batch_upload. */
+typedef struct levins_packed_point {
+    float x, y, z;
+    uint32_t dt_ns;
+} levins_packed_point;
+typedef struct levins_scan_desc {
+    uint64_t first, count;
+    double stamp;
+} levins_scan_desc;
+int levins_batch_upload_packed(levins_ctx *ctx, const levins_packed_point *points, size_t n_points,
+                               const levins_scan_desc *scans, size_t n_scans, const levins_ins_sample *ins, size_t n_ins,
+                               const float *query_xyz, size_t n_queries, const levins_keyframe_desc *descs, size_t n_keyframes);
 /* Enqueue the whole batch on the context's stream: per keyframe window search + INS table (one launch for the
  * batch), then per wave of keyframes deskew+bin, cell finalisation and association.  Asynchronous. */
 int levins_batch_run(levins_ctx *ctx);
@@ -261,6 +279,42 @@ int levins_set_profiling(levins_ctx *ctx, int enabled);
 int levins_batch_kernel_ms(levins_ctx *ctx, float ms[4], uint32_t launches[4]);
 /* number of kernel launches issued by this context since creation */
 uint64_t levins_launch_count(const levins_ctx *ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * exchange step of a sharded batch.  Keyframes are independent, so ranks (one process per GPU, one context
+ * each) share nothing until the end, when every rank wants the per-feature results of all ranks.  A rank's results are
+ * one contiguous block of 17 bytes per query (xyz_depth, then type; levins_batch_result_pointers); the gathered block holds
+ * one such slot per rank, in rank order.  Every rank must hold the same number of queries (pad the last shard).
+ * The reference is a single process and has no counterpart.  Two interchangeable ways:
+ *
+ * (1) NCCL: levins_gather enqueues one ncclAllGather on the context's stream.  `comm` is an ncclComm_t -- the caller's own,
+ *     or one made by levins_comm_init from an id that rank 0 got from levins_comm_unique_id and handed to the other ranks by
+ *     whatever means the host program has.  libnccl.so.2 is resolved at run time; there is no link-time dependency.
+ *
+ * (2) peer mode: no collective at all.  After levins_peer_export / levins_peer_attach the plane-fit kernel of
+ *     levins_batch_run stores each result straight into slot `rank` of EVERY rank's gathered block (peer memory mapped
+ *     through CUDA IPC; the stores travel over NVLink / NVSwitch) and publishes a per-rank step counter; levins_peer_wait
+ *     holds this context's stream until all ranks have published the current step.  Handles are 64-byte
+ *     cudaIpcMemHandle_t images; the host program carries them between the ranks (all ranks call export, exchange the
+ *     handles, call attach, then synchronise among themselves once before the first levins_batch_run).  Every rank must
+ *     run the same sequence of levins_batch_run calls.  The gathered block is double-buffered by step parity: the results
+ *     of step s stay readable until the rank has called levins_peer_wait for step s + 1.
+ * ------------------------------------------------------------------------------------------------ */
+int levins_comm_unique_id(void *out128);
+int levins_comm_init(levins_ctx *ctx, const void *id128, int n_ranks, int rank, void **comm_out);
+int levins_comm_destroy(void *comm);
+int levins_gather(levins_ctx *ctx, void *nccl_comm, int n_ranks);
+
+int levins_peer_export(levins_ctx *ctx, int n_ranks, size_t n_queries_cap, void *handle_out64);
+int levins_peer_attach(levins_ctx *ctx, int rank, int n_ranks, const void *all_handles /* n_ranks x 64 bytes */);
+int levins_peer_wait(levins_ctx *ctx);
+int levins_peer_detach(levins_ctx *ctx);
+
+/* The gathered block of the latest step on the device (slot r at device_block + r * slot_bytes: xyz_depth
+ * float[4 * queries_per_slot], then type int8[queries_per_slot]) and its copy to the host (synchronises; type[n_ranks *
+ * queries_per_slot], xyz_depth[4 * n_ranks * queries_per_slot], either nullable). */
+int levins_gathered_pointer(levins_ctx *ctx, void **device_block, size_t *slot_bytes, size_t *queries_per_slot);
+int levins_gathered_download(levins_ctx *ctx, int8_t *type, float *xyz_depth);
 
 #ifdef __cplusplus
 }

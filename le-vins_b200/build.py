@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", "levins_abi.cu")]
-DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "device_math.cuh")] + [
+DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "device_math.cuh", "exchange.cuh", "exchange_host.inc")] + [
     os.path.join(ROOT, "include", "levins", "abi.h")]
 OUT = os.path.join(HERE, "liblevins_b200.so")
 
@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     # integer / index / validity results must reproduce the reference's non-contracted SSE2 arithmetic;
     # fused multiply-adds are requested explicitly (fma()) where only a tolerance applies
     "-fmad=false",
-    "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"),
+    "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), "-ldl",
 ]
 
 

@@ -19,6 +19,7 @@
 #include <type_traits>
 
 #include "device_math.cuh"
+#include "exchange.cuh"
 
 namespace lv {
 
@@ -249,6 +250,37 @@ __global__ void __launch_bounds__(RAW_BLOCK) k_raw_scatter(const __grid_constant
         reinterpret_cast<float2*>(out + 1)[0] = make_float2(p.intensity, 0.f);
         reinterpret_cast<double*>(out + 1)[1] = p.time;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_unpack: packed 16-byte points (x, y, z, u32 nanoseconds after the scan's stamp: the fields of a driver record this path
+// reads, with the time as the Ouster / Livox drivers deliver it) -> PointXYZIT in the batch pool.  time = stamp + dt * 1e-9
+// (ROS/lidar/lidar_converter.cc:162, :245).  Half the PCIe bytes of uploading PointXYZIT records.
+// ------------------------------------------------------------------------------------------------
+struct PackedPoint {
+    float x, y, z;
+    unsigned dt_ns;
+};
+struct ScanDesc {
+    unsigned long long first, count;
+    double stamp;
+};
+__global__ void __launch_bounds__(256) k_unpack(const PackedPoint* __restrict__ in, unsigned long long n, const ScanDesc* __restrict__ scans,
+                                                unsigned n_scans, PointXYZIT* __restrict__ out) {
+    const unsigned long long k = (unsigned long long) blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    // the scan that holds point k: last scan with first <= k (scans are sorted by `first`; a block rarely spans two)
+    unsigned lo = 0, hi = n_scans;
+    while (hi - lo > 1) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (__ldg(&scans[mid].first) <= k) lo = mid; else hi = mid;
+    }
+    const double stamp = __ldg(&scans[lo].stamp);
+    const uint4 p = __ldg(reinterpret_cast<const uint4*>(in + k));
+    float4* o = reinterpret_cast<float4*>(out + k);
+    o[0] = make_float4(__uint_as_float(p.x), __uint_as_float(p.y), __uint_as_float(p.z), 0.f);
+    const double t = stamp + (double) p.w * 1.0e-9;
+    o[1] = make_float4(0.f, 0.f, __int_as_float(__double2loint(t)), __int_as_float(__double2hiint(t)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1405,6 +1437,7 @@ struct PlaneArgs {
     float4* xyz_depth;
     int32_t* flags;
     Consts c;
+    PeerOut peer; // peer mode: the results also go straight into every rank's gathered block (exchange.cuh)
 };
 
 __global__ void __launch_bounds__(128) k_plane(const __grid_constant__ PlaneArgs a) {
@@ -1478,6 +1511,16 @@ __global__ void __launch_bounds__(128) k_plane(const __grid_constant__ PlaneArgs
     a.type[qi] = (int8_t) type;
     a.xyz_depth[qi] = make_float4(ox, oy, oz, od);
     a.flags[qi] = flags;
+    // the exchange step fused into the producer: one 16-byte and one 1-byte store per rank over NVLink (peer memory), no
+    // separate collective; k_peer_signal publishes completion afterwards
+    if (a.peer.n_ranks) {
+#pragma unroll 1
+        for (int r = 0; r < a.peer.n_ranks; r++) {
+            unsigned char* slot = a.peer.base[r] + a.peer.parity_off + (unsigned long long) a.peer.rank * a.peer.slot_bytes;
+            reinterpret_cast<float4*>(slot)[qi] = make_float4(ox, oy, oz, od);
+            reinterpret_cast<int8_t*>(slot + 16ull * a.peer.nq_cap)[qi] = (int8_t) type;
+        }
+    }
 }
 
 // PointCloudCommon::pointCloudProjection (pointcloud.cc:50-63): reference operation order, no contraction

@@ -96,11 +96,22 @@ struct levins_ctx {
     DevBuf b_flags, b_nn, b_nn_meta;
     DevBuf b_zbuf, b_cells;
     std::vector<levins_keyframe_desc> b_descs;
+    std::vector<KfState> b_kfs_host;
+    DevBuf b_packed, b_scans; // levins_batch_upload_packed: the records as uploaded, the scan stamps
     size_t b_nq = 0, b_npts = 0, b_nins = 0;
     int b_wave = 256;
     int b_wave_alloc = 0;
     unsigned b_gen = 255;
     bool b_valid = false;
+    // ---- exchange step (exchange.cuh): gathered results of all ranks ----
+    DevBuf g_block;            // [PEER_HDR | halves x ranks x slot]: NCCL mode one half, peer mode two (step parity)
+    size_t g_slot = 0, g_nq = 0; // bytes / queries per rank slot
+    int g_ranks = 0, g_half = 0;
+    PeerOut peer{};
+    PeerFlags pflags{};
+    void* peer_mapped[MAX_PEERS] = {};
+    unsigned long long peer_step = 0;
+    bool peer_on = false;
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
     struct EvSpan {
@@ -483,13 +494,15 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
-                      &ctx->b_cells})
+                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->ev_binned) cudaEventDestroy(ctx->ev_binned);
     if (ctx->ev_counted) cudaEventDestroy(ctx->ev_counted);
     if (ctx->ev_append) cudaEventDestroy(ctx->ev_append);
+    for (int r = 0; r < MAX_PEERS; r++)
+        if (ctx->peer_mapped[r]) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -976,15 +989,14 @@ extern "C" int levins_batch_set_wave(levins_ctx* ctx, int w) {
     return LEVINS_OK;
 }
 
-extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* points, size_t n_points,
-                                   const levins_ins_sample* ins, size_t n_ins, const float* query_xyz, size_t n_queries,
-                                   const levins_keyframe_desc* descs, size_t n_kf) {
-    if (!ctx || !points || !ins || !descs || (!query_xyz && n_queries)) return fail(ctx, LEVINS_ERR_ARG, "null argument");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->device));
+// shared by the two upload entry points: validate the descriptors, size the pools, copy INS / queries / keyframe states.
+// The point pool itself is filled by the caller (a plain copy, or a copy of packed records + k_unpack).
+static int batch_prepare(levins_ctx* ctx, size_t n_points, const levins_ins_sample* ins, size_t n_ins, const float* query_xyz,
+                         size_t n_queries, const levins_keyframe_desc* descs, size_t n_kf) {
     ctx->b_valid = false;
     if (n_kf == 0) return fail(ctx, LEVINS_ERR_ARG, "no keyframes");
-    std::vector<KfState> kfs(n_kf);
+    std::vector<KfState>& kfs = ctx->b_kfs_host; // a member: the copy below stays asynchronous
+    kfs.resize(n_kf);
     size_t table_entries = 0; // the table depends on the keyframe pose, so INS slices shared by keyframes get separate tables
     for (size_t k = 0; k < n_kf; k++) {
         const levins_keyframe_desc& d = descs[k];
@@ -1013,15 +1025,65 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
     CU(ctx->b_flags.ensure(std::max<size_t>(n_queries, 1) * 4));
     CU(ctx->b_nn.ensure(std::max<size_t>(n_queries, 1) * 80));
     CU(ctx->b_nn_meta.ensure(std::max<size_t>(n_queries, 1) * 8));
-    CU(cudaMemcpyAsync(ctx->b_pts.p, points, n_points * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->b_ins.p, ins, n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
     if (n_queries) CU(cudaMemcpyAsync(ctx->b_queries.p, query_xyz, n_queries * 12, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->b_kfs.p, kfs.data(), n_kf * sizeof(KfState), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream)); // kfs is a stack vector
     ctx->b_descs.assign(descs, descs + n_kf);
     ctx->b_nq = n_queries;
     ctx->b_npts = n_points;
     ctx->b_nins = n_ins;
+    return LEVINS_OK;
+}
+
+extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* points, size_t n_points,
+                                   const levins_ins_sample* ins, size_t n_ins, const float* query_xyz, size_t n_queries,
+                                   const levins_keyframe_desc* descs, size_t n_kf) {
+    if (!ctx || !points || !ins || !descs || (!query_xyz && n_queries)) return fail(ctx, LEVINS_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    // the previous batch's copies read caller memory and b_kfs_host: let them finish before either is touched again
+    CU(cudaStreamSynchronize(ctx->stream));
+    int r = batch_prepare(ctx, n_points, ins, n_ins, query_xyz, n_queries, descs, n_kf);
+    if (r) return r;
+    CU(cudaMemcpyAsync(ctx->b_pts.p, points, n_points * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->b_valid = true;
+    return LEVINS_OK;
+}
+
+extern "C" int levins_batch_upload_packed(levins_ctx* ctx, const levins_packed_point* points, size_t n_points,
+                                          const levins_scan_desc* scans, size_t n_scans, const levins_ins_sample* ins, size_t n_ins,
+                                          const float* query_xyz, size_t n_queries, const levins_keyframe_desc* descs, size_t n_kf) {
+    if (!ctx || !points || !scans || !n_scans || !ins || !descs || (!query_xyz && n_queries)) return fail(ctx, LEVINS_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (n_scans > 0xffffffffull) return fail(ctx, LEVINS_ERR_ARG, "too many scans");
+    unsigned long long next = 0;
+    for (size_t i = 0; i < n_scans; i++) { // the scans tile the pool in order
+        if (scans[i].first != next) return fail(ctx, LEVINS_ERR_ARG, "scan descriptors must tile the point pool contiguously");
+        next += scans[i].count;
+    }
+    if (next != n_points) return fail(ctx, LEVINS_ERR_ARG, "scan descriptors do not cover the point pool");
+    int r = batch_prepare(ctx, n_points, ins, n_ins, query_xyz, n_queries, descs, n_kf);
+    if (r) return r;
+    static_assert(sizeof(levins_packed_point) == sizeof(PackedPoint) && sizeof(levins_scan_desc) == sizeof(ScanDesc), "packed layouts");
+    CU(ctx->b_packed.ensure(std::max<size_t>(n_points, 1) * sizeof(PackedPoint)));
+    CU(ctx->b_scans.ensure(n_scans * sizeof(ScanDesc)));
+    CU(cudaMemcpyAsync(ctx->b_scans.p, scans, n_scans * sizeof(ScanDesc), cudaMemcpyHostToDevice, ctx->stream));
+    // a few pieces, each unpacked as soon as it has arrived, so that the expansion hides behind the next piece's copy when the
+    // caller gave the context a stream of its own per direction; on one stream it simply follows
+    const size_t piece = std::max<size_t>((n_points + 7) / 8, 1 << 20);
+    for (size_t o = 0; o < n_points; o += piece) {
+        const size_t n = std::min(piece, n_points - o);
+        CU(cudaMemcpyAsync(ctx->b_packed.as<PackedPoint>() + o, points + o, n * sizeof(PackedPoint), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (n_points) {
+        k_unpack<<<(unsigned) ((n_points + 255) / 256), 256, 0, ctx->stream>>>(ctx->b_packed.as<PackedPoint>(), n_points,
+                                                                               ctx->b_scans.as<ScanDesc>(), (unsigned) n_scans,
+                                                                               ctx->b_pts.as<PointXYZIT>());
+        ctx->launches++;
+        CU(cudaGetLastError());
+    }
     ctx->b_valid = true;
     return LEVINS_OK;
 }
@@ -1169,11 +1231,25 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         pl.xyz_depth = ctx->b_results.as<float4>();
         pl.flags = ctx->b_flags.as<int32_t>();
         pl.c = ctx->consts;
+        if (ctx->peer_on) {
+            if (ctx->b_nq > ctx->g_nq) return fail(ctx, LEVINS_ERR_CAPACITY, "more queries than levins_peer_export reserved per rank");
+            ctx->peer_step++;
+            ctx->g_half = (int) (ctx->peer_step & 1);
+            pl.peer = ctx->peer;
+            pl.peer.parity_off = (unsigned long long) ctx->g_half * ctx->g_ranks * ctx->g_slot;
+        }
         mark(2, true);
         k_plane<<<(unsigned) ((ctx->b_nq + 127) / 128), 128, 0, ctx->stream>>>(pl);
         mark(2, false);
         ctx->launches++;
         CU(cudaGetLastError());
+        if (ctx->peer_on) {
+            PeerFlags pf = ctx->pflags;
+            pf.step = ctx->peer_step;
+            k_peer_signal<<<1, 32, 0, ctx->stream>>>(pf);
+            ctx->launches++;
+            CU(cudaGetLastError());
+        }
     }
     return LEVINS_OK;
 }
@@ -1230,3 +1306,5 @@ extern "C" int levins_batch_download(levins_ctx* ctx, int8_t* type, float* xyz_d
     }
     return LEVINS_OK;
 }
+
+#include "exchange_host.inc"

@@ -28,7 +28,9 @@ EXPORTS = [
     "levins_keyframe", "levins_point_cloud_projection", "levins_batch_upload", "levins_batch_run",
     "levins_batch_download", "levins_batch_set_wave", "levins_set_profiling", "levins_batch_kernel_ms",
     "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host", "levins_append_raw",
-    "levins_append_wait", "levins_ins_window_index", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
+    "levins_append_wait", "levins_ins_window_index", "levins_comm_unique_id", "levins_comm_init", "levins_comm_destroy",
+    "levins_gather", "levins_peer_export", "levins_peer_attach", "levins_peer_wait", "levins_peer_detach", "levins_gathered_pointer",
+    "levins_gathered_download", "levins_batch_upload_packed", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
 ]
 
 
@@ -45,6 +47,28 @@ class Config(C.Structure):
 KF_DESC = np.dtype([("pt_begin", "<u8"), ("pt_count", "<u8"), ("ins_begin", "<u8"), ("ins_count", "<u8"),
                     ("q_begin", "<u8"), ("q_count", "<u8"), ("stamp", "<f8")])
 assert KF_DESC.itemsize == 56
+PACKED = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("dt_ns", "<u4")])
+SCAN_DESC = np.dtype([("first", "<u8"), ("count", "<u8"), ("stamp", "<f8")])
+
+
+def pack_points(points, scan_first, scan_stamp):
+    """PointXYZIT records -> (packed 16-byte records, scan descriptors, the PointXYZIT records with the times the device
+    will reconstruct: stamp + dt_ns * 1e-9).  scan_first: index of each scan's first point; scan_stamp: its stamp."""
+    n = len(points)
+    first = np.asarray(scan_first, np.uint64)
+    count = np.diff(np.concatenate([first, [n]]).astype(np.uint64))
+    stamp = np.asarray(scan_stamp, np.float64)
+    per_point_stamp = np.repeat(stamp, count.astype(np.int64))
+    dt = np.rint((points["time"] - per_point_stamp) * 1e9)
+    assert dt.min() >= 0 and dt.max() < 2**32, "a point lies before its scan's stamp or more than 4.29 s after it"
+    packed = np.zeros(n, PACKED)
+    packed["x"], packed["y"], packed["z"], packed["dt_ns"] = points["x"], points["y"], points["z"], dt.astype(np.uint32)
+    scans = np.zeros(len(first), SCAN_DESC)
+    scans["first"], scans["count"], scans["stamp"] = first, count, stamp
+    exact = points.copy()
+    exact["time"] = per_point_stamp + packed["dt_ns"].astype(np.float64) * 1.0e-9
+    exact["intensity"] = 0
+    return packed, scans, exact
 
 _lib = None
 
@@ -80,12 +104,23 @@ def lib():
             "levins_keyframe": [vp, dbl, vp, sz, vp, sz, vp, vp, vp, vp],
             "levins_point_cloud_projection": [vp, vp, vp, vp, sz],
             "levins_batch_upload": [vp, vp, sz, vp, sz, vp, sz, vp, sz],
+            "levins_batch_upload_packed": [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz],
             "levins_batch_run": [vp],
             "levins_batch_download": [vp, vp, vp, vp, vp, vp],
             "levins_batch_set_wave": [vp, i32],
             "levins_batch_result_pointers": [vp, vp, vp, vp],
             "levins_set_profiling": [vp, i32],
             "levins_batch_kernel_ms": [vp, vp, vp],
+            "levins_comm_unique_id": [vp],
+            "levins_comm_init": [vp, vp, i32, i32, C.POINTER(vp)],
+            "levins_comm_destroy": [vp],
+            "levins_gather": [vp, vp, i32],
+            "levins_peer_export": [vp, i32, sz, vp],
+            "levins_peer_attach": [vp, i32, i32, vp],
+            "levins_peer_wait": [vp],
+            "levins_peer_detach": [vp],
+            "levins_gathered_pointer": [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)],
+            "levins_gathered_download": [vp, vp, vp],
         }.items():
             fn = getattr(L, name)
             fn.restype = i32
@@ -250,6 +285,16 @@ class Context:
                                               len(self._b_ins), _p(self._b_q), len(self._b_q), _p(self._b_descs),
                                               len(self._b_descs)))
 
+    def batch_upload_packed(self, packed, scans, ins, queries, descs):
+        self._b_points = np.ascontiguousarray(packed, PACKED)
+        self._b_scans = np.ascontiguousarray(scans, SCAN_DESC)
+        self._b_ins = np.ascontiguousarray(ins, INS)
+        self._b_q = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+        self._b_descs = np.ascontiguousarray(descs, KF_DESC)
+        self._check(lib().levins_batch_upload_packed(self._h, _p(self._b_points), len(self._b_points), _p(self._b_scans),
+                                                     len(self._b_scans), _p(self._b_ins), len(self._b_ins), _p(self._b_q),
+                                                     len(self._b_q), _p(self._b_descs), len(self._b_descs)))
+
     def batch_run(self):
         self._check(lib().levins_batch_run(self._h))
 
@@ -269,6 +314,53 @@ class Context:
         a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(lib().levins_batch_result_pointers(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"type": a.value, "xyz_depth": b.value, "flags": c.value}
+
+    # ---- exchange step (one context per rank) ----
+    @staticmethod
+    def comm_unique_id() -> np.ndarray:
+        out = np.zeros(128, np.uint8)
+        st = lib().levins_comm_unique_id(_p(out))
+        if st != OK:
+            raise LevinsError(st, "levins_comm_unique_id (is libnccl.so.2 loadable?)")
+        return out
+
+    def comm_init(self, unique_id, n_ranks, rank) -> int:
+        uid = np.ascontiguousarray(unique_id, np.uint8)
+        assert uid.size == 128
+        comm = C.c_void_p()
+        self._check(lib().levins_comm_init(self._h, _p(uid), int(n_ranks), int(rank), C.byref(comm)))
+        return comm.value
+
+    @staticmethod
+    def comm_destroy(comm):
+        lib().levins_comm_destroy(C.c_void_p(comm))
+
+    def gather(self, comm, n_ranks):
+        self._check(lib().levins_gather(self._h, C.c_void_p(comm), int(n_ranks)))
+
+    def peer_export(self, n_ranks, n_queries_cap) -> np.ndarray:
+        h = np.zeros(64, np.uint8)
+        self._check(lib().levins_peer_export(self._h, int(n_ranks), int(n_queries_cap), _p(h)))
+        return h
+
+    def peer_attach(self, rank, n_ranks, all_handles):
+        hs = np.ascontiguousarray(all_handles, np.uint8).reshape(-1)
+        assert hs.size == 64 * n_ranks
+        self._check(lib().levins_peer_attach(self._h, int(rank), int(n_ranks), _p(hs)))
+
+    def peer_wait(self):
+        self._check(lib().levins_peer_wait(self._h))
+
+    def peer_detach(self):
+        self._check(lib().levins_peer_detach(self._h))
+
+    def gathered_download(self, n_ranks):
+        p, slot, nq = C.c_void_p(), C.c_size_t(0), C.c_size_t(0)
+        self._check(lib().levins_gathered_pointer(self._h, C.byref(p), C.byref(slot), C.byref(nq)))
+        ty = np.zeros(n_ranks * nq.value, np.int8)
+        xd = np.zeros((n_ranks * nq.value, 4), np.float32)
+        self._check(lib().levins_gathered_download(self._h, _p(ty), _p(xd)))
+        return {"type": ty.reshape(n_ranks, nq.value), "xyz_depth": xd.reshape(n_ranks, nq.value, 4)}
 
     def batch_kernel_ms(self):
         ms = np.zeros(4, np.float32)

@@ -224,6 +224,37 @@ def test_batch_matches_single_keyframes(ctx, oracle):
             assert d.max() <= REL_TOL
 
 
+def test_packed_upload_equals_plain_upload(ctx, oracle):
+    """levins_batch_upload_packed (16-byte records, time = scan stamp + u32 ns) fills the pool with exactly the PointXYZIT
+    records abi.pack_points predicts, so the batch results equal those of a plain upload of these records bytewise, and
+    the oracle's on them."""
+    shp = synth.Shape(**{**synth.shape(3).__dict__, "stack_interval": 0.3})
+    b = synth.make_batch(3, 3, n_unique_scans=5, shp=shp, ins_span=1.5)
+    per = b.shape.pts_per_scan
+    packed, scans, exact = abi.pack_points(b.points, np.arange(len(b.points) // per) * per, b.points["time"][::per])
+    assert np.max(np.abs(exact["time"] - b.points["time"])) < 1e-9 and packed.nbytes * 2 == exact.nbytes
+    ctx.close()
+    c = abi.Context(0, stack_interval=0.3)
+    c.set_extrinsics(b.shape.rig.pose_b_c, b.shape.rig.pose_c_l, b.shape.rig.td_b_l)
+    descs = abi.batch_descs(b)
+    c.batch_upload_packed(packed, scans, b.ins, b.queries.reshape(-1, 3), descs)
+    c.batch_run()
+    got = c.batch_download()
+    c.batch_upload(exact, b.ins, b.queries.reshape(-1, 3), descs)
+    c.batch_run()
+    plain = c.batch_download()
+    assert all(got[k].tobytes() == plain[k].tobytes() for k in got)
+    b.points = exact
+    f = b.queries.shape[1]
+    for k in range(b.n_keyframes):
+        kf = synth.batch_keyframe(b, k)
+        ref = oracle.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries, 0.3)
+        assert got["n_projected"][k] == ref["n_projected"] and got["m"][k] == ref["m"]
+        assert np.array_equal(got["type"][k * f:(k + 1) * f], ref["type"])
+    assert (got["type"] == 1).sum() > 10
+    c.close()
+
+
 def test_point_cloud_projection(ctx, oracle):
     rng = np.random.default_rng(3)
     cloud = np.zeros(5000, synth.XYZI)
