@@ -222,6 +222,26 @@ int levins_associate(levins_ctx *ctx, const float *query_xyz, size_t n_features,
 int levins_keyframe(levins_ctx *ctx, double stamp, const levins_ins_sample *ins, size_t n_ins, const float *query_xyz,
                     size_t n_features, int8_t *type, float *xyz_depth, size_t *n_projected_out, size_t *m_out);
 
+/* The feature side of the two association drivers on the device: tracked pixels in, accepted map points
+ * out.  Per feature: Camera::undistortPoints (camera.cc:72-74: cv::undistortPoints(pts, pts, K, D, Mat(), K), OpenCV's
+ * 5-iteration fixed point; skipped when `undistort` is 0 because the caller's pixels are undistorted already) ->
+ * Camera::pixel2unitcam -> cast to float (tracking.cc:381-395 / 489-504) -> depthAssociationPlaneFitting ->
+ * accept iff type != NONE && isGoodDepth(depth, 1) (tracking.cc:431-435 / 539-542) -> cam2world with the reference frame's
+ * pose (tracking.cc:437-439 / 544-545, camera.cc:149-151).  Outputs (each nullable): type, xyz_depth as in levins_associate;
+ * accepted[F]; pw[3 F] world points of accepted features (zeros otherwise; needs pose_ref); undistorted[2 F] pixels. */
+typedef struct levins_camera {
+    double fx, fy, cx, cy, skew; /* Camera::fx_ ... skew_ */
+    double k1, k2, p1, p2, k3;   /* distortion_ in OpenCV order */
+} levins_camera;
+int levins_associate_pixels(levins_ctx *ctx, const levins_camera *camera, const float *pixels, size_t n_features, int undistort,
+                            const levins_pose *pose_ref, int8_t *type, float *xyz_depth, uint8_t *accepted, double *pw,
+                            float *undistorted);
+/* levins_keyframe with the feature side on the device as above */
+int levins_keyframe_pixels(levins_ctx *ctx, double stamp, const levins_ins_sample *ins, size_t n_ins, const levins_camera *camera,
+                           const float *pixels, size_t n_features, int undistort, const levins_pose *pose_ref, int8_t *type,
+                           float *xyz_depth, uint8_t *accepted, double *pw, float *undistorted, size_t *n_projected_out,
+                           size_t *m_out);
+
 /* PointCloudCommon::pointCloudProjection (pointcloud.cc:50-63): dst[k] = f32(R * f64(src[k]) + t). */
 int levins_point_cloud_projection(levins_ctx *ctx, const levins_pose *pose, const levins_point_xyzi *src,
                                   levins_point_xyzi *dst, size_t n);

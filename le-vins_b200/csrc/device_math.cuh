@@ -765,6 +765,55 @@ __device__ __forceinline__ bool deskew_point(float x, float y, float z, double t
 }
 
 // ------------------------------------------------------------------------------------------------
+// feature side: Camera::undistortPoints -> pixel2unitcam before the association, cam2world after it
+// ------------------------------------------------------------------------------------------------
+struct CameraModel {
+    double fx, fy, cx, cy, skew;
+    double k1, k2, p1, p2, k3; // OpenCV order of the first five distortion coefficients
+};
+// cv::undistortPoints(pts, pts, K, D, Mat(), K) (camera.cc:72-74): OpenCV's fixed-point iteration with its default
+// criteria (5 iterations), R = identity, P = K, operation for operation (no contraction, IEEE division); f32 in, f64
+// arithmetic, f32 out like cv::Point2f.
+__device__ __forceinline__ void undistort_pixel(const CameraModel& c, float& pu, float& pv) {
+    const double ifx = 1. / c.fx, ify = 1. / c.fy;
+    const double u = (double) pu, v = (double) pv;
+    double x = (u - c.cx) * ifx, y = (v - c.cy) * ify;
+    const double x0 = x, y0 = y;
+#pragma unroll 1
+    for (int j = 0; j < 5; j++) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1. / (1 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2); // numerator: k4 = k5 = k6 = 0
+        if (icdist < 0) {
+            x = (u - c.cx) * ifx;
+            y = (v - c.cy) * ify;
+            break;
+        }
+        const double deltaX = 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
+        const double deltaY = c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
+        x = (x0 - deltaX) * icdist;
+        y = (y0 - deltaY) * icdist;
+    }
+    pu = (float) (c.fx * x + c.skew * y + c.cx);
+    pv = (float) (c.fy * y + c.cy);
+}
+// Camera::pixel2unitcam (camera.cc:123-135) then .cast<float>() (tracking.cc:391-393)
+__device__ __forceinline__ void pixel_to_unit_ray(const CameraModel& c, float pu, float pv, float& qx, float& qy, float& qz) {
+    const double y = ((double) pv - c.cy) / c.fy;
+    const double x = ((double) pu - c.cx - c.skew * y) / c.fx;
+    double r[3] = {x, y, 1.0};
+    const double z = v3_dot(r, r);
+    if (z > 0) {
+        const double s = sqrt(z);
+        r[0] /= s;
+        r[1] /= s;
+        r[2] /= s;
+    }
+    qx = (float) r[0];
+    qy = (float) r[1];
+    qz = (float) r[2];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Eigen::ColPivHouseholderQR<Matrix<double,5,3>> compute + solve (Eigen >= 3.3 algorithm, LAPACK-style norm down-dating)
 // ------------------------------------------------------------------------------------------------
 __device__ inline void colpiv_qr_solve_5x3(const double (*P)[3], double* x) {

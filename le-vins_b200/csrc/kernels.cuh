@@ -1221,6 +1221,12 @@ struct AssocArgs {
     int count_cells; // FUSED: also count the live cells of the z-buffer (M) in this launch
     Extrinsics ext;
     // outputs
+    // feature side on the device (levins_associate_pixels): queries are made here from tracked pixels
+    const float* pixels; // nullable; 2 floats per query, same indexing as `queries`
+    float* queries_out;  // the f32 rays, stored for k_plane (the query pool itself)
+    float* undist_out;   // nullable: the undistorted pixels
+    int undistort;       // run Camera::undistortPoints first (camera.cc:72-74)
+    CameraModel cam;
     float4* nn;       // 5 per query: neighbours (unit vector + range) for k_plane
     uint2* nn_meta;   // (found, bits of the 5th squared distance)
     int32_t* knn_idx; // nullable, 5 per query
@@ -1238,7 +1244,25 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32, LV_ASSOC_MINBLK) k_associate
         return;
     }
     const size_t qi = kf->q_begin + f;
-    const float qx = __ldg(a.queries + 3 * qi), qy = __ldg(a.queries + 3 * qi + 1), qz = __ldg(a.queries + 3 * qi + 2);
+    float qx, qy, qz;
+    if (a.pixels) { // tracking.cc:381-395: undistort, pixel2unitcam, cast to float (every lane computes the same ray)
+        float pu = __ldg(a.pixels + 2 * qi), pv = __ldg(a.pixels + 2 * qi + 1);
+        if (a.undistort) undistort_pixel(a.cam, pu, pv);
+        pixel_to_unit_ray(a.cam, pu, pv, qx, qy, qz);
+        if (lane == 0) {
+            a.queries_out[3 * qi] = qx;
+            a.queries_out[3 * qi + 1] = qy;
+            a.queries_out[3 * qi + 2] = qz;
+            if (a.undist_out) {
+                a.undist_out[2 * qi] = pu;
+                a.undist_out[2 * qi + 1] = pv;
+            }
+        }
+    } else {
+        qx = __ldg(a.queries + 3 * qi);
+        qy = __ldg(a.queries + 3 * qi + 1);
+        qz = __ldg(a.queries + 3 * qi + 2);
+    }
 
     // The query's position in cell units.  Precision is irrelevant: the window and the mask below carry half a cell
     // of slack, and every candidate they keep is measured with the reference's exact f32 arithmetic afterwards.
@@ -1438,6 +1462,10 @@ struct PlaneArgs {
     int32_t* flags;
     Consts c;
     PeerOut peer; // peer mode: the results also go straight into every rank's gathered block (exchange.cuh)
+    // feature side on the device: the drivers' accept gate and cam2world (tracking.cc:431-439, 539-545)
+    unsigned char* accepted; // nullable: type != NONE && isGoodDepth(depth, 1)
+    double* pw;              // nullable: 3 per query, world point of accepted features (0 otherwise)
+    double poseR[9], poset[3]; // frame_ref_->pose(), R column-major
 };
 
 __global__ void __launch_bounds__(128) k_plane(const __grid_constant__ PlaneArgs a) {
@@ -1511,6 +1539,25 @@ __global__ void __launch_bounds__(128) k_plane(const __grid_constant__ PlaneArgs
     a.type[qi] = (int8_t) type;
     a.xyz_depth[qi] = make_float4(ox, oy, oz, od);
     a.flags[qi] = flags;
+    if (a.accepted) {
+        const double depth = (double) od; // tracking.cc:430: double depth = point.intensity
+        const bool ok = (type != -1) && (depth > a.c.nearest) && (depth < a.c.farthest * 1.0); // visual_mappoint.cc:90-92
+        a.accepted[qi] = ok ? 1 : 0;
+        if (a.pw) {
+            double w[3] = {0, 0, 0};
+            if (ok) { // camera.cc:149-151: pose.R * pc + pose.t
+                const double pc[3] = {(double) ox, (double) oy, (double) oz};
+                double r[3];
+                m3_mul_v(a.poseR, pc, r);
+                w[0] = r[0] + a.poset[0];
+                w[1] = r[1] + a.poset[1];
+                w[2] = r[2] + a.poset[2];
+            }
+            a.pw[3 * qi] = w[0];
+            a.pw[3 * qi + 1] = w[1];
+            a.pw[3 * qi + 2] = w[2];
+        }
+    }
     // the exchange step fused into the producer: one 16-byte and one 1-byte store per rank over NVLink (peer memory), no
     // separate collective; k_peer_signal publishes completion afterwards
     if (a.peer.n_ranks) {

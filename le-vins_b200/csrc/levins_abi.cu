@@ -68,6 +68,7 @@ struct levins_ctx {
     DevBuf chunks; // ChunkDesc of the current k_deskew_bin launch (streaming and batch)
     DevBuf raw_stage, raw_blocks, raw_misc; // levins_append_raw: records, per-block counts, {min, max, result}
     DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2, s_nn, s_nn_meta;
+    DevBuf s_pixels, s_undist, s_accepted, s_pw; // feature side on the device (levins_associate_pixels)
     DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
     DevBuf s_in_cloud; // explicit cloud uploaded by build_range_image
     DevBuf s_zbuf, s_cells, s_c2c, s_unit, s_winner;
@@ -86,7 +87,10 @@ struct levins_ctx {
     size_t pin_q() const { return pin_ins() + ((cfg.max_ins * sizeof(InsSample) + 255) & ~size_t(255)); }
     size_t pin_type() const { return pin_q() + ((cfg.max_features * 12 + 255) & ~size_t(255)); }
     size_t pin_xyzd() const { return pin_type() + ((cfg.max_features + 255) & ~size_t(255)); }
-    size_t pin_total() const { return pin_xyzd() + cfg.max_features * 16 + 256; }
+    size_t pin_acc() const { return pin_xyzd() + cfg.max_features * 16; }
+    size_t pin_und() const { return pin_acc() + ((cfg.max_features + 255) & ~size_t(255)); }
+    size_t pin_pw() const { return pin_und() + cfg.max_features * 8; }
+    size_t pin_total() const { return pin_pw() + cfg.max_features * 24 + 256; }
 
     // ---- batch state ----
     DevBuf b_pts, b_ins, b_table, b_queries, b_kfs;
@@ -210,6 +214,10 @@ int ensure_stream_buffers(levins_ctx* ctx, size_t n_ins, size_t n_feat) {
     CU(ctx->s_knn_d2.ensure(std::max<size_t>(n_feat, 1) * 20));
     CU(ctx->s_nn.ensure(std::max<size_t>(n_feat, 1) * 80));
     CU(ctx->s_nn_meta.ensure(std::max<size_t>(n_feat, 1) * 8));
+    CU(ctx->s_pixels.ensure(std::max<size_t>(n_feat, 1) * 8));
+    CU(ctx->s_undist.ensure(std::max<size_t>(n_feat, 1) * 8));
+    CU(ctx->s_accepted.ensure(std::max<size_t>(n_feat, 1)));
+    CU(ctx->s_pw.ensure(std::max<size_t>(n_feat, 1) * 24));
     CU(ctx->s_cells.ensure((size_t) CELLS * sizeof(float4)));
     CU(ctx->s_c2c.ensure((size_t) CELLS * 4));
     CU(ctx->s_unit.ensure((size_t) CELLS * sizeof(PointXYZI)));
@@ -368,8 +376,23 @@ int run_finalize_stream(levins_ctx* ctx, bool from_cloud, const PointXYZI* cloud
     return LEVINS_OK;
 }
 
-int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused) {
+// feature side on the device: tracked pixels in, accept gate + world points out (null camera: plain unit-ray queries)
+struct PixelOpts {
+    const levins_camera* cam = nullptr;
+    int undistort = 0;
+    const levins_pose* pose_ref = nullptr;
+};
+
+int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused, const PixelOpts& px = PixelOpts()) {
     AssocArgs aa{};
+    if (px.cam) {
+        aa.pixels = ctx->s_pixels.as<float>();
+        aa.queries_out = ctx->s_queries.as<float>();
+        aa.undist_out = ctx->s_undist.as<float>();
+        aa.undistort = px.undistort;
+        static_assert(sizeof(levins_camera) == sizeof(CameraModel), "camera layout");
+        memcpy(&aa.cam, px.cam, sizeof(CameraModel));
+    }
     aa.kfs = ctx->s_kf.as<KfState>();
     aa.queries = ctx->s_queries.as<float>();
     aa.cells = ctx->s_cells.as<float4>();
@@ -403,6 +426,14 @@ int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused) 
     pa.xyz_depth = ctx->s_xyzd.as<float4>();
     pa.flags = ctx->s_flags.as<int32_t>();
     pa.c = ctx->consts;
+    if (px.cam) {
+        pa.accepted = ctx->s_accepted.as<unsigned char>();
+        if (px.pose_ref) {
+            pa.pw = ctx->s_pw.as<double>();
+            memcpy(pa.poseR, px.pose_ref->R, sizeof(pa.poseR));
+            memcpy(pa.poset, px.pose_ref->t, sizeof(pa.poset));
+        }
+    }
     k_plane<<<(unsigned) ((nf + 127) / 128), 128, 0, ctx->stream>>>(pa);
     ctx->launches++;
     CU(cudaGetLastError());
@@ -494,7 +525,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
-                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans})
+                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -879,9 +910,8 @@ extern "C" int levins_build_range_image(levins_ctx* ctx, const levins_point_xyzi
     return m ? LEVINS_OK : LEVINS_EMPTY;
 }
 
-extern "C" int levins_associate(levins_ctx* ctx, const float* query_xyz, size_t nf, int8_t* type, float* xyz_depth,
-                                int32_t* knn_idx, float* knn_d2, int32_t* flags) {
-    if (!ctx || (!query_xyz && nf)) return fail(ctx, LEVINS_ERR_ARG, "null queries");
+static int associate_body(levins_ctx* ctx, const float* query_xyz, const float* pixels, size_t nf, const PixelOpts& px, int8_t* type,
+                          float* xyz_depth, int32_t* knn_idx, float* knn_d2, int32_t* flags, uint8_t* accepted, double* pw, float* undistorted) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     if (nf > ctx->cfg.max_features) return fail(ctx, LEVINS_ERR_CAPACITY, "more features than config.max_features");
@@ -889,27 +919,50 @@ extern "C" int levins_associate(levins_ctx* ctx, const float* query_xyz, size_t 
     if (nf == 0) return LEVINS_OK;
     int r = ensure_stream_buffers(ctx, 1, nf);
     if (r) return r;
-    CU(cudaMemcpyAsync(ctx->s_queries.p, query_xyz, nf * 12, cudaMemcpyHostToDevice, ctx->stream));
+    if (pixels)
+        CU(cudaMemcpyAsync(ctx->s_pixels.p, pixels, nf * 8, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        CU(cudaMemcpyAsync(ctx->s_queries.p, query_xyz, nf * 12, cudaMemcpyHostToDevice, ctx->stream));
     // q_count lives in the device KfState
     unsigned long long qc[2] = {0, nf};
     memcpy(ctx->pinned, qc, sizeof(qc));
     CU(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->s_kf.p) + offsetof(KfState, q_begin), ctx->pinned, sizeof(qc),
                        cudaMemcpyHostToDevice, ctx->stream));
-    r = run_associate_stream(ctx, nf, true, false);
+    r = run_associate_stream(ctx, nf, true, false, px);
     if (r) return r;
     if (type) CU(cudaMemcpyAsync(type, ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
     if (xyz_depth) CU(cudaMemcpyAsync(xyz_depth, ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
     if (flags) CU(cudaMemcpyAsync(flags, ctx->s_flags.p, nf * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (knn_idx) CU(cudaMemcpyAsync(knn_idx, ctx->s_knn_idx.p, nf * 20, cudaMemcpyDeviceToHost, ctx->stream));
     if (knn_d2) CU(cudaMemcpyAsync(knn_d2, ctx->s_knn_d2.p, nf * 20, cudaMemcpyDeviceToHost, ctx->stream));
+    if (accepted) CU(cudaMemcpyAsync(accepted, ctx->s_accepted.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pw && px.pose_ref) CU(cudaMemcpyAsync(pw, ctx->s_pw.p, nf * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (undistorted) CU(cudaMemcpyAsync(undistorted, ctx->s_undist.p, nf * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return LEVINS_OK;
 }
 
-extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins,
-                               const float* query_xyz, size_t nf, int8_t* type, float* xyz_depth, size_t* n_projected_out,
-                               size_t* m_out) {
+extern "C" int levins_associate(levins_ctx* ctx, const float* query_xyz, size_t nf, int8_t* type, float* xyz_depth,
+                                int32_t* knn_idx, float* knn_d2, int32_t* flags) {
     if (!ctx || (!query_xyz && nf)) return fail(ctx, LEVINS_ERR_ARG, "null queries");
+    return associate_body(ctx, query_xyz, nullptr, nf, PixelOpts(), type, xyz_depth, knn_idx, knn_d2, flags, nullptr, nullptr, nullptr);
+}
+
+extern "C" int levins_associate_pixels(levins_ctx* ctx, const levins_camera* camera, const float* pixels, size_t nf, int undistort,
+                                       const levins_pose* pose_ref, int8_t* type, float* xyz_depth, uint8_t* accepted, double* pw,
+                                       float* undistorted) {
+    if (!ctx || !camera || (!pixels && nf)) return fail(ctx, LEVINS_ERR_ARG, "null camera or pixels");
+    if (pw && !pose_ref) return fail(ctx, LEVINS_ERR_ARG, "world points need pose_ref");
+    PixelOpts px;
+    px.cam = camera;
+    px.undistort = undistort;
+    px.pose_ref = pose_ref;
+    return associate_body(ctx, nullptr, pixels, nf, px, type, xyz_depth, nullptr, nullptr, nullptr, accepted, pw, undistorted);
+}
+
+static int keyframe_body(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins, const float* query_xyz,
+                         const float* pixels, size_t nf, const PixelOpts& px, int8_t* type, float* xyz_depth, uint8_t* accepted, double* pw,
+                         float* undistorted, size_t* n_projected_out, size_t* m_out) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     if (nf > ctx->cfg.max_features) return fail(ctx, LEVINS_ERR_CAPACITY, "more features than config.max_features");
@@ -924,7 +977,8 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
     if (r == LEVINS_EMPTY) {
         for (size_t k = 0; k < nf; k++) {
             if (type) type[k] = LEVINS_MAPPOINT_NONE;
-            if (xyz_depth) {
+            if (accepted) accepted[k] = 0;
+            if (xyz_depth && query_xyz) {
                 memcpy(xyz_depth + 4 * k, query_xyz + 3 * k, 12);
                 xyz_depth[4 * k + 3] = 0;
             }
@@ -933,13 +987,22 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
     }
     if (r) return r;
     char* pin = reinterpret_cast<char*>(ctx->pinned);
+    const bool want_pw = pw && px.pose_ref;
     if (nf) {
-        memcpy(pin + ctx->pin_q(), query_xyz, nf * 12);
-        CU(cudaMemcpyAsync(ctx->s_queries.p, pin + ctx->pin_q(), nf * 12, cudaMemcpyHostToDevice, ctx->stream));
-        r = run_associate_stream(ctx, nf, false, true); // also counts M
+        if (pixels) {
+            memcpy(pin + ctx->pin_q(), pixels, nf * 8);
+            CU(cudaMemcpyAsync(ctx->s_pixels.p, pin + ctx->pin_q(), nf * 8, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            memcpy(pin + ctx->pin_q(), query_xyz, nf * 12);
+            CU(cudaMemcpyAsync(ctx->s_queries.p, pin + ctx->pin_q(), nf * 12, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        r = run_associate_stream(ctx, nf, false, true, px); // also counts M
         if (r) return r;
         if (type) CU(cudaMemcpyAsync(pin + ctx->pin_type(), ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
         if (xyz_depth) CU(cudaMemcpyAsync(pin + ctx->pin_xyzd(), ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        if (accepted) CU(cudaMemcpyAsync(pin + ctx->pin_acc(), ctx->s_accepted.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
+        if (undistorted) CU(cudaMemcpyAsync(pin + ctx->pin_und(), ctx->s_undist.p, nf * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_pw) CU(cudaMemcpyAsync(pin + ctx->pin_pw(), ctx->s_pw.p, nf * 24, cudaMemcpyDeviceToHost, ctx->stream));
     }
     if (!nf) { // no feature kernel to piggy-back the cell count on
         k_count_cells<<<dim3(64, 1), 256, 0, ctx->stream>>>(ctx->s_kf.as<KfState>(), ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen);
@@ -951,11 +1014,36 @@ extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_s
     if (r) return r;
     if (nf && type) memcpy(type, pin + ctx->pin_type(), nf);
     if (nf && xyz_depth) memcpy(xyz_depth, pin + ctx->pin_xyzd(), nf * 16);
+    if (nf && accepted) memcpy(accepted, pin + ctx->pin_acc(), nf);
+    if (nf && undistorted) memcpy(undistorted, pin + ctx->pin_und(), nf * 8);
+    if (nf && want_pw) memcpy(pw, pin + ctx->pin_pw(), nf * 24);
     if (n_projected_out) *n_projected_out = kf.n_proj;
     if (m_out) *m_out = kf.m;
     // the fused path keeps no cell array: a later levins_associate() needs levins_build_range_image() first
     ctx->s_image_valid = false;
     return (kf.status || kf.m == 0) ? LEVINS_EMPTY : LEVINS_OK;
+}
+
+extern "C" int levins_keyframe(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins,
+                               const float* query_xyz, size_t nf, int8_t* type, float* xyz_depth, size_t* n_projected_out,
+                               size_t* m_out) {
+    if (!ctx || (!query_xyz && nf)) return fail(ctx, LEVINS_ERR_ARG, "null queries");
+    return keyframe_body(ctx, stamp, ins, n_ins, query_xyz, nullptr, nf, PixelOpts(), type, xyz_depth, nullptr, nullptr, nullptr,
+                         n_projected_out, m_out);
+}
+
+extern "C" int levins_keyframe_pixels(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins,
+                                      const levins_camera* camera, const float* pixels, size_t nf, int undistort,
+                                      const levins_pose* pose_ref, int8_t* type, float* xyz_depth, uint8_t* accepted, double* pw,
+                                      float* undistorted, size_t* n_projected_out, size_t* m_out) {
+    if (!ctx || !camera || (!pixels && nf)) return fail(ctx, LEVINS_ERR_ARG, "null camera or pixels");
+    if (pw && !pose_ref) return fail(ctx, LEVINS_ERR_ARG, "world points need pose_ref");
+    PixelOpts px;
+    px.cam = camera;
+    px.undistort = undistort;
+    px.pose_ref = pose_ref;
+    return keyframe_body(ctx, stamp, ins, n_ins, nullptr, pixels, nf, px, type, xyz_depth, accepted, pw, undistorted, n_projected_out,
+                         m_out);
 }
 
 extern "C" int levins_point_cloud_projection(levins_ctx* ctx, const levins_pose* pose, const levins_point_xyzi* src,

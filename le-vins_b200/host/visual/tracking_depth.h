@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common/device.h"
+#include "common/misc.h"
 #include "le_vins/vins_lidar.h"
 #include "lidar/lidar.h"
 #include "visual/camera.h"
@@ -91,54 +92,61 @@ public:
         return num_succeed;
     }
 
-    // Shared body of depthAssociationReference (tracking.cc:387-465) and depthAssociationMapPoint (489-556):
-    // undistorted reference-frame pixels -> unit rays (f32) -> plane fitting -> gate (type != NONE && isGoodDepth) ->
-    // world point.  `skip` marks features whose reference frame is not frame_ref_ (tracking.cc:401) resp. map points that
-    // are already depth associated (tracking.cc:513).  Returns num_associated; `associated` lists the accepted ones.
-    int depthAssociation(const Camera &camera, const std::vector<Point2f> &pts2d_undis, const std::vector<uint8_t> &skip,
-                         const Pose &frame_ref_pose, std::vector<DepthAssociated> &associated) {
+    // Shared body of depthAssociationReference (tracking.cc:381-465) and depthAssociationMapPoint (489-556), one device call:
+    // tracked reference-frame pixels -> [undistort] -> unit rays (f32) -> plane fitting -> gate (type != NONE &&
+    // isGoodDepth) -> world point.  `skip` marks features whose reference frame is not frame_ref_ (tracking.cc:401) resp. map
+    // points that are already depth associated (tracking.cc:513): they are not evaluated.  `undistort`: the pixels are the raw
+    // tracked ones (pts2d_ref_), Camera::undistortPoints runs on the device too; false when the caller undistorted already.
+    // Returns num_associated; `associated` lists the accepted ones.
+    int depthAssociation(const Camera &camera, const std::vector<Point2f> &pts2d, const std::vector<uint8_t> &skip,
+                         const Pose &frame_ref_pose, std::vector<DepthAssociated> &associated, bool undistort = false) {
         associated.clear();
-        if (pts2d_undis.empty()) return 0; // tracking.cc:372-374 / 483-485
-        std::vector<PointType> unit_sphere_features;
-        unit_sphere_features.reserve(pts2d_undis.size());
-        for (const auto &pts2d : pts2d_undis) { // tracking.cc:387-395 / 496-504
-            PointType point;
-            const Vector3d puc = camera.pixel2unitcam(pts2d);
-            point.x = static_cast<float>(puc[0]);
-            point.y = static_cast<float>(puc[1]);
-            point.z = static_cast<float>(puc[2]);
-            point.intensity = 0;
-            unit_sphere_features.push_back(point);
+        if (pts2d.empty() || unit_sphere_size_ == 0) return 0; // tracking.cc:372-374 / 483-485, 165
+        q_.clear();
+        map_.clear();
+        for (size_t k = 0; k < pts2d.size(); k++) {
+            if (!skip.empty() && skip[k]) continue;
+            q_.insert(q_.end(), {pts2d[k].x, pts2d[k].y});
+            map_.push_back(k);
         }
-        std::vector<MapPointType> types;
-        const int num_succeed = depthAssociationPlaneFitting(unit_sphere_features, skip, types);
-        if (!num_succeed) return 0; // tracking.cc:415-418 / 527-530
-        for (size_t k = 0; k < unit_sphere_features.size(); k++) {
-            const PointType &point = unit_sphere_features[k];
-            const double depth = point.intensity;
-            if ((types[k] == MAPPOINT_NONE) || (!skip.empty() && skip[k]) || !VisualMapPoint::isGoodDepth(depth, 1.0))
-                continue; // tracking.cc:431-435 / 539-542
-            const Vector3d pc(point.x, point.y, point.z);
-            associated.push_back({k, Camera::cam2world(pc, frame_ref_pose), depth, types[k]}); // tracking.cc:437-439
-        }
+        const size_t n = map_.size();
+        if (n == 0) return 0;
+        type_.resize(n);
+        xyzd_.resize(4 * n);
+        accepted_.resize(n);
+        pw_.resize(3 * n);
+        const levins_camera cam = camera.abi();
+        levins_pose pose;
+        levins_host::to_abi(frame_ref_pose, pose);
+        levins_host::check(levins_associate_pixels(levins_host::context(), &cam, q_.data(), n, undistort ? 1 : 0, &pose, type_.data(),
+                                                   xyzd_.data(), accepted_.data(), pw_.data(), nullptr),
+                           "depthAssociation");
+        for (size_t i = 0; i < n; i++)
+            if (accepted_[i])
+                associated.push_back({map_[i], Vector3d(pw_[3 * i], pw_[3 * i + 1], pw_[3 * i + 2]), (double) xyzd_[4 * i + 3],
+                                      static_cast<MapPointType>(type_[i])});
         return static_cast<int>(associated.size());
     }
 
-    int depthAssociationReference(const Camera &camera, const std::vector<Point2f> &pts2d_ref_undis,
+    // tracking.cc:370-480: the pixels are pts2d_ref_ as tracked (undistort = true runs tracking.cc:381-385 on the device)
+    int depthAssociationReference(const Camera &camera, const std::vector<Point2f> &pts2d_ref,
                                   const std::vector<uint8_t> &not_current_ref, const Pose &frame_ref_pose,
-                                  std::vector<DepthAssociated> &associated) {
-        return depthAssociation(camera, pts2d_ref_undis, not_current_ref, frame_ref_pose, associated);
+                                  std::vector<DepthAssociated> &associated, bool undistort = false) {
+        return depthAssociation(camera, pts2d_ref, not_current_ref, frame_ref_pose, associated, undistort);
     }
+    // tracking.cc:482-562: the pixels are the map points' reference-frame keypoints (already undistorted, :489-504)
     int depthAssociationMapPoint(const Camera &camera, const std::vector<Point2f> &pts2d_map_undis,
                                  const std::vector<uint8_t> &already_depth_associated, const Pose &frame_ref_pose,
                                  std::vector<DepthAssociated> &associated) {
-        return depthAssociation(camera, pts2d_map_undis, already_depth_associated, frame_ref_pose, associated);
+        return depthAssociation(camera, pts2d_map_undis, already_depth_associated, frame_ref_pose, associated, false);
     }
 
 private:
     size_t unit_sphere_size_ = 0;
     std::vector<float> q_, xyzd_;
     std::vector<int8_t> type_;
+    std::vector<uint8_t> accepted_;
+    std::vector<double> pw_;
     std::vector<size_t> map_;
 };
 

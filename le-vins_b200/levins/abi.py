@@ -30,7 +30,7 @@ EXPORTS = [
     "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host", "levins_append_raw",
     "levins_append_wait", "levins_ins_window_index", "levins_comm_unique_id", "levins_comm_init", "levins_comm_destroy",
     "levins_gather", "levins_peer_export", "levins_peer_attach", "levins_peer_wait", "levins_peer_detach", "levins_gathered_pointer",
-    "levins_gathered_download", "levins_batch_upload_packed", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
+    "levins_gathered_download", "levins_batch_upload_packed", "levins_associate_pixels", "levins_keyframe_pixels", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
 ]
 
 
@@ -102,6 +102,8 @@ def lib():
             "levins_build_range_image": [vp, vp, sz, vp, sz, vp, vp],
             "levins_associate": [vp, vp, sz, vp, vp, vp, vp, vp],
             "levins_keyframe": [vp, dbl, vp, sz, vp, sz, vp, vp, vp, vp],
+            "levins_associate_pixels": [vp, vp, vp, sz, i32, vp, vp, vp, vp, vp, vp],
+            "levins_keyframe_pixels": [vp, dbl, vp, sz, vp, vp, sz, i32, vp, vp, vp, vp, vp, vp, vp, vp],
             "levins_point_cloud_projection": [vp, vp, vp, vp, sz],
             "levins_batch_upload": [vp, vp, sz, vp, sz, vp, sz, vp, sz],
             "levins_batch_upload_packed": [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz],
@@ -267,6 +269,40 @@ class Context:
         st = self._check(lib().levins_keyframe(self._h, float(stamp), _p(ins), len(ins), _p(q), f, _p(ty), _p(xd),
                                                C.byref(npj), C.byref(m)))
         return {"status": st, "type": ty, "xyz_depth": xd, "n_projected": npj.value, "m": m.value}
+
+    @staticmethod
+    def _camera(intr, dist):
+        cam = np.zeros(10, np.float64)
+        cam[:5] = np.asarray(intr, np.float64)[:5]
+        d = np.asarray(dist if dist is not None else [], np.float64)
+        cam[5:5 + len(d)] = d[:5]
+        return cam
+
+    def associate_pixels(self, intr, dist, pixels, undistort=True, pose_ref=None):
+        cam = self._camera(intr, dist)
+        px = np.ascontiguousarray(pixels, np.float32).reshape(-1, 2)
+        f = len(px)
+        pose = None if pose_ref is None else np.ascontiguousarray(pose_ref, np.float64)
+        out = {"type": np.zeros(f, np.int8), "xyz_depth": np.zeros((f, 4), np.float32), "accepted": np.zeros(f, np.uint8),
+               "pw": np.zeros((f, 3), np.float64) if pose is not None else None, "undistorted": np.zeros((f, 2), np.float32)}
+        self._check(lib().levins_associate_pixels(self._h, _p(cam), _p(px), f, int(bool(undistort)), _p(pose), _p(out["type"]),
+                                                  _p(out["xyz_depth"]), _p(out["accepted"]), _p(out["pw"]), _p(out["undistorted"])))
+        return out
+
+    def keyframe_pixels(self, stamp, ins, intr, dist, pixels, undistort=True, pose_ref=None):
+        ins = np.ascontiguousarray(ins, INS)
+        cam = self._camera(intr, dist)
+        px = np.ascontiguousarray(pixels, np.float32).reshape(-1, 2)
+        f = len(px)
+        pose = None if pose_ref is None else np.ascontiguousarray(pose_ref, np.float64)
+        out = {"type": np.zeros(f, np.int8), "xyz_depth": np.zeros((f, 4), np.float32), "accepted": np.zeros(f, np.uint8),
+               "pw": np.zeros((f, 3), np.float64) if pose is not None else None, "undistorted": np.zeros((f, 2), np.float32)}
+        npj, m = C.c_size_t(0), C.c_size_t(0)
+        out["status"] = self._check(lib().levins_keyframe_pixels(
+            self._h, float(stamp), _p(ins), len(ins), _p(cam), _p(px), f, int(bool(undistort)), _p(pose), _p(out["type"]),
+            _p(out["xyz_depth"]), _p(out["accepted"]), _p(out["pw"]), _p(out["undistorted"]), C.byref(npj), C.byref(m)))
+        out["n_projected"], out["m"] = npj.value, m.value
+        return out
 
     def point_cloud_projection(self, pose, cloud):
         pose = np.ascontiguousarray(pose, np.float64)

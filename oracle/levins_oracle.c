@@ -1287,6 +1287,41 @@ void orc_cam2world(const double pc[3], const orc_pose *pose, double pw[3]) {
     pw[1] = r[1] + pose->t[1];
     pw[2] = r[2] + pose->t[2];
 }
+/* cv::undistortPoints(pts, pts, K, D, Mat(), K) as Camera::undistortPoints calls it (camera.cc:72-74; OpenCV >= 3.2,
+ * README.md:40): OpenCV's cvUndistortPointsInternal with the default criteria (5 fixed-point iterations, no epsilon test),
+ * R = identity and P = K, restated operation for operation.  D = (k1, k2, p1, p2, k3); OpenCV normalises with fx, fy, cx, cy
+ * only (the skew K[0][1] enters when the point is projected back with P = K).  The input pixel is f32, the arithmetic f64,
+ * the result is rounded to f32 (Point2f).  Checked bit for bit against this image's cv2.undistortPoints in
+ * tests/test_oracle.py. */
+void orc_undistort_points(const double intr[5], const double dist[5], const float *px_in, size_t n, float *px_out) {
+    const double fx = intr[0], fy = intr[1], cx = intr[2], cy = intr[3], skew = intr[4];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    const double k0 = dist[0], k1 = dist[1], k2 = dist[2], k3 = dist[3], k4 = dist[4];
+    for (size_t i = 0; i < n; i++) {
+        const double u = (double) px_in[2 * i], v = (double) px_in[2 * i + 1];
+        double x = (u - cx) * ifx, y = (v - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int j = 0; j < 5; j++) {
+            const double r2 = x * x + y * y;
+            const double icdist = (1 + ((0 * r2 + 0) * r2 + 0) * r2) / (1 + ((k4 * r2 + k1) * r2 + k0) * r2);
+            if (icdist < 0) {
+                x = (u - cx) * ifx;
+                y = (v - cy) * ify;
+                break;
+            }
+            const double deltaX = 2 * k2 * x * y + k3 * (r2 + 2 * x * x) + 0 * r2 + 0 * r2 * r2;
+            const double deltaY = k2 * (r2 + 2 * y * y) + 2 * k3 * x * y + 0 * r2 + 0 * r2 * r2;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+        }
+        const double xx = fx * x + skew * y + cx;
+        const double yy = 0 * x + fy * y + cy;
+        const double ww = 1. / (0 * x + 0 * y + 1);
+        px_out[2 * i] = (float) (xx * ww);
+        px_out[2 * i + 1] = (float) (yy * ww);
+    }
+}
+
 int orc_is_good_depth(double depth, double scale) { return (depth > NEAREST_DEPTH) && (depth < FARTHEST_DEPTH * scale); }
 
 /* ------------------------------------------------------------------------------------------

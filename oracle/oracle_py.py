@@ -349,6 +349,17 @@ def cam2world(pc, pose):
     return o
 
 
+def undistort_points(intr, dist, px):
+    """Camera::undistortPoints (camera.cc:72-74) on an (F, 2) f32 pixel array; dist = k1 k2 p1 p2 k3."""
+    intr = _c(intr, np.float64)
+    dist = _c(np.concatenate([np.asarray(dist, np.float64), np.zeros(5)])[:5], np.float64)
+    px = _c(px, np.float32).reshape(-1, 2)
+    out = np.zeros_like(px)
+    lib().orc_undistort_points.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib().orc_undistort_points(_p(intr), _p(dist), _p(px), len(px), _p(out))
+    return out
+
+
 def is_good_depth(depth, scale=1.0) -> bool:
     return bool(lib().orc_is_good_depth(float(depth), float(scale)))
 

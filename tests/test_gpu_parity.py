@@ -305,3 +305,41 @@ def test_cell_ids_on_rounding_boundaries(oracle, built_lib, libm_mode):
         else:  # CUDA's double atan2 is not glibc's; on-boundary points may legitimately fall either way
             assert diff < 0.02 * ref["m"]
     c.close()
+
+
+def test_feature_side_on_the_device(ctx, oracle):
+    """levins_associate_pixels / levins_keyframe_pixels (SURVEY 8f rank 2): Camera::undistortPoints -> pixel2unitcam -> f32
+    query -> plane fitting -> accept gate -> cam2world, against the oracle's restatement of the same chain
+    (tracking.cc:381-395, 431-439; camera.cc:72-74, 123-151).  The oracle's undistortion is itself pinned bit for bit against
+    cv2.undistortPoints in tests/test_oracle.py."""
+    kf = make_keyframe(cfg=2, pts_per_scan=6000)
+    ctx.set_extrinsics(kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l)
+    dist = np.array([-0.1080, 0.1050, -1.2872e-4, 5.7923e-5, -0.0222])  # config/le_vins_r3live.yaml:51
+    rng = np.random.default_rng(5)
+    w, h = kf.rig.resolution
+    px = np.stack([rng.uniform(5, w - 5, 400), rng.uniform(5, h - 5, 400)], -1).astype(np.float32)
+    ok, pose_ref = oracle.get_pose_from_ins_window(kf.ins, kf.rig.pose_b_c, kf.stamp)
+    ref1 = cached_stage1(oracle, dict(cfg=2, pts_per_scan=6000), kf)
+    ref2 = oracle.range_image(ref1["cloud"])
+    for undistort in (True, False):
+        und = oracle.undistort_points(kf.rig.intr, dist, px) if undistort else px
+        q = np.stack([oracle.pixel2unitcam(kf.rig.intr, u, v) for u, v in und]).astype(np.float32)
+        ref3 = oracle.associate(ref2["unit_sphere"], q)
+        depth = ref3["xyz_depth"][:, 3].astype(np.float64)
+        acc = (ref3["type"] != -1) & (depth > 1.0) & (depth < 200.0)
+        pw = np.zeros((len(px), 3))
+        for k in np.nonzero(acc)[0]:
+            pw[k] = oracle.cam2world(ref3["xyz_depth"][k, :3].astype(np.float64), pose_ref)
+        # stage-wise: the image built from the oracle's cloud
+        ctx.build_range_image(ref1["cloud"])
+        got = ctx.associate_pixels(kf.rig.intr, dist, px, undistort=undistort, pose_ref=pose_ref)
+        # fused keyframe
+        ctx.buffer_clear()
+        ctx.append_scan(kf.points)
+        fused = ctx.keyframe_pixels(kf.stamp, kf.ins, kf.rig.intr, dist, px, undistort=undistort, pose_ref=pose_ref)
+        for g in (got, fused):
+            assert g["undistorted"].tobytes() == und.tobytes()
+            assert np.array_equal(g["type"], ref3["type"]) and g["xyz_depth"].tobytes() == ref3["xyz_depth"].tobytes()
+            assert np.array_equal(g["accepted"].astype(bool), acc) and acc.sum() > 30
+            assert np.array_equal(g["pw"], pw)
+        assert fused["n_projected"] == ref1["n"] and fused["m"] == ref2["m"]

@@ -493,3 +493,20 @@ def test_whole_keyframe_driver_consistency(oracle):
     assert whole["m"] == r2["m"] and whole["n_projected"] == r1["n"]
     assert np.array_equal(whole["type"], r3["type"]) and np.array_equal(whole["xyz_depth"], r3["xyz_depth"])
     assert (whole["type"] == 1).sum() > 10
+
+
+def test_undistort_points_equals_opencv(oracle):
+    """orc_undistort_points restates cv::undistortPoints(pts, pts, K, D, Mat(), K) (camera.cc:72-74): bit for bit against the
+    OpenCV in this image, with radial + tangential coefficients, with k3 and with a skewed K."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    cases = [((863.4241, 863.4171, 640.6808, 518.3392, 0.0), (-0.1080, 0.1050, -1.2872e-4, 5.7923e-5, -0.0222)),
+             ((593.5669, 593.8849, 513.3945, 401.9319, 0.0), (-0.33, 0.11, 0.0005, -0.0003, 0.0)),
+             ((458.654, 457.296, 367.215, 248.375, 0.7), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0)),
+             ((458.654, 457.296, 367.215, 248.375, 0.0), (0.0, 0.0, 0.0, 0.0, 0.0))]
+    for intr, dist in cases:
+        px = np.stack([rng.uniform(-50, 1400, 30000), rng.uniform(-50, 1100, 30000)], -1).astype(np.float32)
+        K = np.array([[intr[0], intr[4], intr[2]], [0, intr[1], intr[3]], [0, 0, 1]])
+        ref = cv2.undistortPoints(px.reshape(-1, 1, 2), K, np.array(dist).reshape(5, 1), None, K).reshape(-1, 2)
+        got = oracle.undistort_points(intr, dist, px)
+        assert got.tobytes() == ref.tobytes()
