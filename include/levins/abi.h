@@ -247,6 +247,28 @@ int levins_point_cloud_projection(levins_ctx *ctx, const levins_pose *pose, cons
                                   levins_point_xyzi *dst, size_t n);
 
 /* ------------------------------------------------------------------------------------------------
+ * batched plane geometry of lidar::PointCloudCommon (no call site in the reference, kept for the surface)
+ * and the consumer of the depths in the optimiser (rank 4).  Host arrays in and out; one thread per group / factor.
+ * ------------------------------------------------------------------------------------------------ */
+/* PointCloudCommon::planeEstimation (pointcloud.cc:73-105) on n_groups groups of PLANE_ESTIMATION_POINT_SZIE = 5 points:
+ * valid[n], unit_normal[3 n], norm_inverse[n], distance[5 n] (filled up to and including the first failing point, like the
+ * reference's `distance` vector; n_distance[n] says how many), each nullable. */
+int levins_plane_estimation_batch(levins_ctx *ctx, const levins_point_xyzi *points, size_t n_groups, double threshold,
+                                  uint8_t *valid, double *unit_normal, double *norm_inverse, double *distance, int32_t *n_distance);
+/* PointCloudCommon::pointToPlaneStd (pointcloud.cc:111-190): n_groups x (group_size neighbours, one target) -> sigma[n]. */
+int levins_point_to_plane_std_batch(levins_ctx *ctx, const levins_point_xyzi *nearest, size_t group_size,
+                                    const levins_point_xyzi *targets, size_t n_groups, double point_std, double *std_out);
+/* DepthFactor (factors/depth_factor.h:38-42) as Optimizer::addReprojectionFactors adds it for depth-associated map points
+ * (optimizer.cc:659-665: sigma = Tracking::ASSOCIATE_DEPTH_STD, ceres::HuberLoss(1.0)): residual (depth - 1 / invdepth) / sigma,
+ * Jacobian d residual / d invdepth, robustified cost 0.5 rho(residual^2).  huber_a <= 0: no loss function.  Each output nullable. */
+int levins_depth_factor_batch(levins_ctx *ctx, const double *depth, const double *invdepth, size_t n, double sigma, double huber_a,
+                              double *residual, double *jacobian, double *cost);
+/* Optimizer::visualOutlierCullingByChi2 (optimizer.cc:752-783) on n residual blocks of `dim` values: cost = r^T r (nullable),
+ * outlier = cost > threshold (5.991 in the reference). */
+int levins_chi2_culling_batch(levins_ctx *ctx, const double *residuals, size_t n, size_t dim, double threshold, double *cost,
+                              uint8_t *outlier);
+
+/* ------------------------------------------------------------------------------------------------
  * batch API -- many independent keyframes resident in HBM (BASELINE config 5 and the bench workload)
  * ------------------------------------------------------------------------------------------------ */
 typedef struct levins_keyframe_desc {

@@ -973,4 +973,44 @@ __device__ inline void colpiv_qr_solve_5x3(const double (*P)[3], double* x) {
         }
 }
 
+// ------------------------------------------------------------------------------------------------
+// symmetric 3x3 eigen-decomposition (cyclic Jacobi): stands in for the Eigen::EigenSolver call on the neighbourhood
+// covariance at pointcloud.cc:132-134.  w: eigenvalues, v: eigenvectors as columns (row-major).
+// ------------------------------------------------------------------------------------------------
+__device__ inline void sym_eigen3(const double* a_in, double* w, double* v) {
+    double a[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) a[i][j] = a_in[3 * i + j];
+    for (int sweep = 0; sweep < 60; sweep++) {
+        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; p++)
+            for (int q = p + 1; q < 3; q++) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                for (int k = 0; k < 3; k++) {
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = cs * akp - sn * akq;
+                    a[k][q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < 3; k++) {
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = cs * apk - sn * aqk;
+                    a[q][k] = sn * apk + cs * aqk;
+                }
+                for (int k = 0; k < 3; k++) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = cs * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + cs * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 3; i++) {
+        w[i] = a[i][i];
+        for (int j = 0; j < 3; j++) v[3 * i + j] = V[i][j];
+    }
+}
+
 } // namespace lv

@@ -1586,4 +1586,172 @@ __global__ void __launch_bounds__(256) k_project(const PointXYZI* __restrict__ s
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// Batched forms of the plane geometry of lidar::PointCloudCommon and of the consumer of the depths in the
+// optimiser (rank 4).  One thread per group / factor; reference operation order, no contraction.
+// ------------------------------------------------------------------------------------------------
+// PointCloudCommon::planeEstimation (pointcloud.cc:73-105): groups of 5 points
+__global__ void __launch_bounds__(128) k_plane_estimation(const PointXYZI* __restrict__ pts, unsigned n_groups, double threshold,
+                                                          unsigned char* valid, double* unit_normal, double* norm_inverse,
+                                                          double* distance, int* n_distance) {
+    const unsigned g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= n_groups) return;
+    double P[5][3];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pts + 5 * (size_t) g + k));
+        P[k][0] = (double) p.x;
+        P[k][1] = (double) p.y;
+        P[k][2] = (double) p.z;
+    }
+    double nv[3];
+    colpiv_qr_solve_5x3(P, nv);                       // :89
+    const double ninv = 1.0 / sqrt(v3_dot(nv, nv));    // :92
+    const double un[3] = {nv[0] * ninv, nv[1] * ninv, nv[2] * ninv}; // :93
+    int nd = 0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 5; k++) { // :96-103: the distances up to and including the first failing point
+        if (ok) {
+            const double dis = v3_dot(un, P[k]) + ninv;
+            distance[5 * (size_t) g + k] = dis;
+            nd++;
+            if (fabs(dis) > threshold) ok = false;
+        } else {
+            distance[5 * (size_t) g + k] = 0.0;
+        }
+    }
+    valid[g] = ok ? 1 : 0;
+    unit_normal[3 * (size_t) g] = un[0];
+    unit_normal[3 * (size_t) g + 1] = un[1];
+    unit_normal[3 * (size_t) g + 2] = un[2];
+    norm_inverse[g] = ninv;
+    n_distance[g] = nd;
+}
+
+// PointCloudCommon::pointToPlaneStd (pointcloud.cc:111-190): groups of `gs` neighbours + one target each
+__global__ void __launch_bounds__(128) k_point_to_plane_std(const PointXYZI* __restrict__ nearest, unsigned gs, const PointXYZI* __restrict__ targets,
+                                                            unsigned n_groups, double point_std, double* out) {
+    const unsigned g = blockIdx.x * 128 + threadIdx.x;
+    if (g >= n_groups) return;
+    const PointXYZI* __restrict__ pts = nearest + (size_t) g * gs;
+    const double pvv = point_std * point_std; // :113-114
+    const double inv = 1.0 / (double) gs;     // :117
+    double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, center[3] = {0, 0, 0};
+    for (unsigned i = 0; i < gs; i++) { // :120-126
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pts + i));
+        const double pv[3] = {(double) p.x, (double) p.y, (double) p.z};
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            center[r] += pv[r];
+#pragma unroll
+            for (int c = 0; c < 3; c++) cov[3 * r + c] += pv[r] * pv[c];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) center[r] *= inv; // :127
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) cov[3 * r + c] = cov[3 * r + c] * inv - center[r] * center[c]; // :128
+    double evals[3], evecs[9];
+    sym_eigen3(cov, evals, evecs); // :131-136
+    int emin = 0;                  // :138-140
+    for (int m = 1; m < 3; m++)
+        if (evals[m] < evals[emin]) emin = m;
+    double nrm[3], ev[3][3]; // ev[m] = eigenvector m
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) ev[m][r] = evecs[3 * r + m];
+#pragma unroll
+    for (int r = 0; r < 3; r++) nrm[r] = emin == 0 ? ev[0][r] : (emin == 1 ? ev[1][r] : ev[2][r]); // :151
+    const double ev_min = emin == 0 ? evals[0] : (emin == 1 ? evals[1] : evals[2]);
+    double plane_cov[6][6];
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) plane_cov[r][c] = 0;
+    for (unsigned i = 0; i < gs; i++) { // :160-176
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pts + i));
+        const double d[3] = {(double) p.x - center[0], (double) p.y - center[1], (double) p.z - center[2]};
+        double F[3][3];
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const bool skip = m == emin;
+            const double scale = skip ? 0.0 : inv / (ev_min - evals[m]);
+            const double de = d[0] * ev[m][0] + d[1] * ev[m][1] + d[2] * ev[m][2], dn = d[0] * nrm[0] + d[1] * nrm[1] + d[2] * nrm[2];
+#pragma unroll
+            for (int c = 0; c < 3; c++) F[m][c] = skip ? 0.0 : scale * (de * nrm[c] + dn * ev[m][c]);
+        }
+        double J[6][3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double sacc = 0;
+#pragma unroll
+                for (int m = 0; m < 3; m++) sacc += evecs[3 * r + m] * F[m][c];
+                J[r][c] = sacc;
+            }
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) J[3 + r][c] = r == c ? inv : 0.0;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                double sum = 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) sum += J[r][k] * J[c][k];
+                plane_cov[r][c] += pvv * sum;
+            }
+    }
+    const float4 t = __ldg(reinterpret_cast<const float4*>(targets + g));
+    const double jac[6] = {(double) t.x - center[0], (double) t.y - center[1], (double) t.z - center[2], -nrm[0], -nrm[1], -nrm[2]}; // :179-181
+    double var = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) var += jac[r] * plane_cov[r][c] * jac[c]; // :184
+    var += pvv * (nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);     // :186
+    out[g] = sqrt(var);
+}
+
+// DepthFactor (factors/depth_factor.h:38-42) as the optimiser adds it (optimizer.cc:659-665: sigma = ASSOCIATE_DEPTH_STD,
+// ceres::HuberLoss(1.0)): residual r = (depth - 1 / invdepth) / sigma, its Jacobian d r / d invdepth = 1 / (sigma invdepth^2)
+// (what ceres' autodiff yields), and the robustified cost 0.5 rho(r^2) with ceres' Huber rho(s) = s for s <= a^2, else
+// 2 a sqrt(s) - a^2 (Ceres Solver >= 2.1.0, README.md:48; loss_function.h).  huber_a <= 0: no loss function.
+__global__ void __launch_bounds__(256) k_depth_factor(const double* __restrict__ depth, const double* __restrict__ invdepth, unsigned n,
+                                                      double sigma, double huber_a, double* residual, double* jacobian, double* cost) {
+    const unsigned k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    const double rho_inv = invdepth[k];
+    const double r = (depth[k] - 1.0 / rho_inv) / sigma;
+    const double s = r * r;
+    double rho = s;
+    if (huber_a > 0) {
+        const double b = huber_a * huber_a;
+        if (s > b) rho = 2.0 * huber_a * sqrt(s) - b;
+    }
+    if (residual) residual[k] = r;
+    if (jacobian) jacobian[k] = (1.0 / (rho_inv * rho_inv)) / sigma;
+    if (cost) cost[k] = 0.5 * rho;
+}
+
+// Optimizer::visualOutlierCullingByChi2 (optimizer.cc:752-783): cost = r^T r per residual block, outlier iff cost > threshold
+__global__ void __launch_bounds__(256) k_chi2(const double* __restrict__ residuals, unsigned n, unsigned dim, double threshold, double* cost,
+                                              unsigned char* outlier) {
+    const unsigned k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n) return;
+    double c = 0;
+    for (unsigned i = 0; i < dim; i++) {
+        const double r = residuals[(size_t) k * dim + i];
+        c += r * r;
+    }
+    if (cost) cost[k] = c;
+    outlier[k] = c > threshold ? 1 : 0;
+}
+
 } // namespace lv

@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <cstring>
 #include <deque>
+#include <initializer_list>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -69,6 +70,7 @@ struct levins_ctx {
     DevBuf raw_stage, raw_blocks, raw_misc; // levins_append_raw: records, per-block counts, {min, max, result}
     DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2, s_nn, s_nn_meta;
     DevBuf s_pixels, s_undist, s_accepted, s_pw; // feature side on the device (levins_associate_pixels)
+    DevBuf scratch; // inputs / outputs of the small batched entry points (plane geometry, depth factors)
     DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
     DevBuf s_in_cloud; // explicit cloud uploaded by build_range_image
     DevBuf s_zbuf, s_cells, s_c2c, s_unit, s_winner;
@@ -525,7 +527,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
-                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw})
+                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw, &ctx->scratch})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -1064,6 +1066,125 @@ extern "C" int levins_point_cloud_projection(levins_ctx* ctx, const levins_pose*
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(dst, d_dst, n * sizeof(PointXYZI), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LEVINS_OK;
+}
+
+// =================================================================================================
+// batched plane geometry and depth-factor / chi-square batches (rank 4)
+// =================================================================================================
+namespace {
+// one scratch allocation carved into 256-byte aligned pieces
+struct Carver {
+    char* base;
+    size_t off = 0;
+    explicit Carver(void* p) : base(static_cast<char*>(p)) {}
+    template <typename T> T* take(size_t n) {
+        T* r = reinterpret_cast<T*>(base + off);
+        off += (n * sizeof(T) + 255) & ~size_t(255);
+        return r;
+    }
+    static size_t need(std::initializer_list<size_t> bytes) {
+        size_t t = 0;
+        for (size_t b : bytes) t += (b + 255) & ~size_t(255);
+        return t;
+    }
+};
+} // namespace
+
+extern "C" int levins_plane_estimation_batch(levins_ctx* ctx, const levins_point_xyzi* points, size_t n_groups, double threshold,
+                                             uint8_t* valid, double* unit_normal, double* norm_inverse, double* distance,
+                                             int32_t* n_distance) {
+    if (!ctx || (!points && n_groups)) return fail(ctx, LEVINS_ERR_ARG, "null points");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n_groups == 0) return LEVINS_OK;
+    if (n_groups > 0x7fffffffull / 5) return fail(ctx, LEVINS_ERR_ARG, "too many groups");
+    const size_t n = n_groups;
+    CU(ctx->scratch.ensure(Carver::need({n * 5 * sizeof(PointXYZI), n, n * 24, n * 8, n * 40, n * 4})));
+    Carver c(ctx->scratch.p);
+    PointXYZI* d_pts = c.take<PointXYZI>(n * 5);
+    unsigned char* d_valid = c.take<unsigned char>(n);
+    double* d_un = c.take<double>(n * 3);
+    double* d_ninv = c.take<double>(n);
+    double* d_dist = c.take<double>(n * 5);
+    int* d_nd = c.take<int>(n);
+    CU(cudaMemcpyAsync(d_pts, points, n * 5 * sizeof(PointXYZI), cudaMemcpyHostToDevice, ctx->stream));
+    k_plane_estimation<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(d_pts, (unsigned) n, threshold, d_valid, d_un, d_ninv, d_dist, d_nd);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (valid) CU(cudaMemcpyAsync(valid, d_valid, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (unit_normal) CU(cudaMemcpyAsync(unit_normal, d_un, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    if (norm_inverse) CU(cudaMemcpyAsync(norm_inverse, d_ninv, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (distance) CU(cudaMemcpyAsync(distance, d_dist, n * 40, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_distance) CU(cudaMemcpyAsync(n_distance, d_nd, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LEVINS_OK;
+}
+
+extern "C" int levins_point_to_plane_std_batch(levins_ctx* ctx, const levins_point_xyzi* nearest, size_t group_size,
+                                               const levins_point_xyzi* targets, size_t n_groups, double point_std, double* std_out) {
+    if (!ctx || !std_out || ((!nearest || !targets) && n_groups) || group_size == 0) return fail(ctx, LEVINS_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n_groups == 0) return LEVINS_OK;
+    if (n_groups > 0x7fffffffull || group_size > 0xffffu) return fail(ctx, LEVINS_ERR_ARG, "too many groups");
+    const size_t n = n_groups;
+    CU(ctx->scratch.ensure(Carver::need({n * group_size * sizeof(PointXYZI), n * sizeof(PointXYZI), n * 8})));
+    Carver c(ctx->scratch.p);
+    PointXYZI* d_near = c.take<PointXYZI>(n * group_size);
+    PointXYZI* d_tgt = c.take<PointXYZI>(n);
+    double* d_out = c.take<double>(n);
+    CU(cudaMemcpyAsync(d_near, nearest, n * group_size * sizeof(PointXYZI), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_tgt, targets, n * sizeof(PointXYZI), cudaMemcpyHostToDevice, ctx->stream));
+    k_point_to_plane_std<<<(unsigned) ((n + 127) / 128), 128, 0, ctx->stream>>>(d_near, (unsigned) group_size, d_tgt, (unsigned) n, point_std, d_out);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(std_out, d_out, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LEVINS_OK;
+}
+
+extern "C" int levins_depth_factor_batch(levins_ctx* ctx, const double* depth, const double* invdepth, size_t n, double sigma,
+                                         double huber_a, double* residual, double* jacobian, double* cost) {
+    if (!ctx || ((!depth || !invdepth) && n) || !(sigma > 0)) return fail(ctx, LEVINS_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return LEVINS_OK;
+    if (n > 0x7fffffffull) return fail(ctx, LEVINS_ERR_ARG, "too many factors");
+    CU(ctx->scratch.ensure(Carver::need({n * 8, n * 8, n * 8, n * 8, n * 8})));
+    Carver c(ctx->scratch.p);
+    double *d_depth = c.take<double>(n), *d_inv = c.take<double>(n), *d_r = c.take<double>(n), *d_j = c.take<double>(n), *d_c = c.take<double>(n);
+    CU(cudaMemcpyAsync(d_depth, depth, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_inv, invdepth, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_depth_factor<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(d_depth, d_inv, (unsigned) n, sigma, huber_a, d_r, d_j, d_c);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (residual) CU(cudaMemcpyAsync(residual, d_r, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (jacobian) CU(cudaMemcpyAsync(jacobian, d_j, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cost) CU(cudaMemcpyAsync(cost, d_c, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return LEVINS_OK;
+}
+
+extern "C" int levins_chi2_culling_batch(levins_ctx* ctx, const double* residuals, size_t n, size_t dim, double threshold, double* cost,
+                                         uint8_t* outlier) {
+    if (!ctx || !outlier || (!residuals && n) || dim == 0) return fail(ctx, LEVINS_ERR_ARG, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    if (n == 0) return LEVINS_OK;
+    if (n > 0x7fffffffull || dim > 64) return fail(ctx, LEVINS_ERR_ARG, "too many residual blocks or dimensions");
+    CU(ctx->scratch.ensure(Carver::need({n * dim * 8, n * 8, n})));
+    Carver c(ctx->scratch.p);
+    double* d_r = c.take<double>(n * dim);
+    double* d_c = c.take<double>(n);
+    unsigned char* d_o = c.take<unsigned char>(n);
+    CU(cudaMemcpyAsync(d_r, residuals, n * dim * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_chi2<<<(unsigned) ((n + 255) / 256), 256, 0, ctx->stream>>>(d_r, (unsigned) n, (unsigned) dim, threshold, d_c, d_o);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (cost) CU(cudaMemcpyAsync(cost, d_c, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(outlier, d_o, n, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return LEVINS_OK;
 }

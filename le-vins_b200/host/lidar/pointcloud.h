@@ -9,7 +9,6 @@
 #include <vector>
 
 #include "common/device.h"
-#include "common/small_linalg.h"
 #include "common/types.h"
 #include "lidar/lidar.h"
 
@@ -59,86 +58,50 @@ public:
         return dx * dx + (dy * dy + dz * dz);
     }
 
-    // pointcloud.cc:73-105 (no call site in the reference; kept for the drop-in surface)
+    // pointcloud.cc:73-105 (no call site in the reference; kept for the drop-in surface).  GPU: k_plane_estimation, one thread
+    // per group of 5 points; the single-group form is the batch of one.
     static bool planeEstimation(const PointVector &points, double threshold, Vector3d &unit_normal_vector, double &norm_inverse,
                                 std::vector<double> &distance) {
         if (points.size() < (size_t) PLANE_ESTIMATION_POINT_SZIE) return false;
-        double A[15], b[5], n[3];
-        for (int k = 0; k < PLANE_ESTIMATION_POINT_SZIE; k++) {
-            A[3 * k] = points[k].x;
-            A[3 * k + 1] = points[k].y;
-            A[3 * k + 2] = points[k].z;
-            b[k] = -1.0;
-        }
-        levins_host::colpiv_qr_solve_5x3(A, b, n); // A.colPivHouseholderQr().solve(b)
-        const Vector3d normal_vector(n[0], n[1], n[2]);
-        norm_inverse = 1.0 / normal_vector.norm();
-        unit_normal_vector = normal_vector * norm_inverse;
-        distance.clear();
-        for (int k = 0; k < PLANE_ESTIMATION_POINT_SZIE; k++) {
-            const double dis = unit_normal_vector.dot(Vector3d(points[k].x, points[k].y, points[k].z)) + norm_inverse;
-            distance.push_back(dis);
-            if (std::fabs(dis) > threshold) return false;
-        }
-        return true;
+        uint8_t valid = 0;
+        double un[3], dist[5];
+        int32_t nd = 0;
+        levins_host::check(levins_plane_estimation_batch(levins_host::context(), reinterpret_cast<const levins_point_xyzi *>(points.data()), 1,
+                                                         threshold, &valid, un, &norm_inverse, dist, &nd),
+                           "planeEstimation");
+        unit_normal_vector = Vector3d(un[0], un[1], un[2]);
+        distance.assign(dist, dist + nd);
+        return valid != 0;
+    }
+    // many groups at once: points holds 5 consecutive points per group
+    static void planeEstimationBatch(const PointVector &points, double threshold, std::vector<uint8_t> &valid,
+                                     std::vector<double> &unit_normals, std::vector<double> &norm_inverses) {
+        const size_t n = points.size() / PLANE_ESTIMATION_POINT_SZIE;
+        valid.resize(n);
+        unit_normals.resize(3 * n);
+        norm_inverses.resize(n);
+        levins_host::check(levins_plane_estimation_batch(levins_host::context(), reinterpret_cast<const levins_point_xyzi *>(points.data()), n,
+                                                         threshold, valid.data(), unit_normals.data(), norm_inverses.data(), nullptr, nullptr),
+                           "planeEstimationBatch");
     }
 
     // pointcloud.cc:111-190 (no call site in the reference): point-to-plane sigma by first-order covariance propagation
-    // through the eigen-decomposition of the neighbourhood covariance
+    // through the eigen-decomposition of the neighbourhood covariance.  GPU: k_point_to_plane_std.
     static double pointToPlaneStd(const PointVector &nearest, const PointType &target, double point_std) {
-        const double pvv = point_std * point_std;
-        const size_t point_size = nearest.size();
-        const double inv = 1.0 / static_cast<double>(point_size);
-        double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, center[3] = {0, 0, 0};
-        for (const auto &p : nearest) {
-            const double pv[3] = {p.x, p.y, p.z};
-            for (int i = 0; i < 3; i++) {
-                center[i] += pv[i];
-                for (int j = 0; j < 3; j++) cov[3 * i + j] += pv[i] * pv[j];
-            }
-        }
-        for (int i = 0; i < 3; i++) center[i] *= inv;
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) cov[3 * i + j] = cov[3 * i + j] * inv - center[i] * center[j];
-        double evals[3], evecs[9]; // evecs column m = evecs[3*i + m]
-        levins_host::sym_eigen_3x3(cov, evals, evecs);
-        int emin = 0;
-        for (int m = 1; m < 3; m++)
-            if (evals[m] < evals[emin]) emin = m;
-        const double nrm[3] = {evecs[emin], evecs[3 + emin], evecs[6 + emin]};
-        double plane_cov[6][6] = {};
-        for (size_t i = 0; i < point_size; i++) {
-            const double d[3] = {nearest[i].x - center[0], nearest[i].y - center[1], nearest[i].z - center[2]};
-            double F[3][3] = {};
-            for (int m = 0; m < 3; m++) {
-                if (m == emin) continue;
-                const double em[3] = {evecs[m], evecs[3 + m], evecs[6 + m]};
-                const double scale = inv / (evals[emin] - evals[m]);
-                // row m = scale * d^T (e_m n^T + n e_m^T)
-                const double de = d[0] * em[0] + d[1] * em[1] + d[2] * em[2], dn = d[0] * nrm[0] + d[1] * nrm[1] + d[2] * nrm[2];
-                for (int c = 0; c < 3; c++) F[m][c] = scale * (de * nrm[c] + dn * em[c]);
-            }
-            double J[6][3] = {};
-            for (int r = 0; r < 3; r++)
-                for (int c = 0; c < 3; c++) {
-                    double s = 0;
-                    for (int m = 0; m < 3; m++) s += evecs[3 * r + m] * F[m][c];
-                    J[r][c] = s;
-                }
-            for (int r = 0; r < 3; r++) J[3 + r][r] = inv;
-            for (int r = 0; r < 6; r++)
-                for (int c = 0; c < 6; c++) {
-                    double s = 0;
-                    for (int k = 0; k < 3; k++) s += J[r][k] * J[c][k];
-                    plane_cov[r][c] += pvv * s;
-                }
-        }
-        const double jac[6] = {target.x - center[0], target.y - center[1], target.z - center[2], -nrm[0], -nrm[1], -nrm[2]};
-        double var = 0;
-        for (int r = 0; r < 6; r++)
-            for (int c = 0; c < 6; c++) var += jac[r] * plane_cov[r][c] * jac[c];
-        var += pvv * (nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
-        return std::sqrt(var);
+        double out = 0;
+        levins_host::check(levins_point_to_plane_std_batch(levins_host::context(), reinterpret_cast<const levins_point_xyzi *>(nearest.data()),
+                                                           nearest.size(), reinterpret_cast<const levins_point_xyzi *>(&target), 1, point_std,
+                                                           &out),
+                           "pointToPlaneStd");
+        return out;
+    }
+    static void pointToPlaneStdBatch(const PointVector &nearest, size_t group_size, const PointVector &targets, double point_std,
+                                     std::vector<double> &stds) {
+        stds.resize(targets.size());
+        levins_host::check(levins_point_to_plane_std_batch(levins_host::context(), reinterpret_cast<const levins_point_xyzi *>(nearest.data()),
+                                                           group_size, reinterpret_cast<const levins_point_xyzi *>(targets.data()),
+                                                           targets.size(), point_std, stds.data()),
+                           "pointToPlaneStdBatch");
     }
 
 public:

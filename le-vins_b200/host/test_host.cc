@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "le_vins/vins_lidar.h"
+#include "lidar/pointcloud.h"
 #include "ros/lidar_converter.h"
 #include "visual/tracking_depth.h"
 
@@ -161,6 +162,31 @@ int main(int argc, char **argv) {
                 write_bin(dir + "/cloud_raw.bin", from_records.points);
                 std::ofstream s2(dir + "/summary_raw.txt");
                 s2 << "stacked " << ok << "\nappended " << total << "\nn " << from_records.size() << "\n";
+            }
+        }
+        // PointCloudCommon::planeEstimation / pointToPlaneStd / pointSquareDistance (GPU-backed) on consecutive groups of 5 points
+        {
+            std::ifstream probe(dir + "/pts.bin");
+            if (probe) {
+                const auto pts = read_bin<PointType>(dir + "/pts.bin");
+                std::vector<double> plane, stds;
+                for (size_t k = 0; k + 5 <= pts.size(); k += 5) {
+                    PointVector five(pts.begin() + k, pts.begin() + k + 5);
+                    Vector3d n;
+                    double ninv = 0;
+                    std::vector<double> dist;
+                    const bool ok = lidar::PointCloudCommon::planeEstimation(five, 0.1, n, ninv, dist);
+                    plane.insert(plane.end(), {ok ? 1.0 : 0.0, n[0], n[1], n[2], ninv, (double) dist.size()});
+                    stds.push_back(lidar::PointCloudCommon::pointToPlaneStd(five, pts[(k + 7) % pts.size()], 0.03));
+                    stds.push_back(lidar::PointCloudCommon::pointSquareDistance(pts[k], pts[k + 1]));
+                }
+                write_bin(dir + "/plane.bin", plane);
+                write_bin(dir + "/std.bin", stds);
+                std::vector<uint8_t> valid;
+                std::vector<double> normals, ninvs;
+                lidar::PointCloudCommon::planeEstimationBatch(PointVector(pts.begin(), pts.end()), 0.1, valid, normals, ninvs);
+                std::vector<double> vb(valid.begin(), valid.end());
+                write_bin(dir + "/plane_batch.bin", vb);
             }
         }
         // the three PointCloud2 drivers through LidarConverter::*PointCloudAppend (conversion on the device)

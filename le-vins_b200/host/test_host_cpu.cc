@@ -1,7 +1,7 @@
 // CPU-only driver for the part of the host mirror that needs no GPU: MISC pose lookup (host exports of the library), the single-point
-// PointCloudCommon statics, planeEstimation, pointToPlaneStd, Camera.  tests/test_host_mirror.py feeds it binary vectors
+// PointCloudCommon statics, Camera.  tests/test_host_mirror.py feeds it binary vectors
 // and compares every output with the oracle.
-//   test_host_cpu <dir>   reads ins.bin times.bin ext.bin pts.bin   writes poses.bin proj.bin plane.bin std.bin cam.bin
+//   test_host_cpu <dir>   reads ins.bin times.bin ext.bin pts.bin   writes poses.bin proj.bin cam.bin
 #include <cstdio>
 #include <fstream>
 #include <string>
@@ -77,26 +77,6 @@ int main(int argc, char **argv) {
         proj.push_back(lidar::PointCloudCommon::relativeProjectionToCamera(pose_c_l, p0, p1, pts[k]));
     }
     write_bin(dir + "/proj.bin", proj);
-
-    // planeEstimation / pointToPlaneStd on consecutive groups of 5 points
-    std::vector<double> plane, stds;
-    for (size_t k = 0; k + 5 <= pts.size(); k += 5) {
-        PointVector five(pts.begin() + k, pts.begin() + k + 5);
-        Vector3d n;
-        double ninv = 0;
-        std::vector<double> dist;
-        const bool ok = lidar::PointCloudCommon::planeEstimation(five, 0.1, n, ninv, dist);
-        plane.push_back(ok ? 1.0 : 0.0);
-        plane.push_back(n[0]);
-        plane.push_back(n[1]);
-        plane.push_back(n[2]);
-        plane.push_back(ninv);
-        plane.push_back((double) dist.size());
-        stds.push_back(lidar::PointCloudCommon::pointToPlaneStd(five, pts[(k + 7) % pts.size()], 0.03));
-        stds.push_back(lidar::PointCloudCommon::pointSquareDistance(pts[k], pts[k + 1]));
-    }
-    write_bin(dir + "/plane.bin", plane);
-    write_bin(dir + "/std.bin", stds);
 
     // Camera + isGoodDepth
     visual::Camera camera(ext[24], ext[25], ext[26], ext[27], ext[28]);

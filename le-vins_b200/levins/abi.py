@@ -30,7 +30,8 @@ EXPORTS = [
     "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host", "levins_append_raw",
     "levins_append_wait", "levins_ins_window_index", "levins_comm_unique_id", "levins_comm_init", "levins_comm_destroy",
     "levins_gather", "levins_peer_export", "levins_peer_attach", "levins_peer_wait", "levins_peer_detach", "levins_gathered_pointer",
-    "levins_gathered_download", "levins_batch_upload_packed", "levins_associate_pixels", "levins_keyframe_pixels", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
+    "levins_gathered_download", "levins_batch_upload_packed", "levins_associate_pixels", "levins_keyframe_pixels", "levins_plane_estimation_batch",
+    "levins_point_to_plane_std_batch", "levins_depth_factor_batch", "levins_chi2_culling_batch", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
 ]
 
 
@@ -106,6 +107,10 @@ def lib():
             "levins_keyframe_pixels": [vp, dbl, vp, sz, vp, vp, sz, i32, vp, vp, vp, vp, vp, vp, vp, vp],
             "levins_point_cloud_projection": [vp, vp, vp, vp, sz],
             "levins_batch_upload": [vp, vp, sz, vp, sz, vp, sz, vp, sz],
+            "levins_plane_estimation_batch": [vp, vp, sz, dbl, vp, vp, vp, vp, vp],
+            "levins_point_to_plane_std_batch": [vp, vp, sz, vp, sz, dbl, vp],
+            "levins_depth_factor_batch": [vp, vp, vp, sz, dbl, dbl, vp, vp, vp],
+            "levins_chi2_culling_batch": [vp, vp, sz, sz, dbl, vp, vp],
             "levins_batch_upload_packed": [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz],
             "levins_batch_run": [vp],
             "levins_batch_download": [vp, vp, vp, vp, vp, vp],
@@ -303,6 +308,37 @@ class Context:
             _p(out["xyz_depth"]), _p(out["accepted"]), _p(out["pw"]), _p(out["undistorted"]), C.byref(npj), C.byref(m)))
         out["n_projected"], out["m"] = npj.value, m.value
         return out
+
+    def plane_estimation_batch(self, points, threshold):
+        pts = np.ascontiguousarray(points, XYZI).reshape(-1)
+        n = len(pts) // 5
+        out = {"valid": np.zeros(n, np.uint8), "unit_normal": np.zeros((n, 3)), "norm_inverse": np.zeros(n),
+               "distance": np.zeros((n, 5)), "n_distance": np.zeros(n, np.int32)}
+        self._check(lib().levins_plane_estimation_batch(self._h, _p(pts), n, float(threshold), _p(out["valid"]), _p(out["unit_normal"]),
+                                                        _p(out["norm_inverse"]), _p(out["distance"]), _p(out["n_distance"])))
+        return out
+
+    def point_to_plane_std_batch(self, nearest, group_size, targets, point_std):
+        near = np.ascontiguousarray(nearest, XYZI).reshape(-1)
+        tgt = np.ascontiguousarray(targets, XYZI).reshape(-1)
+        out = np.zeros(len(tgt))
+        self._check(lib().levins_point_to_plane_std_batch(self._h, _p(near), int(group_size), _p(tgt), len(tgt), float(point_std), _p(out)))
+        return out
+
+    def depth_factor_batch(self, depth, invdepth, sigma=0.1, huber_a=1.0):
+        d = np.ascontiguousarray(depth, np.float64)
+        i = np.ascontiguousarray(invdepth, np.float64)
+        out = {"residual": np.zeros(len(d)), "jacobian": np.zeros(len(d)), "cost": np.zeros(len(d))}
+        self._check(lib().levins_depth_factor_batch(self._h, _p(d), _p(i), len(d), float(sigma), float(huber_a), _p(out["residual"]),
+                                                    _p(out["jacobian"]), _p(out["cost"])))
+        return out
+
+    def chi2_culling_batch(self, residuals, threshold=5.991):
+        r = np.ascontiguousarray(residuals, np.float64)
+        n, dim = r.shape
+        cost, outlier = np.zeros(n), np.zeros(n, np.uint8)
+        self._check(lib().levins_chi2_culling_batch(self._h, _p(r), n, dim, float(threshold), _p(cost), _p(outlier)))
+        return cost, outlier
 
     def point_cloud_projection(self, pose, cloud):
         pose = np.ascontiguousarray(pose, np.float64)

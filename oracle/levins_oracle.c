@@ -1325,6 +1325,32 @@ void orc_undistort_points(const double intr[5], const double dist[5], const floa
 int orc_is_good_depth(double depth, double scale) { return (depth > NEAREST_DEPTH) && (depth < FARTHEST_DEPTH * scale); }
 
 /* ------------------------------------------------------------------------------------------
+ * factors/depth_factor.h:38-42 as added at optimizer.cc:659-665 (sigma = ASSOCIATE_DEPTH_STD = 0.1, ceres::HuberLoss(1.0)),
+ * and the chi-square test of optimizer.cc:752-783.  Ceres Solver (>= 2.1.0, README.md:48) is not vendored: the residual is
+ * the functor's own expression, the Jacobian is its derivative (what ceres::AutoDiffCostFunction evaluates with Jets:
+ * d/d rho of -1/rho is 1/rho^2), the loss is ceres::HuberLoss::Evaluate (loss_function.cc: rho(s) = s for s <= a^2, else
+ * 2 a sqrt(s) - a^2) and a residual block's cost is 0.5 rho(|r|^2).
+ * ------------------------------------------------------------------------------------------ */
+void orc_depth_factor(double depth, double invdepth, double sigma, double huber_a, double *residual, double *jacobian, double *cost) {
+    const double r = (depth - 1.0 / invdepth) / sigma;
+    const double s = r * r;
+    double rho = s;
+    if (huber_a > 0) {
+        const double b = huber_a * huber_a;
+        if (s > b) rho = 2.0 * huber_a * sqrt(s) - b;
+    }
+    *residual = r;
+    *jacobian = (1.0 / (invdepth * invdepth)) / sigma;
+    *cost = 0.5 * rho;
+}
+int orc_chi2_outlier(const double *residual, size_t dim, double threshold, double *cost_out) {
+    double c = 0;
+    for (size_t i = 0; i < dim; i++) c += residual[i] * residual[i];
+    if (cost_out) *cost_out = c;
+    return c > threshold;
+}
+
+/* ------------------------------------------------------------------------------------------
  * whole keyframe with the reference's structure (bench CPU legs)
  * ------------------------------------------------------------------------------------------ */
 size_t orc_keyframe(const orc_point_xyzit *buf, size_t n_buf, double stamp, double stack_interval, const orc_ins *ins,

@@ -360,6 +360,25 @@ def undistort_points(intr, dist, px):
     return out
 
 
+def depth_factor(depth, invdepth, sigma=0.1, huber_a=1.0):
+    """DepthFactor residual, Jacobian and robustified cost (depth_factor.h:38-42, optimizer.cc:659-665)."""
+    L = lib()
+    L.orc_depth_factor.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    r, j, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    L.orc_depth_factor(float(depth), float(invdepth), float(sigma), float(huber_a), C.byref(r), C.byref(j), C.byref(c))
+    return r.value, j.value, c.value
+
+
+def chi2_outlier(residual, threshold=5.991):
+    L = lib()
+    L.orc_chi2_outlier.restype = C.c_int
+    L.orc_chi2_outlier.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_void_p]
+    r = _c(residual, np.float64)
+    c = C.c_double(0)
+    out = L.orc_chi2_outlier(_p(r), len(r), float(threshold), C.byref(c))
+    return bool(out), c.value
+
+
 def is_good_depth(depth, scale=1.0) -> bool:
     return bool(lib().orc_is_good_depth(float(depth), float(scale)))
 

@@ -20,6 +20,58 @@ def _build():
     return mod.build()
 
 
+def _plane_patches(rng):
+    """patches of 5 nearly coplanar points + noise so that planeEstimation sees both outcomes"""
+    pts = np.zeros(200, synth.XYZI)
+    base = rng.normal(0, 8, (40, 3)) + [0, 0, 15]
+    nrm = rng.normal(0, 1, (40, 3))
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    for g in range(40):
+        off = rng.normal(0, 0.4, (5, 3))
+        if g % 3:  # two thirds of the patches are planar (1 cm roughness), the rest scatter 0.4 m off the plane
+            off -= np.outer(off @ nrm[g], nrm[g]) * 0.975
+        p = (base[g] + off).astype(np.float32)
+        pts["x"][5 * g:5 * g + 5], pts["y"][5 * g:5 * g + 5], pts["z"][5 * g:5 * g + 5] = p[:, 0], p[:, 1], p[:, 2]
+    pts["w"] = 1.0
+    pts["intensity"] = rng.uniform(0, 100, 200).astype(np.float32)
+    return pts
+
+
+def _check_plane_outputs(oracle, pts, plane, stds, plane_batch):
+    """planeEstimation bit for bit against the oracle, pointToPlaneStd against the oracle (1e-12) and against an independent
+    numpy restatement of pointcloud.cc:111-190 with numpy.linalg.eigh (1e-6)"""
+    import ctypes
+
+    n_ok = 0
+    for g in range(40):
+        five = pts[5 * g:5 * g + 5]
+        ok, n, ninv, dist = oracle.plane_estimation(five, 0.1)
+        assert bool(plane[g, 0]) == ok and np.array_equal(plane[g, 1:4], n) and plane[g, 4] == ninv and int(plane[g, 5]) == len(dist)
+        assert bool(plane_batch[g]) == ok
+        n_ok += ok
+        target = pts[(5 * g + 7) % len(pts)]
+        s_or = oracle.point_to_plane_std(five, target, 0.03)
+        assert np.isclose(stds[g, 0], s_or, rtol=1e-12)
+        P = np.stack([five["x"], five["y"], five["z"]], -1).astype(np.float64)
+        c = P.mean(0)
+        cov = P.T @ P / 5 - np.outer(c, c)
+        w, V = np.linalg.eigh(cov)
+        nn = V[:, 0]
+        pc = np.zeros((6, 6))
+        for i in range(5):
+            F = np.zeros((3, 3))
+            for m in (1, 2):
+                F[m] = (1 / 5) * (P[i] - c) / (w[0] - w[m]) @ (np.outer(V[:, m], nn) + np.outer(nn, V[:, m]))
+            J = np.vstack([V @ F, np.eye(3) / 5])
+            pc += J @ (np.eye(3) * 0.03**2) @ J.T
+        jac = np.concatenate([np.array([target["x"], target["y"], target["z"]], np.float64) - c, -nn])
+        ref = np.sqrt(jac @ pc @ jac + 0.03**2 * nn @ nn)
+        assert np.isclose(s_or, ref, rtol=1e-6), (s_or, ref)
+        assert stds[g, 1] == np.float32(oracle.lib().orc_point_square_distance(
+            five[0:1].ctypes.data_as(ctypes.c_void_p), five[1:2].ctypes.data_as(ctypes.c_void_p)))
+    assert 5 < n_ok < 35  # both planeEstimation outcomes exercised
+
+
 def _dump(kf, d, frame_pose, n_scans):
     kf.points.tofile(os.path.join(d, "points.bin"))
     ins = np.concatenate([kf.ins["time"][:, None], kf.ins["state_time"][:, None], kf.ins["p"], kf.ins["q"]], axis=1)
@@ -73,8 +125,12 @@ def test_host_mirror_matches_oracle(oracle, built_lib, tmp_path):
     np.array([drv_stamp, 1.0, 200.0, 1.0, 128], np.float64).tofile(tmp_path / "raw_meta.bin")
     for name in ("velodyne", "ouster", "hesai"):
         cases[name][2].tofile(tmp_path / f"raw_{name}.bin")
+    patches = _plane_patches(np.random.default_rng(11))
+    patches.tofile(tmp_path / "pts.bin")
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    _check_plane_outputs(oracle, patches, np.fromfile(tmp_path / "plane.bin").reshape(-1, 6),
+                         np.fromfile(tmp_path / "std.bin").reshape(-1, 2), np.fromfile(tmp_path / "plane_batch.bin"))
     drv = np.fromfile(tmp_path / "append_drivers.bin", np.float64).reshape(3, 4)
     for i, name in enumerate(("velodyne", "ouster", "hesai")):
         _, fmt, rec, tb, st, lines = cases[name]
@@ -117,8 +173,7 @@ def test_host_mirror_matches_oracle(oracle, built_lib, tmp_path):
 
 def test_host_mirror_cpu_functions_match_oracle(oracle, built_lib, tmp_path):
     """The part of the C++ mirror that needs no GPU: MISC pose lookup (host exports of the library), PointCloudCommon single-point statics,
-    planeEstimation, pointToPlaneStd, Camera -- bit-for-bit against the oracle (same operation order, -ffp-contract=off),
-    pointToPlaneStd also against an independent numpy restatement."""
+    Camera -- bit-for-bit against the oracle (same operation order, -ffp-contract=off)."""
     _build()
     exe = os.path.join(ROOT, "le-vins_b200", "host", "test_host_cpu")
     kf = synth.make_keyframe(2, pts_per_scan=400, n_features=8)
@@ -130,19 +185,7 @@ def test_host_mirror_cpu_functions_match_oracle(oracle, built_lib, tmp_path):
     times = np.concatenate([rng.uniform(t[0], t[-1], 60), [t[0] - 1.0, t[0], t[5], t[-1], t[-1] + 2.0]])
     times.tofile(tmp_path / "times.bin")
     np.concatenate([rig.pose_b_c, rig.pose_c_l, rig.intr]).tofile(tmp_path / "ext.bin")
-    # points: patches of 5 nearly coplanar points + noise so that planeEstimation sees both outcomes
-    pts = np.zeros(200, synth.XYZI)
-    base = rng.normal(0, 8, (40, 3)) + [0, 0, 15]
-    nrm = rng.normal(0, 1, (40, 3))
-    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
-    for g in range(40):
-        off = rng.normal(0, 0.4, (5, 3))
-        if g % 3:  # two thirds of the patches are planar (1 cm roughness), the rest scatter 0.4 m off the plane
-            off -= np.outer(off @ nrm[g], nrm[g]) * 0.975
-        p = (base[g] + off).astype(np.float32)
-        pts["x"][5 * g:5 * g + 5], pts["y"][5 * g:5 * g + 5], pts["z"][5 * g:5 * g + 5] = p[:, 0], p[:, 1], p[:, 2]
-    pts["w"] = 1.0
-    pts["intensity"] = rng.uniform(0, 100, 200).astype(np.float32)
+    pts = _plane_patches(rng)
     pts.tofile(tmp_path / "pts.bin")
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -160,36 +203,6 @@ def test_host_mirror_cpu_functions_match_oracle(oracle, built_lib, tmp_path):
         assert proj[k, 0].tobytes() == oracle.point_projection(rig.pose_c_l, pts[k]).tobytes()
         assert proj[k, 1].tobytes() == oracle.relative_projection(p0, p1, pts[k]).tobytes()
         assert proj[k, 2].tobytes() == oracle.relative_projection_to_camera(rig.pose_c_l, p0, p1, pts[k]).tobytes()
-    plane = np.fromfile(tmp_path / "plane.bin").reshape(-1, 6)
-    stds = np.fromfile(tmp_path / "std.bin").reshape(-1, 2)
-    n_ok = 0
-    for g in range(40):
-        five = pts[5 * g:5 * g + 5]
-        ok, n, ninv, dist = oracle.plane_estimation(five, 0.1)
-        assert bool(plane[g, 0]) == ok and np.array_equal(plane[g, 1:4], n) and plane[g, 4] == ninv and int(plane[g, 5]) == len(dist)
-        n_ok += ok
-        target = pts[(5 * g + 7) % len(pts)]
-        s_or = oracle.point_to_plane_std(five, target, 0.03)
-        assert np.isclose(stds[g, 0], s_or, rtol=1e-12)
-        # independent restatement of pointcloud.cc:111-190 with numpy.linalg.eigh
-        P = np.stack([five["x"], five["y"], five["z"]], -1).astype(np.float64)
-        c = P.mean(0)
-        cov = P.T @ P / 5 - np.outer(c, c)
-        w, V = np.linalg.eigh(cov)
-        nn = V[:, 0]
-        pc = np.zeros((6, 6))
-        for i in range(5):
-            F = np.zeros((3, 3))
-            for m in (1, 2):
-                F[m] = (1 / 5) * (P[i] - c) / (w[0] - w[m]) @ (np.outer(V[:, m], nn) + np.outer(nn, V[:, m]))
-            J = np.vstack([V @ F, np.eye(3) / 5])
-            pc += J @ (np.eye(3) * 0.03**2) @ J.T
-        jac = np.concatenate([np.array([target["x"], target["y"], target["z"]], np.float64) - c, -nn])
-        ref = np.sqrt(jac @ pc @ jac + 0.03**2 * nn @ nn)
-        assert np.isclose(s_or, ref, rtol=1e-6), (s_or, ref)
-        assert stds[g, 1] == np.float32(oracle.lib().orc_point_square_distance(
-            five[0:1].ctypes.data_as(__import__("ctypes").c_void_p), five[1:2].ctypes.data_as(__import__("ctypes").c_void_p)))
-    assert 5 < n_ok < 35  # both planeEstimation outcomes exercised
     cam = np.fromfile(tmp_path / "cam.bin").reshape(-1, 10)
     for k in range(len(pts)):
         u, v = np.float32(pts["x"][k] * np.float32(10.0) + np.float32(600.0)), np.float32(pts["y"][k] * np.float32(10.0) + np.float32(500.0))
