@@ -595,7 +595,7 @@ def stream_latency(abi, synth, device, n_keyframes=40):
             src = hb.array
         ctx = abi.Context(device)
         ctx.set_extrinsics(shp.rig.pose_b_c, shp.rig.pose_c_l, shp.rig.td_b_l)
-        times, t_append = [], []
+        times, t_append, t_call = [], [], []
         scan = 0
         for k, stamp in enumerate(b.stamps):
             kf_ins = b.ins[b.ins_begin[k]: b.ins_begin[k] + b.ins_count[k]]
@@ -603,12 +603,20 @@ def stream_latency(abi, synth, device, n_keyframes=40):
             while scan < n_scans and b.points["time"][scan * per] <= stamp + 1e-9:  # everything that started before the stamp
                 ta = time.perf_counter()
                 if raw:
-                    ctx.append_raw(rawfmt.fmt_livox(), src[scan * step:(scan + 1) * step], per, timebase_ns=bases[scan], scan_line=6)
+                    ctx.append_raw(rawfmt.fmt_livox(), src[scan * step:(scan + 1) * step], per, timebase_ns=bases[scan], scan_line=6,
+                                   want_result=False)
                 else:
                     ctx.append_scan(src[scan * per:(scan + 1) * per])
                 t_append.append(1e6 * (time.perf_counter() - ta))
                 scan += 1
-            ctx.keyframe(float(stamp), kf_ins, b.queries[k])
+            if kind == "pinned":  # live operation: the scans arrived earlier, only the keyframe call itself is on the clock
+                ctx.synchronize()
+                tk = time.perf_counter()
+                ctx.keyframe(float(stamp), kf_ins, b.queries[k])
+                t_call.append(1e3 * (time.perf_counter() - tk))
+                t0 += 0.0
+            else:
+                ctx.keyframe(float(stamp), kf_ins, b.queries[k])
             times.append(1e3 * (time.perf_counter() - t0))
         ctx.close()
         if hb is not None:
@@ -616,6 +624,8 @@ def stream_latency(abi, synth, device, n_keyframes=40):
             hb.close()
         out[kind] = float(np.median(times[3:])) if len(times) > 3 else None
         out[kind + "_append_us"] = float(np.median(t_append[5:])) if len(t_append) > 5 else None
+        if t_call:
+            out["keyframe_call_ms_scans_resident"] = float(np.median(t_call[3:]))
     return out
 
 

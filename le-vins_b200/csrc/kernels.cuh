@@ -77,9 +77,15 @@ __device__ __forceinline__ unsigned long long warp_search(unsigned long long cou
 // ------------------------------------------------------------------------------------------------
 // ring buffer append bookkeeping: VINS::addNewPointCloud eviction rule (le_vins.cc:156-159)
 // ------------------------------------------------------------------------------------------------
+// (one warp)
+__device__ __forceinline__ void ring_append(RingState* ring, const PointXYZIT* __restrict__ pts, unsigned long long cap,
+                                            unsigned long long n_new, double reserved_time);
 __global__ void k_ring_append(RingState* ring, const PointXYZIT* __restrict__ pts, unsigned long long cap,
-                              unsigned long long n_new, double reserved_time, const unsigned long long* n_new_dev = nullptr) {
-    if (n_new_dev) n_new = *n_new_dev; // levins_append_raw: the number of records that survived is known on the device only
+                              unsigned long long n_new, double reserved_time) {
+    ring_append(ring, pts, cap, n_new, reserved_time);
+}
+__device__ __forceinline__ void ring_append(RingState* ring, const PointXYZIT* __restrict__ pts, unsigned long long cap,
+                                            unsigned long long n_new, double reserved_time) {
     const unsigned long long head = ring->head;
     const unsigned long long count = ring->count + n_new;
     if (count == 0) return;
@@ -117,8 +123,11 @@ struct RawArgs {
     unsigned* block_kept;       // [ceil(n / 256)] survivor counts, turned into exclusive offsets by k_raw_scan
     unsigned long long* minmax; // ordered bit patterns of start (min) and end (max)
     PointXYZIT* ring;
-    unsigned long long cap, tail;
+    unsigned long long cap;
     RawResult* result;
+    RingState* ring_state; // the scatter appends behind head + count and the last block to finish does the bookkeeping
+    unsigned* ticket;      // blocks finished (reset by k_raw_count)
+    double reserved_time;  // le_vins.cc:156
 };
 constexpr int RAW_BLOCK = 256;
 
@@ -177,6 +186,7 @@ __global__ void __launch_bounds__(RAW_BLOCK) k_raw_count(const __grid_constant__
     if (k < a.n) seen = raw_decode(a, k, p, kept);
     const int c = __syncthreads_count(kept);
     if (threadIdx.x == 0) a.block_kept[blockIdx.x] = (unsigned) c;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket = 0;
     // start / end over every considered record, before the range gate (:58-63)
     unsigned long long lo = seen ? ordered_key(p.time) : ~0ull, hi = seen ? ordered_key(p.time) : 0ull;
 #pragma unroll
@@ -190,66 +200,60 @@ __global__ void __launch_bounds__(RAW_BLOCK) k_raw_count(const __grid_constant__
     }
 }
 
-// one block: exclusive scan of the per-block counts (in place) + the result record
-__global__ void __launch_bounds__(1024) k_raw_scan(unsigned* block_kept, unsigned nblocks, const unsigned long long* minmax, RawResult* result) {
-    __shared__ unsigned s_warp[32];
-    __shared__ unsigned s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (unsigned base = 0; base < nblocks; base += 1024) {
-        const unsigned i = base + threadIdx.x;
-        const unsigned v = i < nblocks ? block_kept[i] : 0u;
-        unsigned x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) >= o) x += y;
-        }
-        if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            unsigned w = s_warp[threadIdx.x];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned y = __shfl_up_sync(0xffffffffu, w, o);
-                if (threadIdx.x >= o) w += y;
-            }
-            s_warp[threadIdx.x] = w; // inclusive over warps
-        }
-        __syncthreads();
-        const unsigned warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0u;
-        const unsigned carry = s_carry;
-        if (i < nblocks) block_kept[i] = carry + warp_off + x - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = carry + warp_off + x;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        result->count = s_carry;
-        result->start = ordered_value(minmax[0]);
-        result->end = ordered_value(minmax[1]);
-    }
-}
-
+// Ordered scatter.  Every block sums the survivor counts of the blocks before it (a few hundred values from L2), places its
+// survivors behind the ring's tail, and the last block to finish writes the result record and does VINS::addNewPointCloud's
+// bookkeeping (count += appended, 11 s eviction): conversion + append are two launches in all.
 __global__ void __launch_bounds__(RAW_BLOCK) k_raw_scatter(const __grid_constant__ RawArgs a) {
     __shared__ unsigned s_warp[RAW_BLOCK / 32];
+    __shared__ unsigned s_base[RAW_BLOCK / 32];
+    __shared__ unsigned s_last;
     const unsigned k = blockIdx.x * RAW_BLOCK + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PointXYZIT p;
     bool kept = false;
     if (k < a.n) raw_decode(a, k, p, kept);
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // exclusive offset of this block
+    unsigned part = 0;
+    for (unsigned i = threadIdx.x; i < blockIdx.x; i += RAW_BLOCK) part += a.block_kept[i];
+    part = __reduce_add_sync(0xffffffffu, part);
     const unsigned bal = __ballot_sync(0xffffffffu, kept);
-    if (lane == 0) s_warp[warp] = __popc(bal);
+    if (lane == 0) {
+        s_warp[warp] = __popc(bal);
+        s_base[warp] = part;
+    }
     __syncthreads();
-    unsigned off = a.block_kept[blockIdx.x]; // exclusive offset of this block (k_raw_scan)
+    unsigned off = 0;
+#pragma unroll
+    for (int w = 0; w < RAW_BLOCK / 32; w++) off += s_base[w];
     for (unsigned w = 0; w < warp; w++) off += s_warp[w];
+    const unsigned long long tail = wrap(a.ring_state->head + a.ring_state->count, a.cap); // stable until the last block updates it
     if (kept) {
-        const unsigned long long dst = wrap(a.tail + off + __popc(bal & ((1u << lane) - 1u)), a.cap);
+        const unsigned long long dst = wrap(tail + off + __popc(bal & ((1u << lane) - 1u)), a.cap);
         float4* out = reinterpret_cast<float4*>(a.ring + dst);
         out[0] = make_float4(p.x, p.y, p.z, 0.f);
         reinterpret_cast<float2*>(out + 1)[0] = make_float2(p.intensity, 0.f);
         reinterpret_cast<double*>(out + 1)[1] = p.time;
     }
+    // last block: result record + ring bookkeeping
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last || warp != 0) return;
+    __threadfence();
+    unsigned total = 0;
+    for (unsigned i = lane; i < gridDim.x; i += 32) total += __ldcg(a.block_kept + i);
+    total = __reduce_add_sync(0xffffffffu, total);
+    if (lane == 0) {
+        a.result->count = total;
+        a.result->start = ordered_value(__ldcg(a.minmax));
+        a.result->end = ordered_value(__ldcg(a.minmax + 1));
+        // start = DBL_MAX, end = 0 for the next scan (lidar_converter.cc:50-51)
+        a.minmax[0] = ordered_key(DBL_MAX);
+        a.minmax[1] = ordered_key(0.0);
+    }
+    __syncwarp();
+    ring_append(a.ring_state, a.ring, a.cap, total, a.reserved_time);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -570,22 +574,34 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
         const double inv_mean_dt = nins > 1 ? (double) (nins - 1) / (t_last - t_first) : 0.0;
         const unsigned long long table_begin = kf->table_begin;
         ChunkDesc* __restrict__ out = a.chunks + (size_t) blockIdx.x * a.chunks_per_kf;
-        // all first-point times of this thread's chunks first (independent loads, one memory round trip), then the probes
-        constexpr int ROUNDS = 8; // the host fuses the descriptors only for chunks_per_kf <= 8 * 256
-        double tp[ROUNDS];
-        unsigned long long ph[ROUNDS];
+        // all first-point times of this thread's chunks first (independent loads, one memory round trip), then the probes;
+        // chunks past the projected points only get an empty descriptor
+        constexpr int ROUNDS = 8;
+        for (unsigned base = 0; base < a.chunks_per_kf; base += ROUNDS * 256u) {
+            if ((unsigned long long) base * CHUNK_PTS >= n_proj) { // nothing live from here on
+                ChunkDesc e;
+                e.phys = 0;
+                e.ent0 = 0;
+                e.cnt = 0;
+                for (unsigned c = base + threadIdx.x; c < a.chunks_per_kf; c += 256u) out[c] = e;
+                break;
+            }
+            double tp[ROUNDS];
+            unsigned long long ph[ROUNDS];
 #pragma unroll
-        for (int i = 0; i < ROUNDS; i++) {
-            const unsigned off = (threadIdx.x + i * 256u) * CHUNK_PTS;
-            const bool live = threadIdx.x + i * 256u < a.chunks_per_kf && off < n_proj;
-            ph[i] = live ? wrap(proj_begin + off, a.pts_cap) : 0ull;
-            tp[i] = live ? a.pts[ph[i]].time : 0.0;
-        }
+            for (int i = 0; i < ROUNDS; i++) {
+                const unsigned c = base + threadIdx.x + i * 256u;
+                const unsigned long long off = (unsigned long long) c * CHUNK_PTS;
+                const bool live = c < a.chunks_per_kf && off < n_proj;
+                ph[i] = live ? wrap(proj_begin + off, a.pts_cap) : 0ull;
+                tp[i] = live ? a.pts[ph[i]].time : 0.0;
+            }
 #pragma unroll
-        for (int i = 0; i < ROUNDS; i++) {
-            const unsigned c = threadIdx.x + i * 256u;
-            if (c < a.chunks_per_kf)
-                out[c] = chunk_desc_from_time<false>(c, n_proj, ph[i], tp[i], a.ext.td_b_l, tab, table_begin, nins, t_first, t_last, inv_mean_dt);
+            for (int i = 0; i < ROUNDS; i++) {
+                const unsigned c = base + threadIdx.x + i * 256u;
+                if (c < a.chunks_per_kf)
+                    out[c] = chunk_desc_from_time<false>(c, n_proj, ph[i], tp[i], a.ext.td_b_l, tab, table_begin, nins, t_first, t_last, inv_mean_dt);
+            }
         }
     }
 }
@@ -1463,6 +1479,12 @@ struct PlaneArgs {
     Consts c;
     PeerOut peer; // peer mode: the results also go straight into every rank's gathered block (exchange.cuh)
     // feature side on the device: the drivers' accept gate and cam2world (tracking.cc:431-439, 539-545)
+    // streaming keyframe: the final KfState and RingState are copied next to the results, so that one device->host copy
+    // brings everything back (k_associate, which counts M, has completed when this kernel runs)
+    const KfState* kf_src;
+    KfState* kf_out;
+    const RingState* ring_src;
+    RingState* ring_out;
     unsigned char* accepted; // nullable: type != NONE && isGoodDepth(depth, 1)
     double* pw;              // nullable: 3 per query, world point of accepted features (0 otherwise)
     double poseR[9], poset[3]; // frame_ref_->pose(), R column-major
@@ -1470,6 +1492,10 @@ struct PlaneArgs {
 
 __global__ void __launch_bounds__(128) k_plane(const __grid_constant__ PlaneArgs a) {
     const unsigned long long i = (unsigned long long) blockIdx.x * 128 + threadIdx.x;
+    if (i == 0 && a.kf_out) {
+        *a.kf_out = *a.kf_src;
+        if (a.ring_out) *a.ring_out = *a.ring_src;
+    }
     if (i >= a.q_count) return;
     const size_t qi = a.q_begin + i;
     const float qx = __ldg(a.queries + 3 * qi), qy = __ldg(a.queries + 3 * qi + 1), qz = __ldg(a.queries + 3 * qi + 2);

@@ -63,7 +63,8 @@ struct levins_ctx {
     // ---- streaming state ----
     DevBuf ring;      // PointXYZIT x cfg.max_points
     DevBuf ring_state; // RingState
-    uint64_t ring_tail = 0;     // physical index one past the newest point
+    uint64_t ring_tail = 0;     // physical index one past the newest point (levins_append_scan's copy target)
+    bool ring_tail_known = true; // false after levins_append_raw until the ring state is read back
     uint64_t ring_count_ub = 0; // host's upper bound of the live point count
     DevBuf s_ins, s_table, s_kf, s_queries;
     DevBuf chunks; // ChunkDesc of the current k_deskew_bin launch (streaming and batch)
@@ -71,6 +72,9 @@ struct levins_ctx {
     DevBuf s_type, s_xyzd, s_flags, s_knn_idx, s_knn_d2, s_nn, s_nn_meta;
     DevBuf s_pixels, s_undist, s_accepted, s_pw; // feature side on the device (levins_associate_pixels)
     DevBuf scratch; // inputs / outputs of the small batched entry points (plane geometry, depth factors)
+    DevBuf s_arena_in, s_arena_out; // fused keyframe: everything sent / returned in one copy each (keyframe_body)
+    void* pin_io = nullptr;       // their page-locked mirrors (first half in, second half out)
+    size_t pin_io_bytes = 0;
     DevBuf s_cloud;    // resident deskewed cloud (PointXYZI)
     DevBuf s_in_cloud; // explicit cloud uploaded by build_range_image
     DevBuf s_zbuf, s_cells, s_c2c, s_unit, s_winner;
@@ -238,6 +242,7 @@ int ensure_ring(levins_ctx* ctx) {
     CU(ctx->ring_state.ensure(sizeof(RingState)));
     CU(cudaMemsetAsync(ctx->ring_state.p, 0, sizeof(RingState), ctx->stream));
     ctx->ring_tail = 0;
+    ctx->ring_tail_known = true;
     ctx->ring_count_ub = 0;
     return LEVINS_OK;
 }
@@ -293,8 +298,40 @@ int read_ring_state(levins_ctx* ctx, RingState* out) {
     return LEVINS_OK;
 }
 
-// stage 1 on the ring: k_prepare (+ pops) then k_deskew_bin.  Leaves KfState in s_kf.
-int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins, bool write_cloud, bool bin, size_t n_queries = 0) {
+// Where the per-keyframe inputs and outputs of the streaming path live on the device.  The stage-wise entry points use the
+// context's individual buffers; the fused keyframe packs everything into one input and one output arena so that a keyframe
+// costs one host->device and one device->host copy.
+struct StreamPtrs {
+    KfState* kf;
+    InsSample* ins;
+    float* queries;
+    float* pixels;
+    int8_t* type;
+    float4* xyzd;
+    unsigned char* accepted;
+    float* undist;
+    double* pw;
+    KfState* kf_out = nullptr; // arena mode: k_plane leaves the final states next to the results
+    RingState* ring_out = nullptr;
+};
+StreamPtrs default_ptrs(levins_ctx* ctx) {
+    StreamPtrs sp{};
+    sp.kf = ctx->s_kf.as<KfState>();
+    sp.ins = ctx->s_ins.as<InsSample>();
+    sp.queries = ctx->s_queries.as<float>();
+    sp.pixels = ctx->s_pixels.as<float>();
+    sp.type = ctx->s_type.as<int8_t>();
+    sp.xyzd = ctx->s_xyzd.as<float4>();
+    sp.accepted = ctx->s_accepted.as<unsigned char>();
+    sp.undist = ctx->s_undist.as<float>();
+    sp.pw = ctx->s_pw.as<double>();
+    return sp;
+}
+
+// stage 1 on the ring: k_prepare (+ pops, + chunk descriptors) then k_deskew_bin.  Leaves KfState in sp.kf.
+// uploaded: the caller has already put KfState and the INS window on the device (arena mode).
+int run_stage1(levins_ctx* ctx, const StreamPtrs& sp, double stamp, const levins_ins_sample* ins, size_t n_ins, bool write_cloud,
+               size_t n_queries = 0, bool uploaded = false) {
     if (!ctx->have_ext) return fail(ctx, LEVINS_ERR_STATE, "levins_set_extrinsics has not been called");
     if (!ins || n_ins == 0) return fail(ctx, LEVINS_ERR_ARG, "empty INS window");
     if (n_ins > ctx->cfg.max_ins) return fail(ctx, LEVINS_ERR_CAPACITY, "INS window larger than config.max_ins");
@@ -308,25 +345,28 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
         int r = size_chunks(ctx, da, n_ub, 1);
         if (r) return r;
     }
-    char* pin = reinterpret_cast<char*>(ctx->pinned);
-    memcpy(pin + ctx->pin_ins(), ins, n_ins * sizeof(InsSample));
-    CU(cudaMemcpyAsync(ctx->s_ins.p, pin + ctx->pin_ins(), n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
-    KfState kf{};
-    kf.pt_begin = 0;
-    kf.pt_count = 0;
-    kf.ins_begin = 0;
-    kf.ins_count = n_ins;
-    kf.q_begin = 0;
-    kf.q_count = n_queries; // levins_keyframe: the features follow in the same call
-    kf.stamp = stamp;
-    memcpy(ctx->pinned, &kf, sizeof(kf));
-    CU(cudaMemcpyAsync(ctx->s_kf.p, ctx->pinned, sizeof(kf), cudaMemcpyHostToDevice, ctx->stream));
+    if (!uploaded) {
+        char* pin = reinterpret_cast<char*>(ctx->pinned);
+        memcpy(pin + ctx->pin_ins(), ins, n_ins * sizeof(InsSample));
+        CU(cudaMemcpyAsync(sp.ins, pin + ctx->pin_ins(), n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
+        KfState kf{};
+        kf.ins_count = n_ins;
+        kf.q_count = n_queries; // levins_keyframe: the features follow in the same call
+        kf.stamp = stamp;
+        memcpy(ctx->pinned, &kf, sizeof(kf));
+        CU(cudaMemcpyAsync(sp.kf, ctx->pinned, sizeof(kf), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    // one keyframe: its block writes the chunk descriptors too unless the ring holds very many points (the descriptors of
+    // chunks past the projected window are empty and cost a store each)
+    const bool fused_desc = da.chunks_per_kf <= 8192;
     PrepareArgs pa{};
-    pa.kfs = ctx->s_kf.as<KfState>();
+    pa.kfs = sp.kf;
     pa.pts = ctx->ring.as<PointXYZIT>();
     pa.pts_cap = ctx->cfg.max_points;
-    pa.ins = ctx->s_ins.as<InsSample>();
+    pa.ins = sp.ins;
     pa.table = ctx->s_table.as<Interval>();
+    pa.chunks = fused_desc ? da.chunks : nullptr;
+    pa.chunks_per_kf = da.chunks_per_kf;
     pa.ring = ctx->ring_state.as<RingState>();
     pa.ext = ctx->ext;
     pa.c = ctx->consts;
@@ -338,7 +378,7 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
         int r = next_gen(ctx, ctx->s_zbuf.as<unsigned long long>(), CELLS, &ctx->s_gen);
         if (r) return r;
     }
-    da.kfs = ctx->s_kf.as<KfState>();
+    da.kfs = sp.kf;
     da.pts = ctx->ring.as<PointXYZIT>();
     da.pts_cap = ctx->cfg.max_points;
     da.table = ctx->s_table.as<Interval>();
@@ -347,8 +387,7 @@ int run_stage1(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size
     da.gen = ctx->s_gen;
     da.ext = ctx->ext;
     da.c = ctx->consts;
-    (void) bin;
-    {
+    if (!fused_desc) {
         int r = launch_chunks(ctx, da, n_ub, 1);
         if (r) return r;
     }
@@ -385,18 +424,18 @@ struct PixelOpts {
     const levins_pose* pose_ref = nullptr;
 };
 
-int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused, const PixelOpts& px = PixelOpts()) {
+int run_associate_stream(levins_ctx* ctx, const StreamPtrs& sp, size_t nf, bool with_idx, bool fused, const PixelOpts& px = PixelOpts()) {
     AssocArgs aa{};
     if (px.cam) {
-        aa.pixels = ctx->s_pixels.as<float>();
-        aa.queries_out = ctx->s_queries.as<float>();
-        aa.undist_out = ctx->s_undist.as<float>();
+        aa.pixels = sp.pixels;
+        aa.queries_out = sp.queries;
+        aa.undist_out = sp.undist;
         aa.undistort = px.undistort;
         static_assert(sizeof(levins_camera) == sizeof(CameraModel), "camera layout");
         memcpy(&aa.cam, px.cam, sizeof(CameraModel));
     }
-    aa.kfs = ctx->s_kf.as<KfState>();
-    aa.queries = ctx->s_queries.as<float>();
+    aa.kfs = sp.kf;
+    aa.queries = sp.queries;
     aa.cells = ctx->s_cells.as<float4>();
     aa.c2c = with_idx ? ctx->s_c2c.as<int32_t>() : nullptr;
     aa.zbuf = ctx->s_zbuf.as<unsigned long long>();
@@ -419,19 +458,25 @@ int run_associate_stream(levins_ctx* ctx, size_t nf, bool with_idx, bool fused, 
     ctx->launches++;
     CU(cudaGetLastError());
     PlaneArgs pa{};
-    pa.queries = ctx->s_queries.as<float>();
+    pa.queries = sp.queries;
     pa.nn = ctx->s_nn.as<float4>();
     pa.nn_meta = ctx->s_nn_meta.as<uint2>();
     pa.q_begin = 0;
     pa.q_count = nf;
-    pa.type = ctx->s_type.as<int8_t>();
-    pa.xyz_depth = ctx->s_xyzd.as<float4>();
+    pa.type = sp.type;
+    pa.xyz_depth = sp.xyzd;
     pa.flags = ctx->s_flags.as<int32_t>();
     pa.c = ctx->consts;
+    if (sp.kf_out) {
+        pa.kf_src = sp.kf;
+        pa.kf_out = sp.kf_out;
+        pa.ring_src = ctx->ring_state.as<RingState>();
+        pa.ring_out = sp.ring_out;
+    }
     if (px.cam) {
-        pa.accepted = ctx->s_accepted.as<unsigned char>();
+        pa.accepted = sp.accepted;
         if (px.pose_ref) {
-            pa.pw = ctx->s_pw.as<double>();
+            pa.pw = sp.pw;
             memcpy(pa.poseR, px.pose_ref->R, sizeof(pa.poseR));
             memcpy(pa.poset, px.pose_ref->t, sizeof(pa.poset));
         }
@@ -527,7 +572,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
-                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw, &ctx->scratch})
+                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw, &ctx->scratch, &ctx->s_arena_in, &ctx->s_arena_out})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -537,6 +582,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
     for (int r = 0; r < MAX_PEERS; r++)
         if (ctx->peer_mapped[r]) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->pin_io) cudaFreeHost(ctx->pin_io);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -648,6 +694,13 @@ extern "C" int levins_append_scan(levins_ctx* ctx, const levins_point_xyzit* poi
         if (r) return r;
         if (st.count + n > cap) return fail(ctx, LEVINS_ERR_CAPACITY, "ring buffer full: raise config.max_points");
     }
+    if (!ctx->ring_tail_known) { // levins_append_raw moved the tail by a count only the device knows
+        RingState st;
+        r = read_ring_state(ctx, &st);
+        if (r) return r;
+        ctx->ring_tail = (st.head + st.count) % cap;
+        ctx->ring_tail_known = true;
+    }
     const uint64_t tail = ctx->ring_tail;
     const uint64_t first = std::min<uint64_t>(n, cap - tail);
     PointXYZIT* base = ctx->ring.as<PointXYZIT>();
@@ -700,8 +753,22 @@ extern "C" int levins_append_raw(levins_ctx* ctx, const levins_raw_format* fmt, 
     const unsigned nblocks = (unsigned) ((n + RAW_BLOCK - 1) / RAW_BLOCK);
     CU(ctx->raw_stage.ensure(bytes));
     CU(ctx->raw_blocks.ensure((size_t) nblocks * 4));
-    CU(ctx->raw_misc.ensure(64));
+    char* pin = reinterpret_cast<char*>(ctx->pinned);
+    if (!ctx->raw_misc.p) { // {min, max} keys | result | ticket; the kernels re-arm the keys after every scan
+        CU(ctx->raw_misc.ensure(64));
+        const double init[2] = {DBL_MAX, 0.0}; // start = DBL_MAX, end = 0 as ordered keys (positive doubles: sign bit set)
+        unsigned long long keys[8] = {};
+        for (int i = 0; i < 2; i++) {
+            unsigned long long b;
+            memcpy(&b, &init[i], 8);
+            keys[i] = b | 0x8000000000000000ull;
+        }
+        memcpy(pin + 512, keys, 64);
+        CU(cudaMemcpyAsync(ctx->raw_misc.p, pin + 512, 64, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CU(cudaMemcpyAsync(ctx->raw_stage.p, records, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!ctx->ev_append) CU(cudaEventCreateWithFlags(&ctx->ev_append, cudaEventDisableTiming));
+    CU(cudaEventRecord(ctx->ev_append, ctx->stream)); // levins_append_wait(): the caller's buffer has been read
     RawArgs a{};
     a.rec = ctx->raw_stage.as<unsigned char>();
     a.n = (unsigned) n;
@@ -720,33 +787,23 @@ extern "C" int levins_append_raw(levins_ctx* ctx, const levins_raw_format* fmt, 
     a.block_kept = ctx->raw_blocks.as<unsigned>();
     a.minmax = ctx->raw_misc.as<unsigned long long>();
     a.result = reinterpret_cast<RawResult*>(ctx->raw_misc.as<unsigned char>() + 16);
+    a.ticket = reinterpret_cast<unsigned*>(ctx->raw_misc.as<unsigned char>() + 48);
     a.ring = ctx->ring.as<PointXYZIT>();
     a.cap = cap;
-    a.tail = ctx->ring_tail;
-    // start = DBL_MAX, end = 0 as ordered keys (positive doubles: sign bit set)
-    char* pin = reinterpret_cast<char*>(ctx->pinned);
-    const double init[2] = {DBL_MAX, 0.0};
-    unsigned long long keys[2];
-    for (int i = 0; i < 2; i++) {
-        unsigned long long b;
-        memcpy(&b, &init[i], 8);
-        keys[i] = b | 0x8000000000000000ull;
-    }
-    memcpy(pin + 512, keys, 16);
-    CU(cudaMemcpyAsync(ctx->raw_misc.p, pin + 512, 16, cudaMemcpyHostToDevice, ctx->stream));
+    a.ring_state = ctx->ring_state.as<RingState>();
+    a.reserved_time = ctx->cfg.reserved_buffer_length + ctx->cfg.stack_interval * 2; // le_vins.cc:156
     k_raw_count<<<nblocks, RAW_BLOCK, 0, ctx->stream>>>(a);
-    k_raw_scan<<<1, 1024, 0, ctx->stream>>>(a.block_kept, nblocks, a.minmax, a.result);
-    k_raw_scatter<<<nblocks, RAW_BLOCK, 0, ctx->stream>>>(a);
-    const double reserved = ctx->cfg.reserved_buffer_length + ctx->cfg.stack_interval * 2; // le_vins.cc:156
-    k_ring_append<<<1, 32, 0, ctx->stream>>>(ctx->ring_state.as<RingState>(), a.ring, cap, 0, reserved, &a.result->count);
-    ctx->launches += 4;
+    k_raw_scatter<<<nblocks, RAW_BLOCK, 0, ctx->stream>>>(a); // + block offsets, result record, ring bookkeeping (last block)
+    ctx->launches += 2;
     CU(cudaGetLastError());
+    ctx->ring_count_ub += n;       // an upper bound until the next read-back
+    ctx->ring_tail_known = false;  // the tail moved by a count only the device knows
+    if (!n_appended && !t_start && !t_end) return LEVINS_OK; // nothing to report: fully asynchronous
     CU(cudaMemcpyAsync(pin + 640, a.result, sizeof(RawResult), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     RawResult res;
     memcpy(&res, pin + 640, sizeof(res));
-    ctx->ring_tail = (ctx->ring_tail + res.count) % cap;
-    ctx->ring_count_ub += res.count;
+    ctx->ring_count_ub -= n - res.count;
     if (n_appended) *n_appended = (size_t) res.count;
     if (t_start) *t_start = res.start;
     if (t_end) *t_end = res.end;
@@ -802,6 +859,7 @@ extern "C" int levins_buffer_clear(levins_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     if (ctx->ring.p) CU(cudaMemsetAsync(ctx->ring_state.p, 0, sizeof(RingState), ctx->stream));
     ctx->ring_tail = 0;
+    ctx->ring_tail_known = true;
     ctx->ring_count_ub = 0;
     ctx->s_cloud_valid = false;
     ctx->s_image_valid = false;
@@ -831,7 +889,7 @@ extern "C" int levins_stack_deskew(levins_ctx* ctx, double stamp, const levins_i
     ctx->s_image_valid = false;
     int r = ensure_stream_buffers(ctx, n_ins, 1);
     if (r) return r;
-    r = run_stage1(ctx, stamp, ins, n_ins, /*write_cloud=*/true, /*bin=*/true);
+    r = run_stage1(ctx, default_ptrs(ctx), stamp, ins, n_ins, /*write_cloud=*/true);
     if (r) return r;
     KfState kf;
     r = fetch_kf(ctx, &kf);
@@ -930,7 +988,7 @@ static int associate_body(levins_ctx* ctx, const float* query_xyz, const float* 
     memcpy(ctx->pinned, qc, sizeof(qc));
     CU(cudaMemcpyAsync(reinterpret_cast<char*>(ctx->s_kf.p) + offsetof(KfState, q_begin), ctx->pinned, sizeof(qc),
                        cudaMemcpyHostToDevice, ctx->stream));
-    r = run_associate_stream(ctx, nf, true, false, px);
+    r = run_associate_stream(ctx, default_ptrs(ctx), nf, true, false, px);
     if (r) return r;
     if (type) CU(cudaMemcpyAsync(type, ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
     if (xyz_depth) CU(cudaMemcpyAsync(xyz_depth, ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
@@ -962,12 +1020,16 @@ extern "C" int levins_associate_pixels(levins_ctx* ctx, const levins_camera* cam
     return associate_body(ctx, nullptr, pixels, nf, px, type, xyz_depth, nullptr, nullptr, nullptr, accepted, pw, undistorted);
 }
 
+// The fused keyframe.  Everything the call sends travels in ONE host->device copy (KfState | INS window | rays or pixels, packed
+// in page-locked memory) and everything it returns in ONE device->host copy (final KfState | RingState | type | xyz_depth |
+// accepted | undistorted | world points: k_plane leaves the states next to the results).
 static int keyframe_body(levins_ctx* ctx, double stamp, const levins_ins_sample* ins, size_t n_ins, const float* query_xyz,
                          const float* pixels, size_t nf, const PixelOpts& px, int8_t* type, float* xyz_depth, uint8_t* accepted, double* pw,
                          float* undistorted, size_t* n_projected_out, size_t* m_out) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     if (nf > ctx->cfg.max_features) return fail(ctx, LEVINS_ERR_CAPACITY, "more features than config.max_features");
+    if (n_ins > ctx->cfg.max_ins) return fail(ctx, LEVINS_ERR_CAPACITY, "INS window larger than config.max_ins");
     if (n_projected_out) *n_projected_out = 0;
     if (m_out) *m_out = 0;
     ctx->s_cloud_valid = false;
@@ -975,7 +1037,61 @@ static int keyframe_body(levins_ctx* ctx, double stamp, const levins_ins_sample*
     int r = ensure_stream_buffers(ctx, n_ins, nf);
     if (r) return r;
     ctx->s_image_from_raw = false;
-    r = run_stage1(ctx, stamp, ins, n_ins, /*write_cloud=*/false, /*bin=*/true, nf);
+    auto a16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+    // input arena
+    const size_t in_ins = 256, in_q = in_ins + a16(n_ins * sizeof(InsSample)), in_px = in_q + a16(nf * 12), in_end = in_px + a16(nf * 8);
+    // output arena
+    const size_t o_ring = 128, o_type = 256, o_xyzd = o_type + a16(nf), o_acc = o_xyzd + nf * 16, o_und = o_acc + a16(nf),
+                 o_pw = o_und + a16(nf * 8), o_end = o_pw + nf * 24;
+    CU(ctx->s_arena_in.ensure(in_end));
+    CU(ctx->s_arena_out.ensure(o_end));
+    if (ctx->pin_io_bytes < in_end + o_end) {
+        if (ctx->pin_io) cudaFreeHost(ctx->pin_io);
+        ctx->pin_io = nullptr;
+        ctx->pin_io_bytes = 0;
+        const size_t want = (in_end + o_end) * 2 + 4096;
+        CU(cudaMallocHost(&ctx->pin_io, want));
+        ctx->pin_io_bytes = want;
+    }
+    char* hin = static_cast<char*>(ctx->pin_io);
+    char* hout = hin + ctx->pin_io_bytes / 2;
+    char* din = ctx->s_arena_in.as<char>();
+    char* dout = ctx->s_arena_out.as<char>();
+    StreamPtrs sp{};
+    sp.kf = reinterpret_cast<KfState*>(din);
+    sp.ins = reinterpret_cast<InsSample*>(din + in_ins);
+    sp.queries = reinterpret_cast<float*>(din + in_q);
+    sp.pixels = reinterpret_cast<float*>(din + in_px);
+    sp.type = reinterpret_cast<int8_t*>(dout + o_type);
+    sp.xyzd = reinterpret_cast<float4*>(dout + o_xyzd);
+    sp.accepted = reinterpret_cast<unsigned char*>(dout + o_acc);
+    sp.undist = reinterpret_cast<float*>(dout + o_und);
+    sp.pw = reinterpret_cast<double*>(dout + o_pw);
+    sp.kf_out = reinterpret_cast<KfState*>(dout);
+    sp.ring_out = reinterpret_cast<RingState*>(dout + o_ring);
+
+    if (!ctx->have_ext) return fail(ctx, LEVINS_ERR_STATE, "levins_set_extrinsics has not been called");
+    if (!ins || n_ins == 0) return fail(ctx, LEVINS_ERR_ARG, "empty INS window");
+    const bool empty = !ctx->ring.p || ctx->ring_count_ub == 0;
+    if (!empty) {
+        KfState kf{};
+        kf.ins_count = n_ins;
+        kf.q_count = nf;
+        kf.stamp = stamp;
+        static_assert(sizeof(KfState) <= 256, "input arena header");
+        memcpy(hin, &kf, sizeof(kf));
+        memcpy(hin + in_ins, ins, n_ins * sizeof(InsSample));
+        size_t used = in_q;
+        if (nf && pixels) {
+            memcpy(hin + in_px, pixels, nf * 8);
+            used = in_px + nf * 8;
+        } else if (nf) {
+            memcpy(hin + in_q, query_xyz, nf * 12);
+            used = in_q + nf * 12;
+        }
+        CU(cudaMemcpyAsync(din, hin, used, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    r = empty ? LEVINS_EMPTY : run_stage1(ctx, sp, stamp, ins, n_ins, /*write_cloud=*/false, nf, /*uploaded=*/true);
     if (r == LEVINS_EMPTY) {
         for (size_t k = 0; k < nf; k++) {
             if (type) type[k] = LEVINS_MAPPOINT_NONE;
@@ -988,37 +1104,36 @@ static int keyframe_body(levins_ctx* ctx, double stamp, const levins_ins_sample*
         return LEVINS_EMPTY;
     }
     if (r) return r;
-    char* pin = reinterpret_cast<char*>(ctx->pinned);
     const bool want_pw = pw && px.pose_ref;
+    KfState kf;
     if (nf) {
-        if (pixels) {
-            memcpy(pin + ctx->pin_q(), pixels, nf * 8);
-            CU(cudaMemcpyAsync(ctx->s_pixels.p, pin + ctx->pin_q(), nf * 8, cudaMemcpyHostToDevice, ctx->stream));
-        } else {
-            memcpy(pin + ctx->pin_q(), query_xyz, nf * 12);
-            CU(cudaMemcpyAsync(ctx->s_queries.p, pin + ctx->pin_q(), nf * 12, cudaMemcpyHostToDevice, ctx->stream));
-        }
-        r = run_associate_stream(ctx, nf, false, true, px); // also counts M
+        r = run_associate_stream(ctx, sp, nf, false, true, px); // also counts M; k_plane leaves the states in the output arena
         if (r) return r;
-        if (type) CU(cudaMemcpyAsync(pin + ctx->pin_type(), ctx->s_type.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
-        if (xyz_depth) CU(cudaMemcpyAsync(pin + ctx->pin_xyzd(), ctx->s_xyzd.p, nf * 16, cudaMemcpyDeviceToHost, ctx->stream));
-        if (accepted) CU(cudaMemcpyAsync(pin + ctx->pin_acc(), ctx->s_accepted.p, nf, cudaMemcpyDeviceToHost, ctx->stream));
-        if (undistorted) CU(cudaMemcpyAsync(pin + ctx->pin_und(), ctx->s_undist.p, nf * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (want_pw) CU(cudaMemcpyAsync(pin + ctx->pin_pw(), ctx->s_pw.p, nf * 24, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    if (!nf) { // no feature kernel to piggy-back the cell count on
-        k_count_cells<<<dim3(64, 1), 256, 0, ctx->stream>>>(ctx->s_kf.as<KfState>(), ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen);
+        size_t span = o_xyzd + nf * 16; // KfState | RingState | type | xyz_depth are always fetched
+        if (px.cam) span = want_pw ? o_end : (undistorted ? o_pw : o_und);
+        CU(cudaMemcpyAsync(hout, dout, span, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream)); // the one synchronisation of the call
+        memcpy(&kf, hout, sizeof(KfState));
+        RingState st;
+        memcpy(&st, hout + o_ring, sizeof(st));
+        ctx->ring_count_ub = st.count;
+        if (type) memcpy(type, hout + o_type, nf);
+        if (xyz_depth) memcpy(xyz_depth, hout + o_xyzd, nf * 16);
+        if (accepted && px.cam) memcpy(accepted, hout + o_acc, nf);
+        if (undistorted && px.cam) memcpy(undistorted, hout + o_und, nf * 8);
+        if (want_pw) memcpy(pw, hout + o_pw, nf * 24);
+    } else { // no feature kernel to piggy-back the cell count and the state copy on
+        k_count_cells<<<dim3(64, 1), 256, 0, ctx->stream>>>(sp.kf, ctx->s_zbuf.as<unsigned long long>(), ctx->s_gen);
         ctx->launches++;
         CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hout, sp.kf, sizeof(KfState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(hout + o_ring, ctx->ring_state.p, sizeof(RingState), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        memcpy(&kf, hout, sizeof(KfState));
+        RingState st;
+        memcpy(&st, hout + o_ring, sizeof(st));
+        ctx->ring_count_ub = st.count;
     }
-    KfState kf;
-    r = fetch_kf(ctx, &kf); // the one synchronisation of the call
-    if (r) return r;
-    if (nf && type) memcpy(type, pin + ctx->pin_type(), nf);
-    if (nf && xyz_depth) memcpy(xyz_depth, pin + ctx->pin_xyzd(), nf * 16);
-    if (nf && accepted) memcpy(accepted, pin + ctx->pin_acc(), nf);
-    if (nf && undistorted) memcpy(undistorted, pin + ctx->pin_und(), nf * 8);
-    if (nf && want_pw) memcpy(pw, pin + ctx->pin_pw(), nf * 24);
     if (n_projected_out) *n_projected_out = kf.n_proj;
     if (m_out) *m_out = kf.m;
     // the fused path keeps no cell array: a later levins_associate() needs levins_build_range_image() first

@@ -210,8 +210,10 @@ class Context:
         pts = np.ascontiguousarray(points, XYZIT)
         self._check(lib().levins_append_scan(self._h, _p(pts), len(pts)))
 
-    def append_raw(self, fmt, records, n, timebase_ns=0, stamp=0.0, to_gps_time=True, scan_line=128, nearest=1.0, farthest=200.0):
-        """levins_append_raw: driver records (flat uint8, n * point_step bytes) -> ring.  Returns (appended, start, end)."""
+    def append_raw(self, fmt, records, n, timebase_ns=0, stamp=0.0, to_gps_time=True, scan_line=128, nearest=1.0, farthest=200.0,
+                   want_result=True):
+        """levins_append_raw: driver records (flat uint8, n * point_step bytes) -> ring.  Returns (appended, start, end); with
+        want_result=False nothing is read back and the call is asynchronous (returns None)."""
         from .rawfmt import RAW_FORMAT
 
         f = np.ascontiguousarray(fmt, RAW_FORMAT).reshape(1)
@@ -221,6 +223,10 @@ class Context:
         L = lib()
         L.levins_append_raw.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint64, C.c_double, C.c_int, C.c_int,
                                         C.c_double, C.c_double, C.POINTER(C.c_size_t), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        if not want_result:
+            self._check(L.levins_append_raw(self._h, _p(f), _p(rec), int(n), int(timebase_ns), float(stamp), int(bool(to_gps_time)),
+                                            int(scan_line), float(nearest), float(farthest), None, None, None))
+            return None
         self._check(L.levins_append_raw(self._h, _p(f), _p(rec), int(n), int(timebase_ns), float(stamp), int(bool(to_gps_time)),
                                         int(scan_line), float(nearest), float(farthest), C.byref(m), C.byref(a), C.byref(b)))
         return m.value, a.value, b.value

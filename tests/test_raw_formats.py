@@ -164,3 +164,30 @@ def test_append_raw_wraps_the_ring(oracle, built_lib):
     assert n == n2 > 0 and cloud.tobytes() == cloud2.tobytes()
     c.close()
     c2.close()
+
+
+@pytest.mark.gpu
+def test_append_raw_without_read_back_then_points(ctx, oracle):
+    """levins_append_raw with no output pointers is asynchronous: the survivor count stays on the device and the next
+    levins_append_scan has to learn the ring's tail from there.  Mixed sequence raw, raw, points, raw; the keyframe must
+    equal the one computed from the oracle-converted points."""
+    kf = synth.make_keyframe(2, pts_per_scan=5000, n_features=48)
+    ctx.set_extrinsics(kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l)
+    rng = np.random.default_rng(21)
+    conv = []
+    for i, s in enumerate(range(0, len(kf.points), 5000)):
+        scan = kf.points[s:s + 5000]
+        rec, tb = rawfmt.livox_records(scan, WEEK, rng=rng, bad_fraction=0.05)
+        raw = rawfmt.as_bytes(rec)
+        want, _, _ = oracle.convert_raw(rawfmt.fmt_livox(), raw, len(rec), tb, 0.0, True, 6, 1.0, 200.0)
+        if i % 3 == 2:
+            ctx.append_scan(want)  # PointXYZIT records from the host converter
+        else:
+            assert ctx.append_raw(rawfmt.fmt_livox(), raw, len(rec), timebase_ns=tb, scan_line=6, want_result=False) is None
+        conv.append(want)
+    pts = np.concatenate(conv)
+    assert ctx.buffer_info()[0] == len(pts)
+    got = ctx.keyframe(kf.stamp, kf.ins, kf.queries)
+    ref = oracle.keyframe(pts, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries)
+    assert got["n_projected"] == ref["n_projected"] and got["m"] == ref["m"]
+    assert np.array_equal(got["type"], ref["type"]) and got["xyz_depth"].tobytes() == ref["xyz_depth"].tobytes()
