@@ -98,6 +98,8 @@ struct __align__(16) KfState {
     int status; // LEVINS_OK / LEVINS_EMPTY
     unsigned int m;
     double ins_t0, ins_t_last, inv_mean_dt;
+    unsigned int ticket; // k_prepare blocks of this keyframe that have finished (streaming: the last one pops the ring)
+    unsigned int pad[3];
 };
 static_assert(sizeof(KfState) % 16 == 0 && sizeof(KfState) <= 128, "KfState is copied in 16-byte chunks");
 

@@ -2,7 +2,7 @@
 //
 //   k_prepare      per keyframe: window search (le_vins.cc:413-437), keyframe pose (le_vins.cc:441-442), the
 //                  per-INS-interval table that replaces the per-point pose interpolation (misc.cc:62-103) and, in
-//                  batches, the chunk descriptors of k_deskew_bin (k_chunk_desc does those for the streaming path)
+//                  the chunk descriptors of k_deskew_bin; grid (keyframes, slices)
 //   k_deskew_bin   per point: range gate + deskew (le_vins.cc:445-464) fused with range-image binning
 //                  (tracking.cc:307-336) through a 64-bit atomicMin key (range bits | point index); persistent warps,
 //                  each with its own TMA ring
@@ -299,13 +299,28 @@ struct __align__(16) ChunkDesc {
     unsigned cnt;            // points in the chunk (0 = empty)
 };
 
+// Index of the INS interval that holds time t (misc.cc:25-60 semantics on the IMU times of the window): i in [1, n - 1] with
+// time[i-1] <= t < time[i], 0 outside the window or when no pair brackets t.  Near-uniform sampling: the guess from the mean
+// spacing is almost always right; otherwise bisection.
+__device__ __forceinline__ int interval_of_time(const InsSample* __restrict__ w, int nins, double t, double t0, double t_last, double inv_mean_dt) {
+    if (nins < 2 || t0 > t || t_last <= t) return 0; // misc.cc:28-30
+    int g = 1 + (int) ((t - t0) * inv_mean_dt);
+    g = min(max(g, 1), nins - 1);
+    if (w[g - 1].time <= t && t < w[g].time) return g;
+    int lo = 1, hi = nins - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (w[mid].time > t) hi = mid; else lo = mid + 1;
+    }
+    return (w[lo - 1].time <= t && t < w[lo].time) ? lo : 0;
+}
+
 // Descriptor of chunk `c` of a keyframe.  The entry index is only a hint for k_deskew_bin (every point still checks
 // that its entry brackets it), so any answer is correct; the right one is fast.  k_deskew_bin stages entries idx and
 // idx + 1: the next interval, the fallback copy in slot nins after the last one, the first interval for a chunk that
-// starts before the window.  NC = false inside the kernel that has just written the table.
-template <bool NC>
+// starts before the window.
 __device__ __forceinline__ ChunkDesc chunk_desc_from_time(unsigned c, unsigned n_proj, unsigned long long phys, double t_point, double td_b_l,
-                                                          const Interval* __restrict__ tab, unsigned long long table_begin, int nins,
+                                                          const InsSample* __restrict__ w, unsigned long long table_begin, int nins,
                                                           double t0, double t_last, double inv_mean_dt) {
     ChunkDesc d;
     d.phys = 0;
@@ -313,39 +328,17 @@ __device__ __forceinline__ ChunkDesc chunk_desc_from_time(unsigned c, unsigned n
     d.cnt = 0;
     const unsigned off = c * CHUNK_PTS;
     if (off < n_proj) {
-        const double t = t_point + td_b_l; // le_vins.cc:455
-        int idx = 0;
-        if (!(nins < 2 || t0 > t || t_last <= t)) { // misc.cc:28-30
-            int g = 1 + (int) ((t - t0) * inv_mean_dt);
-            g = min(max(g, 1), nins - 1);
-            double2 ab;
-            if (NC) {
-                ab = __ldg(reinterpret_cast<const double2*>(tab + g));
-            } else {
-                const volatile double* pv = reinterpret_cast<const volatile double*>(tab + g);
-                ab.x = pv[0];
-                ab.y = pv[1];
-            }
-            idx = ((ab.x <= t) && (t < ab.y)) ? g : find_interval_slow<NC>(tab, nins, t, g, 1, nins - 1);
-        }
+        const int idx = interval_of_time(w, nins, t_point + td_b_l /* le_vins.cc:455 */, t0, t_last, inv_mean_dt);
         d.phys = phys;
         d.ent0 = (unsigned) (table_begin + idx);
         d.cnt = min((unsigned) CHUNK_PTS, n_proj - off);
     }
     return d;
 }
-template <bool NC>
-__device__ __forceinline__ ChunkDesc make_chunk_desc(unsigned c, unsigned n_proj, unsigned long long proj_begin, const PointXYZIT* __restrict__ pts,
-                                                     unsigned long long pts_cap, double td_b_l, const Interval* __restrict__ tab,
-                                                     unsigned long long table_begin, int nins, double t0, double t_last, double inv_mean_dt) {
-    const unsigned off = c * CHUNK_PTS;
-    const unsigned long long phys = off < n_proj ? wrap(proj_begin + off, pts_cap) : 0ull;
-    const double t_point = off < n_proj ? pts[phys].time : 0.0;
-    return chunk_desc_from_time<NC>(c, n_proj, phys, t_point, td_b_l, tab, table_begin, nins, t0, t_last, inv_mean_dt);
-}
 
 // ------------------------------------------------------------------------------------------------
-// k_prepare: one block per keyframe
+// k_prepare: grid (keyframes, slices).  Every block of a keyframe repeats the three window searches (a handful of dependent
+// loads) and the keyframe pose; the INS-interval table and the chunk descriptors are split over the slices.
 // ------------------------------------------------------------------------------------------------
 struct PrepareArgs {
     KfState* kfs;
@@ -353,7 +346,7 @@ struct PrepareArgs {
     unsigned long long pts_cap; // ring capacity (ULLONG_MAX for linear pools)
     const InsSample* ins;
     Interval* table;
-    ChunkDesc* chunks; // batch: [gridDim.x][chunks_per_kf], written here; streaming (null): k_chunk_desc does it
+    ChunkDesc* chunks; // [gridDim.x][chunks_per_kf]
     unsigned chunks_per_kf;
     RingState* ring; // streaming: the keyframe's buffer is the ring (le_vins.cc:410-437), and is popped
     Extrinsics ext;
@@ -435,14 +428,15 @@ __device__ __forceinline__ void fill_cull_record(Interval& e, const Extrinsics& 
     e.pad[0] = e.pad[1] = 0.f;
 }
 
-__global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ PrepareArgs a) {
+__global__ void __launch_bounds__(256, 2) k_prepare(const __grid_constant__ PrepareArgs a) {
     KfState* kf = a.kfs + blockIdx.x;
     __shared__ double sR0[9], st0[3];
     __shared__ unsigned long long s_first, s_end, s_begin, s_count;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned slice = blockIdx.y, n_slices = gridDim.y;
 
     if (threadIdx.x == 0) {
-        if (a.ring) {
+        if (a.ring) { // (the ring state is only changed by the last block of the grid to finish, see below)
             s_begin = a.ring->head;
             s_count = a.ring->count;
         } else {
@@ -484,24 +478,24 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
     }
     __syncthreads();
 
-    if (threadIdx.x == 0) {
-        const unsigned long long first = s_first;
-        const unsigned long long end = s_end > first ? s_end : first;
-        kf->proj_begin = wrap(begin + first, a.pts_cap); // the projected slice starts at the first kept point
+    const unsigned long long first = s_first;
+    const unsigned long long end = s_end > first ? s_end : first;
+    const unsigned n_proj = (unsigned) (end - first);
+    const unsigned long long proj_begin = wrap(begin + first, a.pts_cap); // the projected slice starts at the first kept point
+    const double t_first = w[0].time, t_last = w[nins - 1].time;
+    const double inv_mean_dt = nins > 1 ? (double) (nins - 1) / (t_last - t_first) : 0.0;
+    if (slice == 0 && threadIdx.x == 0) {
+        kf->proj_begin = proj_begin;
         kf->first = (unsigned) first;
-        kf->n_proj = (unsigned) (end - first);
-        kf->status = (end - first) == 0 ? 1 : 0; // le_vins.cc:426-429 / 469
+        kf->n_proj = n_proj;
+        kf->status = n_proj == 0 ? 1 : 0; // le_vins.cc:426-429 / 469
         kf->m = 0;
-        kf->ins_t0 = w[0].time;
-        kf->ins_t_last = w[nins - 1].time;
-        kf->inv_mean_dt = nins > 1 ? (double) (nins - 1) / (w[nins - 1].time - w[0].time) : 0.0;
-        if (a.ring) { // the pops are persistent (the deque is shared state)
-            a.ring->head = wrap(begin + first, a.pts_cap);
-            a.ring->count = count - first;
-        }
+        kf->ins_t0 = t_first;
+        kf->ins_t_last = t_last;
+        kf->inv_mean_dt = inv_mean_dt;
     }
 
-    // per-interval table
+    // this slice's part of the per-interval table
     double R0[9], t0[3];
 #pragma unroll
     for (int i = 0; i < 9; i++) R0[i] = sR0[i];
@@ -509,7 +503,9 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
     t0[1] = st0[1];
     t0[2] = st0[2];
     Interval* __restrict__ tab = a.table + kf->table_begin;
-    for (int j = threadIdx.x; j < nins; j += blockDim.x) {
+    const int per_slice = (nins + (int) n_slices - 1) / (int) n_slices;
+    const int j_end = min(nins, (int) (slice + 1) * per_slice);
+    for (int j = (int) slice * per_slice + (int) threadIdx.x; j < j_end; j += blockDim.x) {
         Interval e;
         double Rq[9], C[9], d[3];
         if (j == 0) { // out-of-window fallback: newest state, no interpolation (misc.cc:74-77)
@@ -561,29 +557,26 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
         e.fast = (ordered && e.theta * e.theta < 2.44140625e-4) ? 1.0 : 0.0;
         fill_cull_record(e, a.ext, j == 0);
         tab[j] = e;
-        if (j == 0) tab[nins] = e; // slot nins: the fallback again, as the successor of the last interval (k_chunk_desc)
+        if (j == 0) tab[nins] = e; // slot nins: the fallback again, as the successor of the last interval
     }
-    // batch mode: the chunk descriptors of this keyframe (k_deskew_bin's work list), while the table is hot in L1/L2
-    if (a.chunks) {
-        __syncthreads(); // the table entries written by the other threads of the block are visible now
-        const unsigned long long first = s_first;
-        const unsigned long long end = s_end > first ? s_end : first;
-        const unsigned n_proj = (unsigned) (end - first);
-        const unsigned long long proj_begin = wrap(begin + first, a.pts_cap);
-        const double t_first = w[0].time, t_last = w[nins - 1].time;
-        const double inv_mean_dt = nins > 1 ? (double) (nins - 1) / (t_last - t_first) : 0.0;
-        const unsigned long long table_begin = kf->table_begin;
+
+    // this slice's part of the chunk descriptors (k_deskew_bin's work list).  The interval hints come from the IMU times of
+    // the window (input), not from the table (other slices are still writing it).
+    {
         ChunkDesc* __restrict__ out = a.chunks + (size_t) blockIdx.x * a.chunks_per_kf;
+        const unsigned long long table_begin = kf->table_begin;
+        const unsigned cps = (a.chunks_per_kf + n_slices - 1) / n_slices;
+        const unsigned c_begin = slice * cps, c_end = min(a.chunks_per_kf, c_begin + cps);
         // all first-point times of this thread's chunks first (independent loads, one memory round trip), then the probes;
         // chunks past the projected points only get an empty descriptor
         constexpr int ROUNDS = 8;
-        for (unsigned base = 0; base < a.chunks_per_kf; base += ROUNDS * 256u) {
+        for (unsigned base = c_begin; base < c_end; base += ROUNDS * 256u) {
             if ((unsigned long long) base * CHUNK_PTS >= n_proj) { // nothing live from here on
                 ChunkDesc e;
                 e.phys = 0;
                 e.ent0 = 0;
                 e.cnt = 0;
-                for (unsigned c = base + threadIdx.x; c < a.chunks_per_kf; c += 256u) out[c] = e;
+                for (unsigned c = base + threadIdx.x; c < c_end; c += 256u) out[c] = e;
                 break;
             }
             double tp[ROUNDS];
@@ -592,15 +585,30 @@ __global__ void __launch_bounds__(256) k_prepare(const __grid_constant__ Prepare
             for (int i = 0; i < ROUNDS; i++) {
                 const unsigned c = base + threadIdx.x + i * 256u;
                 const unsigned long long off = (unsigned long long) c * CHUNK_PTS;
-                const bool live = c < a.chunks_per_kf && off < n_proj;
+                const bool live = c < c_end && off < n_proj;
                 ph[i] = live ? wrap(proj_begin + off, a.pts_cap) : 0ull;
                 tp[i] = live ? a.pts[ph[i]].time : 0.0;
             }
 #pragma unroll
             for (int i = 0; i < ROUNDS; i++) {
                 const unsigned c = base + threadIdx.x + i * 256u;
-                if (c < a.chunks_per_kf)
-                    out[c] = chunk_desc_from_time<false>(c, n_proj, ph[i], tp[i], a.ext.td_b_l, tab, table_begin, nins, t_first, t_last, inv_mean_dt);
+                if (c < c_end)
+                    out[c] = chunk_desc_from_time(c, n_proj, ph[i], tp[i], a.ext.td_b_l, w, table_begin, nins, t_first, t_last, inv_mean_dt);
+            }
+        }
+    }
+
+    // streaming: the pops are persistent (the deque is shared state).  Every block of the grid read the ring state at its
+    // start, so the last one to get here may change it.
+    if (a.ring) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned done = atomicAdd(&kf->ticket, 1u);
+            if (done == gridDim.x * gridDim.y - 1) {
+                a.ring->head = proj_begin;
+                a.ring->count = count - first;
+                kf->ticket = 0;
             }
         }
     }
@@ -665,18 +673,6 @@ struct DeskewArgs {
     Extrinsics ext;
     Consts c;
 };
-
-// k_chunk_desc: one thread per chunk (streaming: a single keyframe with many chunks; batches get their descriptors from
-// k_prepare)
-__global__ void __launch_bounds__(256) k_chunk_desc(const __grid_constant__ DeskewArgs a) {
-    const unsigned c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= a.n_kf * a.chunks_per_kf) return;
-    const unsigned kfi = c / a.chunks_per_kf;
-    const KfState* __restrict__ kf = a.kfs + kfi;
-    a.chunks[c] = make_chunk_desc<true>(c - kfi * a.chunks_per_kf, kf->n_proj, kf->proj_begin, a.pts, a.pts_cap, a.ext.td_b_l,
-                                        a.table + kf->table_begin, kf->table_begin, (int) kf->ins_count, kf->ins_t0, kf->ins_t_last,
-                                        kf->inv_mean_dt);
-}
 
 // ---- mbarrier / TMA bulk-copy primitives (PTX) ----
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned) __cvta_generic_to_shared(p); }

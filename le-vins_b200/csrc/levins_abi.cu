@@ -247,7 +247,7 @@ int ensure_ring(levins_ctx* ctx) {
     return LEVINS_OK;
 }
 
-// Chunk descriptors for k_deskew_bin: size the buffer for `n_kf` keyframes of at most `max_pts` points ...
+// Chunk descriptors for k_deskew_bin (written by k_prepare): size the buffer for `n_kf` keyframes of at most `max_pts` points
 int size_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf) {
     a.n_kf = n_kf;
     a.chunks_per_kf = (unsigned) ((max_pts + CHUNK_PTS - 1) / CHUNK_PTS);
@@ -257,21 +257,17 @@ int size_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf)
     a.chunks = ctx->chunks.as<ChunkDesc>();
     return LEVINS_OK;
 }
-// ... and fill it with one thread per chunk (streaming: one keyframe, many chunks; needs the KfState written by
-// k_prepare).  Batches get their descriptors from k_prepare itself.
-int launch_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf) {
-    int r = size_chunks(ctx, a, max_pts, n_kf);
-    if (r) return r;
-    const uint64_t total = (uint64_t) a.n_kf * a.chunks_per_kf;
-    if (total == 0) return LEVINS_OK;
-    k_chunk_desc<<<(unsigned) ((total + 255) / 256), 256, 0, ctx->stream>>>(a);
-    ctx->launches++;
-    CU(cudaGetLastError());
-    return LEVINS_OK;
+// k_prepare's grid: one row of blocks per keyframe, enough slices that a block writes at most 2 048 chunk descriptors, and at
+// least a few slices when there are few keyframes (the interval table is split over them as well)
+dim3 prepare_grid(const levins_ctx* ctx, unsigned n_kf, unsigned chunks_per_kf) {
+    unsigned slices = std::max(1u, (chunks_per_kf + 2047u) / 2048u);
+    const unsigned room = (unsigned) (2 * ctx->num_sms) / std::max(1u, n_kf); // blocks per keyframe that still run in one wave
+    slices = std::max(slices, std::min(4u, room));
+    return dim3(n_kf, std::min(slices, 65535u));
 }
 
 // k_deskew_bin is persistent: one 16-warp CTA per SM (221 KB of TMA staging), every warp walking its own chunk list.
-// launch_chunks() must have filled a.chunks / a.chunks_per_kf.
+// k_prepare must have filled a.chunks / a.chunks_per_kf.
 int launch_deskew(levins_ctx* ctx, DeskewArgs& a, bool write_cloud) {
     const unsigned total = a.n_kf * a.chunks_per_kf;
     if (total == 0) return LEVINS_OK;
@@ -356,21 +352,18 @@ int run_stage1(levins_ctx* ctx, const StreamPtrs& sp, double stamp, const levins
         memcpy(ctx->pinned, &kf, sizeof(kf));
         CU(cudaMemcpyAsync(sp.kf, ctx->pinned, sizeof(kf), cudaMemcpyHostToDevice, ctx->stream));
     }
-    // one keyframe: its block writes the chunk descriptors too unless the ring holds very many points (the descriptors of
-    // chunks past the projected window are empty and cost a store each)
-    const bool fused_desc = da.chunks_per_kf <= 8192;
     PrepareArgs pa{};
     pa.kfs = sp.kf;
     pa.pts = ctx->ring.as<PointXYZIT>();
     pa.pts_cap = ctx->cfg.max_points;
     pa.ins = sp.ins;
     pa.table = ctx->s_table.as<Interval>();
-    pa.chunks = fused_desc ? da.chunks : nullptr;
+    pa.chunks = da.chunks;
     pa.chunks_per_kf = da.chunks_per_kf;
     pa.ring = ctx->ring_state.as<RingState>();
     pa.ext = ctx->ext;
     pa.c = ctx->consts;
-    k_prepare<<<1, 256, 0, ctx->stream>>>(pa);
+    k_prepare<<<prepare_grid(ctx, 1, da.chunks_per_kf), 256, 0, ctx->stream>>>(pa);
     ctx->launches++;
     CU(cudaGetLastError());
 
@@ -387,10 +380,6 @@ int run_stage1(levins_ctx* ctx, const StreamPtrs& sp, double stamp, const levins
     da.gen = ctx->s_gen;
     da.ext = ctx->ext;
     da.c = ctx->consts;
-    if (!fused_desc) {
-        int r = launch_chunks(ctx, da, n_ub, 1);
-        if (r) return r;
-    }
     return launch_deskew(ctx, da, write_cloud);
 }
 
@@ -1488,21 +1477,13 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         // window search, interval tables and chunk descriptors of the wave (one block per keyframe)
         r = size_chunks(ctx, da, max_pts, (unsigned) nw);
         if (r) return r;
-        // (a keyframe's block writes its own descriptors when that is a few rounds of its 256 threads; keyframes with
-        // more chunks than that leave them to k_chunk_desc, one thread per chunk)
-        const bool fused_desc = da.chunks_per_kf <= 2048;
         pa.kfs = ctx->b_kfs.as<KfState>() + k0;
-        pa.chunks = fused_desc ? da.chunks : nullptr;
+        pa.chunks = da.chunks;
         pa.chunks_per_kf = da.chunks_per_kf;
         mark(0, true);
-        k_prepare<<<(unsigned) nw, 256, 0, ctx->stream>>>(pa);
+        k_prepare<<<prepare_grid(ctx, (unsigned) nw, da.chunks_per_kf), 256, 0, ctx->stream>>>(pa);
         ctx->launches++;
         CU(cudaGetLastError());
-        if (!fused_desc) {
-            k_chunk_desc<<<(unsigned) (((uint64_t) da.n_kf * da.chunks_per_kf + 255) / 256), 256, 0, ctx->stream>>>(da);
-            ctx->launches++;
-            CU(cudaGetLastError());
-        }
         mark(0, false);
         if (max_pts) {
             mark(1, true);
