@@ -448,6 +448,12 @@ def run_gpu(args):
     if rank == 0 and world == 1 and not args.no_also:
         also = bench_cfg2(torch, abi, synth, local_rank, stream, peak)
 
+    # ---- BASELINE configs[4]: the offline batch of independent Ouster keyframes, generated on the device from per-keyframe
+    #      seeds, sharded over the ranks, with the gather of the depths ----
+    cfg5 = None
+    if not args.no_cfg5:
+        cfg5 = bench_cfg5(torch, dist, abi, args, rank, world, local_rank, stream, peak)
+
     # ---- CPU baseline on a bounded sample (rank 0 only), and the parity of the timed batch's results against it ----
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -505,6 +511,7 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "parity": parity,
             "also": also,
+            "cfg5_offline_batch": cfg5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -516,6 +523,113 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     ctx.close()
+
+
+def bench_cfg5(torch, dist, abi, args, rank, world, device, stream, peak, steps=5):
+    """BASELINE configs[4]: an offline batch of independent Ouster OS1-128 keyframes (the reference's default 0.5 s stack
+    window: 5 scans = 655 360 points, 300 features each), 10 000 of them at 8 GPUs = 1 250 per GPU (weak scaling at other N).
+    The keyframes are GENERATED ON THE DEVICE from per-keyframe seeds (le-vins_b200/harness/synthgen.cu) and attached without a
+    copy; the per-feature results of all ranks are exchanged through the C ABI.  Rank 0 re-generates a few keyframes on the
+    host with the generator's numpy twin (bit-identical, tests/test_synthgen.py) and checks the GPU results against the oracle."""
+    from levins import synthgen
+
+    sp = synthgen.Spec()
+    n_kf = args.cfg5_keyframes
+    first = rank * n_kf
+    gen = synthgen.DeviceGenerator(torch, device, sp)
+    d_pts, d_ins, d_q = gen.generate(first, n_kf)
+    ctx = abi.Context(device, stack_interval=sp.stack_interval)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_extrinsics(sp.rig.pose_b_c, sp.rig.pose_c_l, sp.td_b_l)
+    ctx.batch_attach_device(d_pts.data_ptr(), n_kf * sp.per_kf, d_ins.data_ptr(), n_kf * sp.n_ins, d_q.data_ptr(), n_kf * sp.n_feat,
+                            gen.descs(first, n_kf))
+    nq = n_kf * sp.n_feat
+    comm = None
+    if world > 1:
+        if args.gather == "peer":
+            mine = torch.from_numpy(ctx.peer_export(world, nq)).to(d_q.device)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.peer_attach(rank, world, torch.stack(allh).cpu().numpy())
+        else:
+            uid = torch.from_numpy(abi.Context.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).to(d_q.device)
+            dist.broadcast(uid, 0)
+            comm = ctx.comm_init(uid.cpu().numpy(), world, rank)
+        dist.barrier()
+
+    def step():
+        ctx.batch_run()
+        if comm is not None:
+            ctx.gather(comm, world)
+
+    def finish():
+        if world > 1 and comm is None:
+            ctx.peer_wait()
+
+    for _ in range(2):
+        step()
+    finish()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    finish()
+    e1.record(stream)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=d_q.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    out = ctx.batch_download()
+    gathered_ok = None
+    if world > 1:  # what arrived from the other ranks is what they computed: compare rank 0's slot everywhere via a checksum
+        g = ctx.gathered_download(world)
+        mine_ok = bool(np.array_equal(g["type"][rank, :nq], out["type"]) and g["xyz_depth"][rank, :nq].tobytes() == out["xyz_depth"].tobytes())
+        sums = torch.tensor([float(g["xyz_depth"][r, :nq, 3].astype(np.float64).sum()) for r in range(world)], dtype=torch.float64,
+                            device=d_q.device)
+        ref = sums.clone()
+        dist.broadcast(ref, 0)
+        ok = torch.tensor([1.0 if (mine_ok and bool(torch.equal(sums, ref))) else 0.0], dtype=torch.float64, device=d_q.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gathered_ok = bool(ok.item() == 1.0)
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        import oracle_py as orc
+
+        orc.build()
+        dirs = synthgen.directions()
+        res = {}
+        for k in (0, n_kf // 2, n_kf - 1):
+            pts, ins, q = synthgen.keyframe_numpy(sp, first + k, dirs)
+            res[k] = orc.keyframe(pts, sp.stamp(first + k), ins, sp.rig.pose_b_c, sp.rig.pose_c_l, sp.td_b_l, q, sp.stack_interval,
+                                  nthreads=host_cores())
+        parity = parity_report(out, res, sp.n_feat)
+    npts = int(out["n_projected"].astype(np.int64).sum())
+    if world > 1:
+        dist.barrier()
+        if comm is not None:
+            abi.Context.comm_destroy(comm)
+        else:
+            ctx.peer_detach()
+        dist.barrier()
+    ctx.close()
+    del d_pts, d_ins, d_q
+    return {"workload": f"cfg5_offline_os1_128_x{sp.scans_per_kf}scans_F{sp.n_feat}_{n_kf}_keyframes_per_gpu_generated_on_device",
+            "keyframes_total": world * n_kf, "ms_per_step": ms, "keyframes_per_s": world * n_kf / (ms * 1e-3),
+            "features_per_s": world * nq / (ms * 1e-3), "lidar_pts_per_s": world * npts / (ms * 1e-3),
+            "points_per_keyframe": npts // n_kf, "cells_per_keyframe": int(out["m"].mean()),
+            "associated_fraction": float((out["type"] == 1).mean()),
+            "whole_step_hbm_frac": 32.0 * npts / (ms * 1e-3) / 1e9 / peak, "resident_point_bytes_per_gpu": int(d_bytes(n_kf, sp)),
+            "gather": (args.gather if world > 1 else None), "gathered_blocks_consistent": gathered_ok, "parity": parity}
+
+
+def d_bytes(n_kf, sp):
+    return n_kf * sp.per_kf * 32
 
 
 def bench_cfg2(torch, abi, synth, device, stream, peak, n_kf=256, steps=10):
@@ -639,6 +753,8 @@ def main():
     ap.add_argument("--wave", type=int, default=0, help="keyframes per wave of launches (0 = library default)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the device-generated offline batch (configs[4])")
+    ap.add_argument("--cfg5-keyframes", type=int, default=1250, help="keyframes per GPU of the offline batch (10 000 at 8 GPUs)")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurement (configs[1] as a resident batch)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="exchange step at N > 1 (both through the C ABI)")

@@ -283,6 +283,11 @@ typedef struct levins_keyframe_desc {
 int levins_batch_upload(levins_ctx *ctx, const levins_point_xyzit *points, size_t n_points,
                         const levins_ins_sample *ins, size_t n_ins, const float *query_xyz, size_t n_queries,
                         const levins_keyframe_desc *descs, size_t n_keyframes);
+/* The same for pools that already live in this GPU's memory (produced there by another stage, or by a generator): nothing is
+ * copied, the three pools stay the caller's and must outlive the batch; `descs` is a host array as above. */
+int levins_batch_attach_device(levins_ctx *ctx, const levins_point_xyzit *d_points, size_t n_points, const levins_ins_sample *d_ins,
+                               size_t n_ins, const float *d_query_xyz, size_t n_queries, const levins_keyframe_desc *descs,
+                               size_t n_keyframes);
 /* The same with the points as packed 16-byte records: x, y, z and the point's time as the LiDAR drivers deliver it, a u32
  * count of nanoseconds after its scan's stamp (Ouster `t`, Livox `offset_time`; ROS/lidar/lidar_converter.cc:162, :245:
  * time = stamp + t * 1e-9).  These are the fields of a driver record this path reads (intensity is never used), so the upload

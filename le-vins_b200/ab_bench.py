@@ -19,7 +19,7 @@ if __name__ == "__main__":
             if lib != "product":
                 env["LEVINS_LIB"] = os.path.join(HERE, "variants", lib + ".so")
             r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--no-cpu",
-                                "--no-stream", "--e2e-steps", "2"] + extra + [f for f in flags.split(",") if f],
+                                "--no-stream", "--no-cfg5", "--e2e-steps", "2"] + extra + [f for f in flags.split(",") if f],
                                env=env, capture_output=True, text=True)
             try:
                 d = json.loads(r.stdout.strip().splitlines()[-1])

@@ -107,6 +107,11 @@ struct levins_ctx {
     DevBuf b_zbuf, b_cells;
     std::vector<levins_keyframe_desc> b_descs;
     std::vector<KfState> b_kfs_host;
+    // levins_batch_attach_device: the pools are the caller's device memory (null: the library's own b_pts / b_ins / b_queries)
+    const void *b_pts_view = nullptr, *b_ins_view = nullptr, *b_queries_view = nullptr;
+    const PointXYZIT* batch_pts() const { return static_cast<const PointXYZIT*>(b_pts_view ? b_pts_view : b_pts.p); }
+    const InsSample* batch_ins() const { return static_cast<const InsSample*>(b_ins_view ? b_ins_view : b_ins.p); }
+    const float* batch_queries() const { return static_cast<const float*>(b_queries_view ? b_queries_view : b_queries.p); }
     DevBuf b_packed, b_scans; // levins_batch_upload_packed: the records as uploaded, the scan stamps
     size_t b_nq = 0, b_npts = 0, b_nins = 0;
     int b_wave = 256;
@@ -1305,8 +1310,11 @@ extern "C" int levins_batch_set_wave(levins_ctx* ctx, int w) {
 // shared by the two upload entry points: validate the descriptors, size the pools, copy INS / queries / keyframe states.
 // The point pool itself is filled by the caller (a plain copy, or a copy of packed records + k_unpack).
 static int batch_prepare(levins_ctx* ctx, size_t n_points, const levins_ins_sample* ins, size_t n_ins, const float* query_xyz,
-                         size_t n_queries, const levins_keyframe_desc* descs, size_t n_kf) {
+                         size_t n_queries, const levins_keyframe_desc* descs, size_t n_kf, bool borrowed = false) {
     ctx->b_valid = false;
+    ctx->b_pts_view = nullptr;
+    ctx->b_ins_view = nullptr;
+    ctx->b_queries_view = nullptr;
     if (n_kf == 0) return fail(ctx, LEVINS_ERR_ARG, "no keyframes");
     std::vector<KfState>& kfs = ctx->b_kfs_host; // a member: the copy below stays asynchronous
     kfs.resize(n_kf);
@@ -1328,18 +1336,22 @@ static int batch_prepare(levins_ctx* ctx, size_t n_points, const levins_ins_samp
         table_entries += d.ins_count + 1; // + the fallback copy (k_prepare)
         kfs[k] = s;
     }
-    CU(ctx->b_pts.ensure(std::max<size_t>(n_points, 1) * sizeof(PointXYZIT)));
-    CU(ctx->b_ins.ensure(n_ins * sizeof(InsSample)));
+    if (!borrowed) {
+        CU(ctx->b_pts.ensure(std::max<size_t>(n_points, 1) * sizeof(PointXYZIT)));
+        CU(ctx->b_ins.ensure(n_ins * sizeof(InsSample)));
+        CU(ctx->b_queries.ensure(std::max<size_t>(n_queries, 1) * 12));
+    }
     CU(ctx->b_table.ensure(table_entries * sizeof(Interval)));
-    CU(ctx->b_queries.ensure(std::max<size_t>(n_queries, 1) * 12));
     CU(ctx->b_kfs.ensure(n_kf * sizeof(KfState)));
     CU(ctx->b_results.ensure(std::max<size_t>(n_queries, 1) * 17));
     ctx->b_results_nq = std::max<size_t>(n_queries, 1);
     CU(ctx->b_flags.ensure(std::max<size_t>(n_queries, 1) * 4));
     CU(ctx->b_nn.ensure(std::max<size_t>(n_queries, 1) * 80));
     CU(ctx->b_nn_meta.ensure(std::max<size_t>(n_queries, 1) * 8));
-    CU(cudaMemcpyAsync(ctx->b_ins.p, ins, n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
-    if (n_queries) CU(cudaMemcpyAsync(ctx->b_queries.p, query_xyz, n_queries * 12, cudaMemcpyHostToDevice, ctx->stream));
+    if (!borrowed) {
+        CU(cudaMemcpyAsync(ctx->b_ins.p, ins, n_ins * sizeof(InsSample), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_queries) CU(cudaMemcpyAsync(ctx->b_queries.p, query_xyz, n_queries * 12, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CU(cudaMemcpyAsync(ctx->b_kfs.p, kfs.data(), n_kf * sizeof(KfState), cudaMemcpyHostToDevice, ctx->stream));
     ctx->b_descs.assign(descs, descs + n_kf);
     ctx->b_nq = n_queries;
@@ -1359,6 +1371,31 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
     int r = batch_prepare(ctx, n_points, ins, n_ins, query_xyz, n_queries, descs, n_kf);
     if (r) return r;
     CU(cudaMemcpyAsync(ctx->b_pts.p, points, n_points * sizeof(PointXYZIT), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->b_valid = true;
+    return LEVINS_OK;
+}
+
+extern "C" int levins_batch_attach_device(levins_ctx* ctx, const levins_point_xyzit* d_points, size_t n_points,
+                                          const levins_ins_sample* d_ins, size_t n_ins, const float* d_query_xyz, size_t n_queries,
+                                          const levins_keyframe_desc* descs, size_t n_kf) {
+    if (!ctx || !d_points || !d_ins || !descs || (!d_query_xyz && n_queries)) return fail(ctx, LEVINS_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, d_points) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != ctx->device) {
+        cudaGetLastError();
+        return fail(ctx, LEVINS_ERR_ARG, "d_points is not device memory of this context's GPU");
+    }
+    // the library's own pools are released: the batch now lives in the caller's memory
+    ctx->b_pts.release();
+    ctx->b_ins.release();
+    ctx->b_queries.release();
+    int r = batch_prepare(ctx, n_points, nullptr, n_ins, nullptr, n_queries, descs, n_kf, /*borrowed=*/true);
+    if (r) return r;
+    ctx->b_pts_view = d_points;
+    ctx->b_ins_view = d_ins;
+    ctx->b_queries_view = d_query_xyz;
     ctx->b_valid = true;
     return LEVINS_OK;
 }
@@ -1443,9 +1480,9 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
 
     PrepareArgs pa{};
     pa.kfs = ctx->b_kfs.as<KfState>();
-    pa.pts = ctx->b_pts.as<PointXYZIT>();
+    pa.pts = ctx->batch_pts();
     pa.pts_cap = ~0ull;
-    pa.ins = ctx->b_ins.as<InsSample>();
+    pa.ins = ctx->batch_ins();
     pa.table = ctx->b_table.as<Interval>();
     pa.ring = nullptr;
     pa.ext = ctx->ext;
@@ -1466,7 +1503,7 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         if (r) return r;
         DeskewArgs da{};
         da.kfs = ctx->b_kfs.as<KfState>() + k0;
-        da.pts = ctx->b_pts.as<PointXYZIT>();
+        da.pts = ctx->batch_pts();
         da.pts_cap = ~0ull;
         da.table = ctx->b_table.as<Interval>();
         da.zbuf = ctx->b_zbuf.as<unsigned long long>();
@@ -1502,11 +1539,11 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         if (max_q) {
             AssocArgs aa{};
             aa.kfs = ctx->b_kfs.as<KfState>() + k0;
-            aa.queries = ctx->b_queries.as<float>();
+            aa.queries = ctx->batch_queries();
             aa.cells = nullptr;
             aa.c2c = nullptr;
             aa.zbuf = ctx->b_zbuf.as<unsigned long long>();
-            aa.pts = ctx->b_pts.as<PointXYZIT>();
+            aa.pts = ctx->batch_pts();
             aa.pts_cap = ~0ull;
             aa.table = ctx->b_table.as<Interval>();
             aa.gen = ctx->b_gen;
@@ -1527,7 +1564,7 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
     CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_counted, 0)); // join the side stream
     if (ctx->b_nq) { // plane fits for every feature of the batch in one launch (one thread per feature)
         PlaneArgs pl{};
-        pl.queries = ctx->b_queries.as<float>();
+        pl.queries = ctx->batch_queries();
         pl.nn = ctx->b_nn.as<float4>();
         pl.nn_meta = ctx->b_nn_meta.as<uint2>();
         pl.q_begin = 0;

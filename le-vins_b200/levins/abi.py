@@ -30,7 +30,7 @@ EXPORTS = [
     "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host", "levins_append_raw",
     "levins_append_wait", "levins_ins_window_index", "levins_comm_unique_id", "levins_comm_init", "levins_comm_destroy",
     "levins_gather", "levins_peer_export", "levins_peer_attach", "levins_peer_wait", "levins_peer_detach", "levins_gathered_pointer",
-    "levins_gathered_download", "levins_batch_upload_packed", "levins_associate_pixels", "levins_keyframe_pixels", "levins_plane_estimation_batch",
+    "levins_gathered_download", "levins_batch_upload_packed", "levins_batch_attach_device", "levins_associate_pixels", "levins_keyframe_pixels", "levins_plane_estimation_batch",
     "levins_point_to_plane_std_batch", "levins_depth_factor_batch", "levins_chi2_culling_batch", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
 ]
 
@@ -111,6 +111,7 @@ def lib():
             "levins_point_to_plane_std_batch": [vp, vp, sz, vp, sz, dbl, vp],
             "levins_depth_factor_batch": [vp, vp, vp, sz, dbl, dbl, vp, vp, vp],
             "levins_chi2_culling_batch": [vp, vp, sz, sz, dbl, vp, vp],
+            "levins_batch_attach_device": [vp, vp, sz, vp, sz, vp, sz, vp, sz],
             "levins_batch_upload_packed": [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz],
             "levins_batch_run": [vp],
             "levins_batch_download": [vp, vp, vp, vp, vp, vp],
@@ -362,6 +363,13 @@ class Context:
         self._check(lib().levins_batch_upload(self._h, _p(self._b_points), len(self._b_points), _p(self._b_ins),
                                               len(self._b_ins), _p(self._b_q), len(self._b_q), _p(self._b_descs),
                                               len(self._b_descs)))
+
+    def batch_attach_device(self, d_points, n_points, d_ins, n_ins, d_queries, n_queries, descs):
+        """device pointers (ints) of caller-owned pools; nothing is copied"""
+        self._b_descs = np.ascontiguousarray(descs, KF_DESC)
+        self._b_q = np.zeros((int(n_queries), 3), np.float32)  # only its length is used (batch_download)
+        self._check(lib().levins_batch_attach_device(self._h, C.c_void_p(int(d_points)), int(n_points), C.c_void_p(int(d_ins)), int(n_ins),
+                                                     C.c_void_p(int(d_queries)), int(n_queries), _p(self._b_descs), len(self._b_descs)))
 
     def batch_upload_packed(self, packed, scans, ins, queries, descs):
         self._b_points = np.ascontiguousarray(packed, PACKED)
