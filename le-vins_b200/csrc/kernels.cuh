@@ -428,7 +428,13 @@ __device__ __forceinline__ void fill_cull_record(Interval& e, const Extrinsics& 
     e.pad[0] = e.pad[1] = 0.f;
 }
 
-__global__ void __launch_bounds__(256, 2) k_prepare(const __grid_constant__ PrepareArgs a) {
+#ifndef LV_PREP_MINBLK
+#define LV_PREP_MINBLK 2
+#endif
+#ifndef LV_PREP_CHUNKS // chunk descriptors per k_prepare block (decides the number of slices per keyframe)
+#define LV_PREP_CHUNKS 2048
+#endif
+__global__ void __launch_bounds__(256, LV_PREP_MINBLK) k_prepare(const __grid_constant__ PrepareArgs a) {
     KfState* kf = a.kfs + blockIdx.x;
     __shared__ double sR0[9], st0[3];
     __shared__ unsigned long long s_first, s_end, s_begin, s_count;

@@ -265,7 +265,7 @@ int size_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf)
 // k_prepare's grid: one row of blocks per keyframe, enough slices that a block writes at most 2 048 chunk descriptors, and at
 // least a few slices when there are few keyframes (the interval table is split over them as well)
 dim3 prepare_grid(const levins_ctx* ctx, unsigned n_kf, unsigned chunks_per_kf) {
-    unsigned slices = std::max(1u, (chunks_per_kf + 2047u) / 2048u);
+    unsigned slices = std::max(1u, (chunks_per_kf + (unsigned) LV_PREP_CHUNKS - 1u) / (unsigned) LV_PREP_CHUNKS);
     const unsigned room = (unsigned) (2 * ctx->num_sms) / std::max(1u, n_kf); // blocks per keyframe that still run in one wave
     slices = std::max(slices, std::min(4u, room));
     return dim3(n_kf, std::min(slices, 65535u));
