@@ -404,6 +404,7 @@ def run_gpu(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     drain()
+    ctx.batch_download()
     with ClockSampler(local_rank) as clocks:
         ms_total, launches = timed(step_resident, args.steps)
         # keep the sampler alive over the e2e region too so that short runs still collect samples
@@ -569,6 +570,7 @@ def bench_cfg5(torch, dist, abi, args, rank, world, device, stream, peak, steps=
     for _ in range(2):
         step()
     finish()
+    ctx.batch_download()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -643,6 +645,7 @@ def bench_cfg2(torch, abi, synth, device, stream, peak, n_kf=256, steps=10):
     ctx.batch_upload(b.points, b.ins, b.queries.reshape(-1, 3), abi.batch_descs(b))
     for _ in range(3):
         ctx.batch_run()
+        ctx.batch_download()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)

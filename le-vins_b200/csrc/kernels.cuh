@@ -432,7 +432,7 @@ __device__ __forceinline__ void fill_cull_record(Interval& e, const Extrinsics& 
 #define LV_PREP_MINBLK 2
 #endif
 #ifndef LV_PREP_CHUNKS // chunk descriptors per k_prepare block (decides the number of slices per keyframe)
-#define LV_PREP_CHUNKS 2048
+#define LV_PREP_CHUNKS 4096
 #endif
 __global__ void __launch_bounds__(256, LV_PREP_MINBLK) k_prepare(const __grid_constant__ PrepareArgs a) {
     KfState* kf = a.kfs + blockIdx.x;
@@ -676,6 +676,7 @@ struct DeskewArgs {
     unsigned long long* zbuf; // [n_kf][CELLS]
     PointXYZI* cloud_out;     // streaming only (n_kf == 1), nullable
     unsigned gen;             // z-buffer generation of this launch
+    unsigned* cull_stat;      // nullable: {chunks walked, chunks on which the cull fired}, accumulated
     Extrinsics ext;
     Consts c;
 };
@@ -801,7 +802,7 @@ __device__ __forceinline__ bool certainly_outside(const CullRegs& q, float x, fl
     return (zt < -d) | (fmaxf(fabsf(xt), fabsf(yt)) - fabsf(zt) > 2.001f * d);
 }
 
-template <int LIBM_MODE, bool WRITE_CLOUD>
+template <int LIBM_MODE, bool WRITE_CLOUD, bool CULL>
 __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __grid_constant__ DeskewArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -844,7 +845,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __
     // The cull only pays where whole warps fall outside the image cone (a 360-degree scanner: three quarters of the
     // chunks); a sensor that looks where the camera looks never culls anything.  After 8 chunks without a single culled
     // point the warp tries only every 16th chunk.
-    unsigned cull_miss = 0, iter = 0;
+    unsigned cull_miss = 0, iter = 0, stat_hit = 0;
     for (; c < total; c += W, iter++) {
         // stage s_fill was read during the previous iteration: every lane is past those reads here
         __syncwarp();
@@ -863,7 +864,7 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __
         if (cnt) {
             const float4* __restrict__ sp = reinterpret_cast<const float4*>(st);
             const unsigned off = rem * CHUNK_PTS;
-            const bool cull_try = LV_CULL && !WRITE_CLOUD && (cull_miss < 8 || (iter & 15) == 0);
+            const bool cull_try = LV_CULL && CULL && !WRITE_CLOUD && (cull_miss < 8 || (iter & 15) == 0);
             bool culled_any = false;
             // 4 consecutive points per thread (they almost always share one INS interval).  Lane l visits them in the order
             // (j + l) & 3: with the plain order all lanes of a quarter-warp would hit the same 4 banks (128-byte lane stride,
@@ -1043,7 +1044,11 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __
                 }
             }
             } // group
-            if (cull_try) cull_miss = __any_sync(0xffffffffu, culled_any) ? 0u : cull_miss + 1u;
+            if (cull_try) {
+                const bool hit = __any_sync(0xffffffffu, culled_any);
+                cull_miss = hit ? 0u : cull_miss + 1u;
+                stat_hit += hit ? 1u : 0u;
+            }
         }
         s_fill = s;
         if (++s == DESKEW_STAGES) {
@@ -1058,6 +1063,12 @@ __global__ void __launch_bounds__(DESKEW_BLOCK, LV_MINBLK) k_deskew_bin(const __
         }
     }
     if (qn) flush_undecided<LIBM_MODE>(q_pt, q_kf, qn, a.zbuf, a.gen, a.c);
+    // how often the cull fired (chunks): the host picks the instantiation without the cull for sensors that never leave the
+    // image cone, and probes again now and then
+    if (CULL && a.cull_stat && lane == 0 && iter) {
+        atomicAdd(a.cull_stat, iter); // chunks this warp walked (the cull was tried on all of them unless it had backed off)
+        atomicAdd(a.cull_stat + 1, stat_hit);
+    }
 }
 
 

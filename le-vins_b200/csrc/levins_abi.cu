@@ -56,6 +56,10 @@ struct levins_ctx {
     uint64_t launches = 0;
     int num_sms = 148;
     bool deskew_attr_set = false;
+    DevBuf cull_stat;              // {tried, fired} chunk counts of the launches since the last read-back
+    bool cull_off = false;         // the cull never fired lately: run the instantiation without it
+    unsigned cull_off_launches = 0;
+    unsigned kf_calls = 0;
     cudaStream_t side = nullptr; // k_count_cells runs here, overlapped with the latency-bound k_associate
     cudaEvent_t ev_binned = nullptr, ev_counted = nullptr;
     cudaEvent_t ev_append = nullptr; // recorded after the host->device copies of the latest levins_append_scan / levins_append_raw
@@ -262,7 +266,7 @@ int size_chunks(levins_ctx* ctx, DeskewArgs& a, uint64_t max_pts, unsigned n_kf)
     a.chunks = ctx->chunks.as<ChunkDesc>();
     return LEVINS_OK;
 }
-// k_prepare's grid: one row of blocks per keyframe, enough slices that a block writes at most 2 048 chunk descriptors, and at
+// k_prepare's grid: one row of blocks per keyframe, enough slices that a block writes at most LV_PREP_CHUNKS descriptors, and at
 // least a few slices when there are few keyframes (the interval table is split over them as well)
 dim3 prepare_grid(const levins_ctx* ctx, unsigned n_kf, unsigned chunks_per_kf) {
     unsigned slices = std::max(1u, (chunks_per_kf + (unsigned) LV_PREP_CHUNKS - 1u) / (unsigned) LV_PREP_CHUNKS);
@@ -277,16 +281,47 @@ int launch_deskew(levins_ctx* ctx, DeskewArgs& a, bool write_cloud) {
     const unsigned total = a.n_kf * a.chunks_per_kf;
     if (total == 0) return LEVINS_OK;
     using Kernel = void (*)(DeskewArgs);
-    static const Kernel kernels[2][2] = {{k_deskew_bin<0, false>, k_deskew_bin<0, true>}, {k_deskew_bin<1, false>, k_deskew_bin<1, true>}};
+    static const Kernel kernels[2][2][2] = {{{k_deskew_bin<0, false, false>, k_deskew_bin<0, false, true>}, {k_deskew_bin<0, true, false>, k_deskew_bin<0, true, false>}},
+                                            {{k_deskew_bin<1, false, false>, k_deskew_bin<1, false, true>}, {k_deskew_bin<1, true, false>, k_deskew_bin<1, true, false>}}};
     if (!ctx->deskew_attr_set) {
-        for (int i = 0; i < 4; i++)
-            CU(cudaFuncSetAttribute(kernels[i >> 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
+        for (int i = 0; i < 8; i++)
+            CU(cudaFuncSetAttribute(kernels[i >> 2][(i >> 1) & 1][i & 1], cudaFuncAttributeMaxDynamicSharedMemorySize, DESKEW_SMEM));
+        CU(ctx->cull_stat.ensure(16));
+        CU(cudaMemsetAsync(ctx->cull_stat.p, 0, 16, ctx->stream));
         ctx->deskew_attr_set = true;
     }
+    // The certified frustum cull pays for 360-degree scanners and costs ~5 % where every point lies inside the image cone.
+    // The kernel reports how often it fired; when it (almost) never does, the instantiation without it runs, with a probe
+    // every 64th launch.  Both give identical results.
+    bool cull = !write_cloud;
+    if (cull && ctx->cull_off) {
+        if (++ctx->cull_off_launches >= 64) {
+            ctx->cull_off = false; // probe again
+            ctx->cull_off_launches = 0;
+        } else {
+            cull = false;
+        }
+    }
+    a.cull_stat = cull ? ctx->cull_stat.as<unsigned>() : nullptr;
     const unsigned grid = std::min<unsigned>((total + DESKEW_WARPS - 1) / DESKEW_WARPS, (unsigned) LV_MINBLK * (unsigned) ctx->num_sms);
-    kernels[ctx->consts.libm_mode ? 1 : 0][write_cloud ? 1 : 0]<<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
+    kernels[ctx->consts.libm_mode ? 1 : 0][write_cloud ? 1 : 0][cull ? 1 : 0]<<<grid, DESKEW_BLOCK, DESKEW_SMEM, ctx->stream>>>(a);
     ctx->launches++;
     CU(cudaGetLastError());
+    return LEVINS_OK;
+}
+
+// Call right after a synchronisation that follows deskew launches: fetch and reset the cull statistics (8 bytes) and decide
+// which instantiation the next launches use.
+int update_cull_policy(levins_ctx* ctx) {
+    if (!ctx->cull_stat.p || ctx->cull_off) return LEVINS_OK;
+    unsigned st[2] = {0, 0};
+    CU(cudaMemcpyAsync(st, ctx->cull_stat.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemsetAsync(ctx->cull_stat.p, 0, 8, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (st[0] >= 64 && (double) st[1] < 0.02 * (double) st[0]) {
+        ctx->cull_off = true;
+        ctx->cull_off_launches = 0;
+    }
     return LEVINS_OK;
 }
 
@@ -566,7 +601,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
-                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw, &ctx->scratch, &ctx->s_arena_in, &ctx->s_arena_out})
+                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw, &ctx->scratch, &ctx->s_arena_in, &ctx->s_arena_out, &ctx->cull_stat})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -1132,6 +1167,10 @@ static int keyframe_body(levins_ctx* ctx, double stamp, const levins_ins_sample*
     if (m_out) *m_out = kf.m;
     // the fused path keeps no cell array: a later levins_associate() needs levins_build_range_image() first
     ctx->s_image_valid = false;
+    if ((++ctx->kf_calls & 31u) == 0) { // now and then: does the frustum cull ever fire for this sensor?
+        r = update_cull_policy(ctx);
+        if (r) return r;
+    }
     return (kf.status || kf.m == 0) ? LEVINS_EMPTY : LEVINS_OK;
 }
 
@@ -1646,7 +1685,7 @@ extern "C" int levins_batch_download(levins_ctx* ctx, int8_t* type, float* xyz_d
         if (n_projected) n_projected[k] = kfs[k].n_proj;
         if (m) m[k] = kfs[k].m;
     }
-    return LEVINS_OK;
+    return update_cull_policy(ctx);
 }
 
 #include "exchange_host.inc"

@@ -317,3 +317,26 @@ def test_frustum_cull_is_exact_on_the_fov_border(oracle, built_lib, seed):
     assert 200 < ref2["m"] < len(s["pts"])  # both sides of the border are populated
     assert got["m"] == ref2["m"], (got["m"], ref2["m"])
     c.close()
+
+
+def test_results_do_not_depend_on_the_cull_policy(oracle, built_lib):
+    """The library switches between the deskew instantiations with and without the frustum cull from what the cull
+    statistics say (all points inside the image cone: off after the first read-back, a probe every 64th launch).  Seventy
+    runs of one batch walk through on -> off -> probe -> off; every run must give the same bytes."""
+    shp = synth.Shape(**{**synth.shape(2).__dict__, "pts_per_scan": 4000, "n_features": 40})
+    b = synth.make_batch(2, 5, n_unique_scans=9, shp=shp)
+    c = abi.Context(0)
+    c.set_extrinsics(b.shape.rig.pose_b_c, b.shape.rig.pose_c_l, b.shape.rig.td_b_l)
+    c.batch_upload(b.points, b.ins, b.queries.reshape(-1, 3), abi.batch_descs(b))
+    first = None
+    for run in range(70):
+        c.batch_run()
+        out = c.batch_download()
+        if first is None:
+            first = out
+            kf = synth.batch_keyframe(b, 2)
+            ref = oracle.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries, 0.5)
+            assert out["m"][2] == ref["m"] and np.array_equal(out["type"][80:120], ref["type"])
+        else:
+            assert all(out[k].tobytes() == first[k].tobytes() for k in out), run
+    c.close()
