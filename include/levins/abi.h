@@ -315,7 +315,8 @@ int levins_batch_download(levins_ctx *ctx, int8_t *type, float *xyz_depth, int32
 /* Device addresses of the result arrays of the resident batch (type: int8[n_queries], xyz_depth: float[4*n_queries],
  * flags: int32[n_queries]), valid until the next levins_batch_upload.  For exchange steps that stay on the device
  * (e.g. an NCCL all-gather of the depths issued on the same stream).  xyz_depth and type are one contiguous block:
- * type == (int8_t *) xyz_depth + 16 * n_queries, so 17 * n_queries bytes from xyz_depth carry both. */
+ * type == (int8_t *) xyz_depth + 16 * nq16 with nq16 = n_queries rounded up to a multiple of 16, so 17 * nq16 bytes from
+ * xyz_depth carry both (and blocks of several ranks can be laid back to back with every float4 aligned). */
 int levins_batch_result_pointers(levins_ctx *ctx, void **type, void **xyz_depth, void **flags);
 /* Waves: how many keyframes share one set of launches (their z-buffers stay L2-resident). 0 = default. */
 int levins_batch_set_wave(levins_ctx *ctx, int keyframes_per_wave);
@@ -330,8 +331,9 @@ uint64_t levins_launch_count(const levins_ctx *ctx);
 /* ------------------------------------------------------------------------------------------------
  * exchange step of a sharded batch.  Keyframes are independent, so ranks (one process per GPU, one context
  * each) share nothing until the end, when every rank wants the per-feature results of all ranks.  A rank's results are
- * one contiguous block of 17 bytes per query (xyz_depth, then type; levins_batch_result_pointers); the gathered block holds
- * one such slot per rank, in rank order.  Every rank must hold the same number of queries (pad the last shard).
+ * one contiguous block of 17 bytes per query (xyz_depth, then type; levins_batch_result_pointers; the query count is rounded
+ * up to a multiple of 16); the gathered block holds one such slot per rank, in rank order.  Every rank must hold the same
+ * number of queries (pad the last shard).
  * The reference is a single process and has no counterpart.  Two interchangeable ways:
  *
  * (1) NCCL: levins_gather enqueues one ncclAllGather on the context's stream.  `comm` is an ncclComm_t -- the caller's own,

@@ -1382,8 +1382,10 @@ static int batch_prepare(levins_ctx* ctx, size_t n_points, const levins_ins_samp
     }
     CU(ctx->b_table.ensure(table_entries * sizeof(Interval)));
     CU(ctx->b_kfs.ensure(n_kf * sizeof(KfState)));
-    CU(ctx->b_results.ensure(std::max<size_t>(n_queries, 1) * 17));
-    ctx->b_results_nq = std::max<size_t>(n_queries, 1);
+    // one slot = xyz_depth[16 * nq16] then type[nq16], nq16 = the query count rounded up to 16: the slot size (17 * nq16) is
+    // then a multiple of 16, so slots of several ranks can sit back to back (gathered block) with every float4 aligned
+    ctx->b_results_nq = (std::max<size_t>(n_queries, 1) + 15) & ~size_t(15);
+    CU(ctx->b_results.ensure(ctx->b_results_nq * 17));
     CU(ctx->b_flags.ensure(std::max<size_t>(n_queries, 1) * 4));
     CU(ctx->b_nn.ensure(std::max<size_t>(n_queries, 1) * 80));
     CU(ctx->b_nn_meta.ensure(std::max<size_t>(n_queries, 1) * 8));

@@ -22,7 +22,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     per_rank = 3
-    shp = synth.Shape(**{**synth.shape(2).__dict__, "pts_per_scan": 6000, "n_features": 96})
+    shp = synth.Shape(**{**synth.shape(2).__dict__, "pts_per_scan": 6000, "n_features": 97})  # 3 x 97 queries per rank: not a multiple of 16
     whole = synth.make_batch(2, per_rank * world, n_unique_scans=9, shp=shp)  # same seed on every rank
     F = whole.queries.shape[1]
     mine = shard.split_batch(whole, world, rank)
@@ -37,6 +37,10 @@ def main():
     ref_ctx.close()
     want_t = ref["type"].reshape(world, nq)
     want_x = ref["xyz_depth"].reshape(world, nq, 4)
+
+    def slots(g):  # the gathered slots are padded to a multiple of 16 queries
+        return g["type"][:, :nq], g["xyz_depth"][:, :nq]
+
     assert (want_t == 1).sum() > 20
 
     ctx = abi.Context(local)
@@ -49,9 +53,9 @@ def main():
     comm = ctx.comm_init(uid.cpu().numpy(), world, rank)
     ctx.batch_run()
     ctx.gather(comm, world)
-    got = ctx.gathered_download(world)
-    assert got["type"].tobytes() == want_t.tobytes(), f"rank {rank}: NCCL-gathered types differ from the single-GPU run"
-    assert got["xyz_depth"].tobytes() == want_x.tobytes(), f"rank {rank}: NCCL-gathered depths differ"
+    gt, gx = slots(ctx.gathered_download(world))
+    assert gt.tobytes() == want_t.tobytes(), f"rank {rank}: NCCL-gathered types differ from the single-GPU run"
+    assert gx.tobytes() == want_x.tobytes(), f"rank {rank}: NCCL-gathered depths differ"
     abi.Context.comm_destroy(comm)
 
     # (2) peer mode: fused into k_plane, three steps so that both halves of the double buffer are used
@@ -63,9 +67,9 @@ def main():
     for step in range(3):
         ctx.batch_run()
         ctx.peer_wait()
-        got = ctx.gathered_download(world)
-        assert got["type"].tobytes() == want_t.tobytes(), f"rank {rank} step {step}: peer-gathered types differ"
-        assert got["xyz_depth"].tobytes() == want_x.tobytes(), f"rank {rank} step {step}: peer-gathered depths differ"
+        gt, gx = slots(ctx.gathered_download(world))
+        assert gt.tobytes() == want_t.tobytes(), f"rank {rank} step {step}: peer-gathered types differ"
+        assert gx.tobytes() == want_x.tobytes(), f"rank {rank} step {step}: peer-gathered depths differ"
     dist.barrier()
     ctx.peer_detach()
     dist.barrier()
