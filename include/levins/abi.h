@@ -305,14 +305,6 @@ typedef struct levins_scan_desc {
 int levins_batch_upload_packed(levins_ctx *ctx, const levins_packed_point *points, size_t n_points,
                                const levins_scan_desc *scans, size_t n_scans, const levins_ins_sample *ins, size_t n_ins,
                                const float *query_xyz, size_t n_queries, const levins_keyframe_desc *descs, size_t n_keyframes);
-/* The same for spinning scanners, whose firing columns share one timestamp (Ouster OS1-128: 128 rings per column; the
- * driver's own scan format carries one timestamp per column): `xyz` is a plain array of 3 floats per point and
- * `column_dt_ns` holds one u32 of nanoseconds after the scan's stamp per column of `points_per_column` consecutive points
- * (every scan is a whole number of columns).  12 bytes per point plus 4 per column instead of 32 per point. */
-int levins_batch_upload_columns(levins_ctx *ctx, const float *xyz, size_t n_points, const uint32_t *column_dt_ns,
-                                size_t points_per_column, const levins_scan_desc *scans, size_t n_scans,
-                                const levins_ins_sample *ins, size_t n_ins, const float *query_xyz, size_t n_queries,
-                                const levins_keyframe_desc *descs, size_t n_keyframes);
 /* Enqueue the whole batch on the context's stream: per keyframe window search + INS table (one launch for the
  * batch), then per wave of keyframes deskew+bin, cell finalisation and association.  Asynchronous. */
 int levins_batch_run(levins_ctx *ctx);

@@ -287,39 +287,6 @@ __global__ void __launch_bounds__(256) k_unpack(const PackedPoint* __restrict__ 
     o[1] = make_float4(0.f, 0.f, __int_as_float(__double2loint(t)), __int_as_float(__double2hiint(t)));
 }
 
-// The same for spinning scanners, whose firing columns share one timestamp (Ouster: 128 rings per column): coordinates as
-// a plain x, y, z array (12 bytes per point) and one u32 of nanoseconds per column of `group` consecutive points.  Four
-// points per thread: 48 bytes in as three 16-byte loads, 128 bytes out.
-__global__ void __launch_bounds__(256) k_unpack_columns(const float* __restrict__ xyz, unsigned long long n, const unsigned* __restrict__ dt_ns,
-                                                        unsigned group, const ScanDesc* __restrict__ scans, unsigned n_scans,
-                                                        PointXYZIT* __restrict__ out) {
-    const unsigned long long k0 = ((unsigned long long) blockIdx.x * 256 + threadIdx.x) * 4;
-    if (k0 >= n) return;
-    float v[12];
-    if (k0 + 4 <= n) {
-        const float4* p = reinterpret_cast<const float4*>(xyz + 3 * k0);
-        const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
-    } else {
-        for (int i = 0; i < 12; i++) v[i] = 3 * k0 + i < 3 * n ? __ldg(xyz + 3 * k0 + i) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const unsigned long long k = k0 + j;
-        if (k >= n) break;
-        unsigned lo = 0, hi = n_scans;
-        while (hi - lo > 1) {
-            const unsigned mid = (lo + hi) >> 1;
-            if (__ldg(&scans[mid].first) <= k) lo = mid; else hi = mid;
-        }
-        const double t = __ldg(&scans[lo].stamp) + (double) __ldg(dt_ns + k / group) * 1.0e-9;
-        float4* o = reinterpret_cast<float4*>(out + k);
-        o[0] = make_float4(v[3 * j], v[3 * j + 1], v[3 * j + 2], 0.f);
-        o[1] = make_float4(0.f, 0.f, __int_as_float(__double2loint(t)), __int_as_float(__double2hiint(t)));
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // chunks: k_deskew_bin's unit of work is 128 consecutive points of one keyframe (one warp, one iteration)
 // ------------------------------------------------------------------------------------------------
@@ -1507,198 +1474,6 @@ __global__ void __launch_bounds__(ASSOC_WARPS * 32, LV_ASSOC_MINBLK) k_associate
     }
     // M (number of non-empty cells), piggy-backed on this launch: every block counts its slice of the z-buffer
     if (FUSED && a.count_cells) count_live_cells(a.zbuf + (size_t) blockIdx.y * CELLS, a.gen, kf);
-}
-
-// ------------------------------------------------------------------------------------------------
-// The same association split in three for large batches (tens of thousands of features per wave), where k_associate's chain
-// of dependent loads per warp (window keys -> winner points -> interval entries -> arithmetic) is latency-bound at the
-// occupancy its registers allow:
-//   k_assoc_gather   one warp per feature: window scan + mask, the live candidates go to a compact global list
-//   k_assoc_eval     one THREAD per candidate (dense, full occupancy): re-deskew the cell's winner, unit vector + range, d2
-//   k_assoc_select   one warp per feature: top-5 by (d2, cell id) over its candidates
-// Same functions, same operation order => the same bits as k_associate<true>.
-// ------------------------------------------------------------------------------------------------
-constexpr int ASSOC_MAX_CAND = 80; // cells the mask can keep: <= 8 rows x 10 columns (see the mask in k_associate)
-
-struct AssocSplitArgs {
-    KfState* kfs;
-    const float* queries;
-    const unsigned long long* zbuf; // [gridDim.y][CELLS]
-    const PointXYZIT* pts;
-    unsigned long long pts_cap;
-    const Interval* table;
-    unsigned gen;
-    Extrinsics ext;
-    uint4* cand;        // {query, keyframe of the wave, cell, point index}
-    float4* cand_p;     // unit vector + range of the candidate
-    uint2* cand_dc;     // {bits of d2, cell}
-    uint2* span;        // per query of the pool: {first candidate, count}
-    unsigned* total;    // candidates of the wave (reset by the host before k_assoc_gather)
-    float4* nn;
-    uint2* nn_meta;
-    Consts c;
-};
-
-__global__ void __launch_bounds__(128) k_assoc_gather(const __grid_constant__ AssocSplitArgs a) {
-    KfState* __restrict__ kf = a.kfs + blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const unsigned f = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (f >= kf->q_count) return;
-    const size_t qi = kf->q_begin + f;
-    const float qx = __ldg(a.queries + 3 * qi), qy = __ldg(a.queries + 3 * qi + 1), qz = __ldg(a.queries + 3 * qi + 2);
-    // (the query's cell coordinates, the window and the mask exactly as in k_associate)
-    float rq, cq, ael;
-    const float inv_ang = a.c.inv_angle_f, off = (float) a.c.half_offset;
-    if (qz > 0.f && fabsf(qx) <= qz && fabsf(qy) <= qz) {
-        const float el = atan_poly(qy * rsqrtf(fmaf(qx, qx, qz * qz)));
-        rq = fmaf(el, inv_ang, 150.0f);
-        cq = fmaf(-atan_poly(__fdividef(qx, qz)), inv_ang, 150.0f);
-        ael = fabsf(el);
-    } else {
-        const float el = atan2f(qy, sqrtf(qx * qx + qz * qz));
-        const float az = atan2f(qz, qx);
-        rq = (el + off) * inv_ang;
-        cq = (az - off) * inv_ang;
-        ael = fabsf(el);
-    }
-    const int rowq = (int) rintf(rq), colq = (int) rintf(cq);
-    const float cmin = fmaxf(0.f, __cosf(ael) * __cosf(fminf(ael + 0.016f, 1.5707963f))) * 0.999f;
-    const unsigned long long* __restrict__ zb = a.zbuf + (size_t) blockIdx.y * CELLS;
-    bool inmask[4];
-    unsigned long long wkey[4];
-    int wcell[4];
-#pragma unroll
-    for (int itc = 0; itc < 4; itc++) {
-        const int j = lane + 32 * itc;
-        const int r = rowq - WIN_ROWS + j / WIN_W;
-        const int cc = colq - WIN_COLS + j % WIN_W;
-        inmask[itc] = false;
-        wkey[itc] = 0;
-        wcell[itc] = r * IMG + cc;
-        if (j < WIN_CELLS && r >= 0 && r < IMG && cc >= 0 && cc < IMG) {
-            const float dr = fmaxf(0.f, fabsf((float) r - rq) - 0.51f);
-            const float dc = fmaxf(0.f, fabsf((float) cc - cq) - 0.51f);
-            inmask[itc] = dr * dr + cmin * dc * dc <= 9.0601f;
-            if (inmask[itc]) wkey[itc] = __ldg(zb + wcell[itc]);
-        }
-    }
-    unsigned bal[4];
-    int count = 0;
-#pragma unroll
-    for (int itc = 0; itc < 4; itc++) {
-        bal[itc] = __ballot_sync(0xffffffffu, inmask[itc] && key_live(wkey[itc], a.gen));
-        count += __popc(bal[itc]);
-    }
-    unsigned first = 0;
-    if (lane == 0) {
-        first = count ? atomicAdd(a.total, (unsigned) count) : 0u;
-        a.span[qi] = make_uint2(first, (unsigned) count);
-    }
-    first = __shfl_sync(0xffffffffu, first, 0);
-    int pos = 0;
-#pragma unroll
-    for (int itc = 0; itc < 4; itc++) { // candidates in ascending window order, like k_associate's compaction
-        if ((bal[itc] >> lane) & 1u)
-            a.cand[first + pos + __popc(bal[itc] & ((1u << lane) - 1u))] = make_uint4((unsigned) qi, blockIdx.y, (unsigned) wcell[itc], key_index(wkey[itc]));
-        pos += __popc(bal[itc]);
-    }
-}
-
-__global__ void __launch_bounds__(256) k_assoc_eval(const __grid_constant__ AssocSplitArgs a) {
-    const unsigned total = *a.total;
-    for (unsigned i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
-        const uint4 rec = __ldg(a.cand + i);
-        const KfState* __restrict__ kf = a.kfs + rec.y;
-        const KfView kv = kf_view(kf, a.table);
-        const float4* __restrict__ p4 = reinterpret_cast<const float4*>(a.pts + wrap(kf->proj_begin + rec.w, a.pts_cap));
-        const float4 xyz = __ldg(p4);
-        const double tm = __ldg(reinterpret_cast<const double2*>(p4 + 1)).y;
-        EntryRegs e;
-        int cur = -1;
-        float x, y, z;
-        deskew_point(xyz.x, xyz.y, xyz.z, tm, kv, a.ext, a.c, e, cur, x, y, z); // same function, same bits as in k_deskew_bin
-        const float4 c = unit_and_range(x, y, z);                                 // tracking.cc:346-351
-        const float qx = __ldg(a.queries + 3 * (size_t) rec.x), qy = __ldg(a.queries + 3 * (size_t) rec.x + 1),
-                    qz = __ldg(a.queries + 3 * (size_t) rec.x + 2);
-        const float dx = qx - c.x, dy = qy - c.y, dz = qz - c.z; // FLANN L2_Simple<float>
-        float d = dx * dx;
-        d = d + dy * dy;
-        d = d + dz * dz;
-        a.cand_p[i] = c;
-        a.cand_dc[i] = make_uint2(__float_as_uint(d), rec.z);
-    }
-}
-
-__global__ void __launch_bounds__(128) k_assoc_select(const __grid_constant__ AssocSplitArgs a) {
-    KfState* __restrict__ kf = a.kfs + blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const unsigned f = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (f >= kf->q_count) return;
-    const size_t qi = kf->q_begin + f;
-    const uint2 sp = __ldg(a.span + qi);
-    constexpr int NS = (ASSOC_MAX_CAND + 31) / 32; // 3
-    float4 cand[NS];
-    int cid[NS];
-    unsigned dbits[NS];
-#pragma unroll
-    for (int itc = 0; itc < NS; itc++) {
-        cand[itc] = make_float4(0.f, 0.f, 0.f, -1.0f);
-        cid[itc] = 0x7fffffff;
-        dbits[itc] = 0x7f800000u; // +inf
-        const unsigned ci = lane + 32 * itc;
-        if (ci < sp.y) {
-            const uint2 dc = __ldg(a.cand_dc + sp.x + ci);
-            cand[itc] = __ldg(a.cand_p + sp.x + ci);
-            dbits[itc] = dc.x;
-            cid[itc] = (int) dc.y;
-        }
-    }
-    unsigned nn_d[5];
-    float4 nn_p[5];
-    int found = 0;
-#pragma unroll
-    for (int r = 0; r < 5; r++) { // top-5 by (d2, cell id), as in k_associate
-        unsigned bd = dbits[0];
-        int bc = cid[0];
-        float4 bp = cand[0];
-#pragma unroll
-        for (int itc = 1; itc < NS; itc++)
-            if (dbits[itc] < bd || (dbits[itc] == bd && cid[itc] < bc)) {
-                bd = dbits[itc];
-                bc = cid[itc];
-                bp = cand[itc];
-            }
-        const unsigned m1 = __reduce_min_sync(0xffffffffu, bd);
-        const unsigned m2 = __reduce_min_sync(0xffffffffu, bd == m1 ? (unsigned) bc : 0xffffffffu);
-        const bool mine = (bd == m1) && ((unsigned) bc == m2);
-        const int owner = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
-        nn_d[r] = m1;
-        nn_p[r].x = __shfl_sync(0xffffffffu, bp.x, owner);
-        nn_p[r].y = __shfl_sync(0xffffffffu, bp.y, owner);
-        nn_p[r].z = __shfl_sync(0xffffffffu, bp.z, owner);
-        nn_p[r].w = __shfl_sync(0xffffffffu, bp.w, owner);
-        if (m1 != 0x7f800000u) found++;
-        if (mine) {
-#pragma unroll
-            for (int itc = 0; itc < NS; itc++)
-                if (dbits[itc] == m1 && cid[itc] == (int) m2) {
-                    dbits[itc] = 0x7f800000u;
-                    cid[itc] = 0x7fffffff;
-                }
-        }
-    }
-    if (lane < 5) {
-        float4 pp = nn_p[0];
-        unsigned d = nn_d[0];
-#pragma unroll
-        for (int k = 1; k < 5; k++)
-            if (lane == k) {
-                pp = nn_p[k];
-                d = nn_d[k];
-            }
-        a.nn[5 * qi + lane] = pp;
-        if (lane == 4) a.nn_meta[qi] = make_uint2((unsigned) found, d);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------

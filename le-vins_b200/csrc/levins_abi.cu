@@ -5,8 +5,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
-#include <cstdlib>
 #include <cfloat>
 #include <cstring>
 #include <deque>
@@ -117,9 +117,7 @@ struct levins_ctx {
     const PointXYZIT* batch_pts() const { return static_cast<const PointXYZIT*>(b_pts_view ? b_pts_view : b_pts.p); }
     const InsSample* batch_ins() const { return static_cast<const InsSample*>(b_ins_view ? b_ins_view : b_ins.p); }
     const float* batch_queries() const { return static_cast<const float*>(b_queries_view ? b_queries_view : b_queries.p); }
-    DevBuf b_packed, b_scans, b_coldt; // levins_batch_upload_packed / _columns: the records as uploaded, scan stamps, column times
-    DevBuf b_cand, b_cand_p, b_cand_dc, b_cand_span, b_cand_total; // split association: candidate lists of one wave
-    int assoc_split = -1;     // -1 automatic (by the number of features per wave), 0 / 1 forced (LEVINS_ASSOC_SPLIT)
+    DevBuf b_packed, b_scans; // levins_batch_upload_packed: the records as uploaded, the scan stamps
     size_t b_nq = 0, b_npts = 0, b_nins = 0;
     int b_wave = 256;
     int b_wave_alloc = 0;
@@ -584,7 +582,6 @@ extern "C" int levins_create(int device, const levins_config* cfg, levins_ctx** 
         return LEVINS_ERR_ARG;
     }
     ctx->consts = make_consts(ctx->cfg);
-    if (const char* e = getenv("LEVINS_ASSOC_SPLIT")) ctx->assoc_split = atoi(e) ? 1 : 0;
     ctx->num_sms = prop.multiProcessorCount;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost(&ctx->pinned, std::max<size_t>(ctx->pin_total(), 1 << 20)) != cudaSuccess) {
@@ -605,7 +602,7 @@ extern "C" void levins_destroy(levins_ctx* ctx) {
                       &ctx->s_xyzd, &ctx->s_flags, &ctx->s_knn_idx, &ctx->s_knn_d2, &ctx->s_nn, &ctx->s_nn_meta, &ctx->b_nn, &ctx->b_nn_meta, &ctx->s_cloud, &ctx->s_in_cloud,
                       &ctx->s_zbuf, &ctx->s_cells, &ctx->s_c2c, &ctx->s_unit, &ctx->s_winner, &ctx->b_pts, &ctx->b_ins,
                       &ctx->b_table, &ctx->b_queries, &ctx->b_kfs, &ctx->b_results, &ctx->b_flags, &ctx->b_zbuf,
-                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw, &ctx->scratch, &ctx->s_arena_in, &ctx->s_arena_out, &ctx->cull_stat, &ctx->b_coldt, &ctx->b_cand, &ctx->b_cand_p, &ctx->b_cand_dc, &ctx->b_cand_span, &ctx->b_cand_total})
+                      &ctx->b_cells, &ctx->g_block, &ctx->b_packed, &ctx->b_scans, &ctx->s_pixels, &ctx->s_undist, &ctx->s_accepted, &ctx->s_pw, &ctx->scratch, &ctx->s_arena_in, &ctx->s_arena_out, &ctx->cull_stat})
         b->release();
     for (cudaEvent_t ev : ctx->ev_pool) cudaEventDestroy(ev);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -1420,42 +1417,6 @@ extern "C" int levins_batch_upload(levins_ctx* ctx, const levins_point_xyzit* po
     return LEVINS_OK;
 }
 
-extern "C" int levins_batch_upload_columns(levins_ctx* ctx, const float* xyz, size_t n_points, const uint32_t* column_dt_ns,
-                                           size_t points_per_column, const levins_scan_desc* scans, size_t n_scans,
-                                           const levins_ins_sample* ins, size_t n_ins, const float* query_xyz, size_t n_queries,
-                                           const levins_keyframe_desc* descs, size_t n_kf) {
-    if (!ctx || !xyz || !column_dt_ns || !points_per_column || !scans || !n_scans || !ins || !descs || (!query_xyz && n_queries))
-        return fail(ctx, LEVINS_ERR_ARG, "null argument");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
-    if (n_scans > 0xffffffffull || points_per_column > 0xffffffffull) return fail(ctx, LEVINS_ERR_ARG, "too many scans");
-    unsigned long long next = 0;
-    for (size_t i = 0; i < n_scans; i++) { // the scans tile the pool in order, each a whole number of columns
-        if (scans[i].first != next || scans[i].count % points_per_column) return fail(ctx, LEVINS_ERR_ARG, "scan descriptors must tile the pool in whole columns");
-        next += scans[i].count;
-    }
-    if (next != n_points) return fail(ctx, LEVINS_ERR_ARG, "scan descriptors do not cover the point pool");
-    int r = batch_prepare(ctx, n_points, ins, n_ins, query_xyz, n_queries, descs, n_kf);
-    if (r) return r;
-    const size_t n_col = n_points / points_per_column;
-    CU(ctx->b_packed.ensure(std::max<size_t>(n_points, 1) * 12 + 64));
-    CU(ctx->b_coldt.ensure(std::max<size_t>(n_col, 1) * 4));
-    CU(ctx->b_scans.ensure(n_scans * sizeof(ScanDesc)));
-    CU(cudaMemcpyAsync(ctx->b_scans.p, scans, n_scans * sizeof(ScanDesc), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->b_coldt.p, column_dt_ns, n_col * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->b_packed.p, xyz, n_points * 12, cudaMemcpyHostToDevice, ctx->stream));
-    if (n_points) {
-        k_unpack_columns<<<(unsigned) ((n_points + 1023) / 1024), 256, 0, ctx->stream>>>(ctx->b_packed.as<float>(), n_points, ctx->b_coldt.as<unsigned>(),
-                                                                                    (unsigned) points_per_column, ctx->b_scans.as<ScanDesc>(),
-                                                                                    (unsigned) n_scans, ctx->b_pts.as<PointXYZIT>());
-        ctx->launches++;
-        CU(cudaGetLastError());
-    }
-    ctx->b_valid = true;
-    return LEVINS_OK;
-}
-
 extern "C" int levins_batch_attach_device(levins_ctx* ctx, const levins_point_xyzit* d_points, size_t n_points,
                                           const levins_ins_sample* d_ins, size_t n_ins, const float* d_query_xyz, size_t n_queries,
                                           const levins_keyframe_desc* descs, size_t n_kf) {
@@ -1468,6 +1429,9 @@ extern "C" int levins_batch_attach_device(levins_ctx* ctx, const levins_point_xy
         cudaGetLastError();
         return fail(ctx, LEVINS_ERR_ARG, "d_points is not device memory of this context's GPU");
     }
+    // the kernels read the pools with 16-byte vector loads and bulk copies: refuse misaligned pools instead of faulting
+    if (reinterpret_cast<uintptr_t>(d_points) % 32 || reinterpret_cast<uintptr_t>(d_ins) % 8 || reinterpret_cast<uintptr_t>(d_query_xyz) % 4)
+        return fail(ctx, LEVINS_ERR_ARG, "device pools must be aligned: points 32 bytes, INS samples 8, queries 4");
     // the library's own pools are released: the batch now lives in the caller's memory
     ctx->b_pts.release();
     ctx->b_ins.release();
@@ -1635,48 +1599,10 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
             aa.knn_idx = nullptr;
             aa.knn_d2 = nullptr;
             aa.c = ctx->consts;
-            // Many features per wave: the association runs as gather -> one thread per candidate -> select (identical
-            // results; the single kernel is latency-bound at the occupancy its registers allow).  LEVINS_ASSOC_SPLIT=0/1
-            // forces the choice (tests run both).
-            uint64_t wave_q = 0;
-            for (int i = 0; i < nw; i++) wave_q += ctx->b_descs[k0 + i].q_count;
-            const bool split = ctx->assoc_split < 0 ? wave_q >= 16384 : ctx->assoc_split != 0;
             mark(3, true);
-            if (!split) {
-                k_associate<true><<<dim3((unsigned) ((max_q + ASSOC_WARPS - 1) / ASSOC_WARPS), nw), ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
-                ctx->launches++;
-            } else {
-                const size_t cap = (size_t) wave_q * ASSOC_MAX_CAND;
-                CU(ctx->b_cand.ensure(cap * sizeof(uint4)));
-                CU(ctx->b_cand_p.ensure(cap * sizeof(float4)));
-                CU(ctx->b_cand_dc.ensure(cap * sizeof(uint2)));
-                CU(ctx->b_cand_span.ensure(std::max<size_t>(ctx->b_nq, 1) * sizeof(uint2)));
-                CU(ctx->b_cand_total.ensure(16));
-                CU(cudaMemsetAsync(ctx->b_cand_total.p, 0, 4, ctx->stream));
-                AssocSplitArgs sa{};
-                sa.kfs = aa.kfs;
-                sa.queries = aa.queries;
-                sa.zbuf = aa.zbuf;
-                sa.pts = aa.pts;
-                sa.pts_cap = aa.pts_cap;
-                sa.table = aa.table;
-                sa.gen = aa.gen;
-                sa.ext = aa.ext;
-                sa.cand = ctx->b_cand.as<uint4>();
-                sa.cand_p = ctx->b_cand_p.as<float4>();
-                sa.cand_dc = ctx->b_cand_dc.as<uint2>();
-                sa.span = ctx->b_cand_span.as<uint2>();
-                sa.total = ctx->b_cand_total.as<unsigned>();
-                sa.nn = aa.nn;
-                sa.nn_meta = aa.nn_meta;
-                sa.c = aa.c;
-                const dim3 fgrid((unsigned) ((max_q + 3) / 4), nw);
-                k_assoc_gather<<<fgrid, 128, 0, ctx->stream>>>(sa);
-                k_assoc_eval<<<(unsigned) (ctx->num_sms * 8), 256, 0, ctx->stream>>>(sa);
-                k_assoc_select<<<fgrid, 128, 0, ctx->stream>>>(sa);
-                ctx->launches += 3;
-            }
+            k_associate<true><<<dim3((unsigned) ((max_q + ASSOC_WARPS - 1) / ASSOC_WARPS), nw), ASSOC_WARPS * 32, 0, ctx->stream>>>(aa);
             mark(3, false);
+            ctx->launches++;
             CU(cudaGetLastError());
         }
     }
@@ -1694,6 +1620,7 @@ extern "C" int levins_batch_run(levins_ctx* ctx) {
         pl.c = ctx->consts;
         if (ctx->peer_on) {
             if (ctx->b_nq > ctx->g_nq) return fail(ctx, LEVINS_ERR_CAPACITY, "more queries than levins_peer_export reserved per rank");
+            if (ctx->g_slot % 16) return fail(ctx, LEVINS_ERR_STATE, "gathered slots are not 16-byte aligned");
             ctx->peer_step++;
             ctx->g_half = (int) (ctx->peer_step & 1);
             pl.peer = ctx->peer;

@@ -30,7 +30,7 @@ EXPORTS = [
     "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host", "levins_append_raw",
     "levins_append_wait", "levins_ins_window_index", "levins_comm_unique_id", "levins_comm_init", "levins_comm_destroy",
     "levins_gather", "levins_peer_export", "levins_peer_attach", "levins_peer_wait", "levins_peer_detach", "levins_gathered_pointer",
-    "levins_gathered_download", "levins_batch_upload_packed", "levins_batch_attach_device", "levins_batch_upload_columns", "levins_associate_pixels", "levins_keyframe_pixels", "levins_plane_estimation_batch",
+    "levins_gathered_download", "levins_batch_upload_packed", "levins_batch_attach_device", "levins_associate_pixels", "levins_keyframe_pixels", "levins_plane_estimation_batch",
     "levins_point_to_plane_std_batch", "levins_depth_factor_batch", "levins_chi2_culling_batch", "levins_state_interpolate", "levins_state_to_pose", "levins_pose_at",
 ]
 
@@ -50,30 +50,6 @@ KF_DESC = np.dtype([("pt_begin", "<u8"), ("pt_count", "<u8"), ("ins_begin", "<u8
 assert KF_DESC.itemsize == 56
 PACKED = np.dtype([("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("dt_ns", "<u4")])
 SCAN_DESC = np.dtype([("first", "<u8"), ("count", "<u8"), ("stamp", "<f8")])
-
-
-def pack_columns(points, scan_first, scan_stamp, points_per_column):
-    """PointXYZIT records of a spinning scanner -> (xyz f32[n, 3], column_dt_ns u32[n / points_per_column], scan descriptors,
-    the PointXYZIT records with the times the device will reconstruct).  Every column must carry one timestamp."""
-    n, g = len(points), int(points_per_column)
-    assert n % g == 0
-    first = np.asarray(scan_first, np.uint64)
-    count = np.diff(np.concatenate([first, [n]]).astype(np.uint64))
-    assert np.all(count % g == 0)
-    stamp = np.asarray(scan_stamp, np.float64)
-    t_col = points["time"].reshape(-1, g)
-    assert np.all(t_col == t_col[:, :1]), "points of one column have different timestamps"
-    col_stamp = np.repeat(stamp, (count // g).astype(np.int64))
-    dt = np.rint((t_col[:, 0] - col_stamp) * 1e9)
-    assert dt.min() >= 0 and dt.max() < 2**32
-    dt = dt.astype(np.uint32)
-    xyz = np.ascontiguousarray(np.stack([points["x"], points["y"], points["z"]], axis=-1), np.float32)
-    scans = np.zeros(len(first), SCAN_DESC)
-    scans["first"], scans["count"], scans["stamp"] = first, count, stamp
-    exact = points.copy()
-    exact["time"] = np.repeat(col_stamp + dt.astype(np.float64) * 1.0e-9, g)
-    exact["intensity"] = 0
-    return xyz, dt, scans, exact
 
 
 def pack_points(points, scan_first, scan_stamp):
@@ -136,7 +112,6 @@ def lib():
             "levins_depth_factor_batch": [vp, vp, vp, sz, dbl, dbl, vp, vp, vp],
             "levins_chi2_culling_batch": [vp, vp, sz, sz, dbl, vp, vp],
             "levins_batch_attach_device": [vp, vp, sz, vp, sz, vp, sz, vp, sz],
-            "levins_batch_upload_columns": [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz],
             "levins_batch_upload_packed": [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz],
             "levins_batch_run": [vp],
             "levins_batch_download": [vp, vp, vp, vp, vp, vp],
@@ -395,17 +370,6 @@ class Context:
         self._b_q = np.zeros((int(n_queries), 3), np.float32)  # only its length is used (batch_download)
         self._check(lib().levins_batch_attach_device(self._h, C.c_void_p(int(d_points)), int(n_points), C.c_void_p(int(d_ins)), int(n_ins),
                                                      C.c_void_p(int(d_queries)), int(n_queries), _p(self._b_descs), len(self._b_descs)))
-
-    def batch_upload_columns(self, xyz, column_dt_ns, points_per_column, scans, ins, queries, descs):
-        self._b_points = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
-        self._b_coldt = np.ascontiguousarray(column_dt_ns, np.uint32)
-        self._b_scans = np.ascontiguousarray(scans, SCAN_DESC)
-        self._b_ins = np.ascontiguousarray(ins, INS)
-        self._b_q = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
-        self._b_descs = np.ascontiguousarray(descs, KF_DESC)
-        self._check(lib().levins_batch_upload_columns(self._h, _p(self._b_points), len(self._b_points), _p(self._b_coldt),
-                                                      int(points_per_column), _p(self._b_scans), len(self._b_scans), _p(self._b_ins),
-                                                      len(self._b_ins), _p(self._b_q), len(self._b_q), _p(self._b_descs), len(self._b_descs)))
 
     def batch_upload_packed(self, packed, scans, ins, queries, descs):
         self._b_points = np.ascontiguousarray(packed, PACKED)

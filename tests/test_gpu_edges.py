@@ -340,31 +340,3 @@ def test_results_do_not_depend_on_the_cull_policy(oracle, built_lib):
         else:
             assert all(out[k].tobytes() == first[k].tobytes() for k in out), run
     c.close()
-
-
-def test_split_association_equals_single_kernel(oracle, built_lib, monkeypatch):
-    """Large batches run the association as gather -> one thread per candidate -> select instead of one kernel per feature
-    warp (LEVINS_ASSOC_SPLIT forces either).  Both must give the same bytes, and the oracle's decisions."""
-    shp = synth.Shape(**{**synth.shape(2).__dict__, "pts_per_scan": 8000, "n_features": 250})
-    b = synth.make_batch(2, 6, n_unique_scans=9, shp=shp)
-    descs = abi.batch_descs(b)
-    descs["q_count"][1] = 0  # a keyframe without features
-    outs = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("LEVINS_ASSOC_SPLIT", mode)
-        c = abi.Context(0)
-        c.set_extrinsics(b.shape.rig.pose_b_c, b.shape.rig.pose_c_l, b.shape.rig.td_b_l)
-        c.batch_set_wave(4)
-        c.batch_upload(b.points, b.ins, b.queries.reshape(-1, 3), descs)
-        c.batch_run()
-        outs[mode] = c.batch_download()
-        c.close()
-    live = np.ones(6 * 250, bool)
-    live[250:500] = False  # results of the feature-less keyframe are never written
-    for k in ("type", "xyz_depth", "flags"):
-        assert outs["0"][k][live].tobytes() == outs["1"][k][live].tobytes(), k
-    assert np.array_equal(outs["0"]["m"], outs["1"]["m"]) and np.array_equal(outs["0"]["n_projected"], outs["1"]["n_projected"])
-    kf = synth.batch_keyframe(b, 4)
-    ref = oracle.keyframe(kf.points, kf.stamp, kf.ins, kf.rig.pose_b_c, kf.rig.pose_c_l, kf.rig.td_b_l, kf.queries, 0.5)
-    assert np.array_equal(outs["1"]["type"][1000:1250], ref["type"]) and outs["1"]["xyz_depth"][1000:1250].tobytes() == ref["xyz_depth"].tobytes()
-    assert (outs["1"]["type"] == 1).sum() > 200
