@@ -88,7 +88,9 @@ def workload_config(batch, n_kf):
             "scans_per_keyframe": int(round(batch.shape.stack_interval / batch.shape.scan_period)),
             "points_per_scan": int(batch.shape.pts_per_scan), "features_per_keyframe": int(batch.queries.shape[1]),
             "stack_interval_s": float(batch.shape.stack_interval), "td_b_l_s": float(batch.shape.rig.td_b_l),
-            "resolution": list(batch.shape.rig.resolution)}
+            "resolution": list(batch.shape.rig.resolution),
+            "l2": "inputs larger than L2, no flush: %d MB of points per GPU per step against 126 MB of L2" % (
+                int(n_kf) * int(round(batch.shape.stack_interval / batch.shape.scan_period)) * int(batch.shape.pts_per_scan) * 32 // 1000000)}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -491,7 +493,6 @@ def run_gpu(args):
             "run": {"points_per_keyframe": int(n_proj_total / n_kf), "wave": args.wave,
                     "cells_per_keyframe": int(out["m"].mean()), "associated_fraction": float((out["type"] == 1).mean()),
                     "gather": (args.gather if world > 1 else None),
-                    "l2": f"inputs larger than L2: {batch.points.nbytes / 1e6:.0f} MB of points per GPU per step",
                     "e2e_input": "packed 16-byte records (x, y, z, u32 ns after the scan stamp), expanded to PointXYZIT on the device"},
             "lidar_pts_per_s": world * pts_per_step * args.steps / (ms_total * 1e-3),
             "keyframes_per_s": world * n_kf * args.steps / (ms_total * 1e-3),
