@@ -318,6 +318,9 @@ int levins_batch_download(levins_ctx *ctx, int8_t *type, float *xyz_depth, int32
  * type == (int8_t *) xyz_depth + 16 * nq16 with nq16 = n_queries rounded up to a multiple of 16, so 17 * nq16 bytes from
  * xyz_depth carry both (and blocks of several ranks can be laid back to back with every float4 aligned). */
 int levins_batch_result_pointers(levins_ctx *ctx, void **type, void **xyz_depth, void **flags);
+/* Bytes of one rank's result slot for n_queries queries: 17 * (n_queries rounded up to a multiple of 16), always a multiple
+ * of 16 (the stride of the slots in a gathered block). */
+size_t levins_result_slot_bytes(size_t n_queries);
 /* Waves: how many keyframes share one set of launches (their z-buffers stay L2-resident). 0 = default. */
 int levins_batch_set_wave(levins_ctx *ctx, int keyframes_per_wave);
 /* Per-kernel device time of the last levins_batch_run, measured with CUDA events on the launching stream when

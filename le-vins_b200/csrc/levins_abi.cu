@@ -1347,6 +1347,11 @@ extern "C" int levins_batch_set_wave(levins_ctx* ctx, int w) {
     return LEVINS_OK;
 }
 
+extern "C" size_t levins_result_slot_bytes(size_t n_queries) {
+    const size_t nq16 = (std::max<size_t>(n_queries, 1) + 15) & ~size_t(15);
+    return 17 * nq16;
+}
+
 // shared by the two upload entry points: validate the descriptors, size the pools, copy INS / queries / keyframe states.
 // The point pool itself is filled by the caller (a plain copy, or a copy of packed records + k_unpack).
 static int batch_prepare(levins_ctx* ctx, size_t n_points, const levins_ins_sample* ins, size_t n_ins, const float* query_xyz,
@@ -1385,7 +1390,7 @@ static int batch_prepare(levins_ctx* ctx, size_t n_points, const levins_ins_samp
     CU(ctx->b_kfs.ensure(n_kf * sizeof(KfState)));
     // one slot = xyz_depth[16 * nq16] then type[nq16], nq16 = the query count rounded up to 16: the slot size (17 * nq16) is
     // then a multiple of 16, so slots of several ranks can sit back to back (gathered block) with every float4 aligned
-    ctx->b_results_nq = (std::max<size_t>(n_queries, 1) + 15) & ~size_t(15);
+    ctx->b_results_nq = levins_result_slot_bytes(n_queries) / 17;
     CU(ctx->b_results.ensure(ctx->b_results_nq * 17));
     CU(ctx->b_flags.ensure(std::max<size_t>(n_queries, 1) * 4));
     CU(ctx->b_nn.ensure(std::max<size_t>(n_queries, 1) * 80));

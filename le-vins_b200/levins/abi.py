@@ -27,7 +27,7 @@ EXPORTS = [
     "levins_buffer_info", "levins_buffer_clear", "levins_stack_deskew", "levins_build_range_image", "levins_associate",
     "levins_keyframe", "levins_point_cloud_projection", "levins_batch_upload", "levins_batch_run",
     "levins_batch_download", "levins_batch_set_wave", "levins_set_profiling", "levins_batch_kernel_ms",
-    "levins_launch_count", "levins_batch_result_pointers", "levins_alloc_host", "levins_free_host", "levins_append_raw",
+    "levins_launch_count", "levins_batch_result_pointers", "levins_result_slot_bytes", "levins_alloc_host", "levins_free_host", "levins_append_raw",
     "levins_append_wait", "levins_ins_window_index", "levins_comm_unique_id", "levins_comm_init", "levins_comm_destroy",
     "levins_gather", "levins_peer_export", "levins_peer_attach", "levins_peer_wait", "levins_peer_detach", "levins_gathered_pointer",
     "levins_gathered_download", "levins_batch_upload_packed", "levins_batch_attach_device", "levins_associate_pixels", "levins_keyframe_pixels", "levins_plane_estimation_batch",

@@ -68,3 +68,15 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp", ".hpp")):
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "oracle_py" not in txt and "levins_oracle" not in txt and "liblevins_oracle" not in txt, f
+
+
+def test_result_slots_are_16_byte_multiples(built_lib):
+    """The stride of the per-rank slots in a gathered block: k_plane stores float4 results into every rank's slot, so the slot
+    size must be a multiple of 16 for ANY query count (375 000 queries per rank once gave 6 375 000-byte slots and misaligned
+    stores on the odd ranks)."""
+    lib = ctypes.CDLL(built_lib)
+    lib.levins_result_slot_bytes.restype = ctypes.c_size_t
+    lib.levins_result_slot_bytes.argtypes = [ctypes.c_size_t]
+    for n in list(range(0, 70)) + [288, 291, 6400, 375000, 375001, 10**7 + 3]:
+        b = lib.levins_result_slot_bytes(n)
+        assert b % 16 == 0 and b % 17 == 0 and b // 17 >= max(n, 1) and b // 17 < max(n, 1) + 16
