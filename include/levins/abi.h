@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define LEVINS_ABI_VERSION 1
+#define LEVINS_ABI_VERSION 2
 
 /* ---- status codes (the reference has bool/int returns and no error codes) ---- */
 #define LEVINS_OK 0
@@ -151,7 +151,8 @@ int levins_append_scan(levins_ctx *ctx, const levins_point_xyzit *points, size_t
 int levins_alloc_host(size_t bytes, void **out);
 /* levins_append_scan returns before the device has read the caller's buffer when that buffer is page-locked (the copy is
  * ordered on the context's stream behind whatever is queued there).  A buffer may be overwritten again once
- * levins_append_wait() has returned (it waits for the copies of the most recent levins_append_scan), or after any call that
+ * levins_append_wait() has returned (it waits for the copies of the most recent levins_append_scan / levins_append_raw), or
+ * after any call that
  * synchronises the context (levins_keyframe, levins_stack_deskew, levins_synchronize).  Rotating two or three buffers and
  * waiting before re-filling the oldest keeps the converter and the copy overlapped.  Scans in pageable memory are staged by
  * the driver before the call returns and need no wait. */
@@ -168,6 +169,8 @@ int levins_free_host(void *p);
  * to_gps_time converts unix seconds to GPS seconds of week (le_vins/common/gpstime.h:36-41).  A record survives iff
  * nearest^2 < |p|^2 < farthest^2 (:66-67).  point_filter_num_ is the constant 1 in the reference (lidar_converter.h:61).
  * Outputs: the number of points appended and the converter's start / end times (over every considered record, :58-63).
+ * Reporting them needs a device->host read, i.e. a synchronisation; with all three output pointers NULL nothing is read back
+ * and the call only enqueues (one copy, two launches; levins_append_wait tells when `records` has been read).
  * Fields may sit at any byte offset and the stride may be odd (the serialized 19-byte Livox record). */
 typedef struct levins_raw_format {
     uint32_t kind, point_step;
