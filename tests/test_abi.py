@@ -24,7 +24,7 @@ def test_header_functions_are_exported(built_lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in abi.h but not exported"
     assert sorted(abi.EXPORTS) == names, "python binding and header disagree"
-    assert lib.levins_abi_version() == 1
+    assert lib.levins_abi_version() == 2
 
 
 def test_config_defaults_are_the_reference_constants(built_lib):
