@@ -89,19 +89,13 @@ struct levins_ctx {
     bool s_cloud_valid = false;
     bool s_image_valid = false;
     bool s_image_from_raw = false; // cells were built from the ring (fused) rather than from a cloud
-    // pinned staging area: [0,256) KfState | [256,512) RingState | [512,1024) misc | INS window | queries | type | xyz_depth.
-    // Small host arrays go through it so that every copy of the streaming path is truly asynchronous (copies from / to
-    // pageable memory block the calling thread one by one).
+    // pinned staging area of the stage-wise entry points: [0,256) KfState | [256,512) RingState | [512,1024) misc | INS window.
+    // Small host arrays go through it so that their copies are truly asynchronous (copies from / to pageable memory block the
+    // calling thread one by one).  The fused keyframe has its own arenas (pin_io).
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     size_t pin_ins() const { return 1024; }
-    size_t pin_q() const { return pin_ins() + ((cfg.max_ins * sizeof(InsSample) + 255) & ~size_t(255)); }
-    size_t pin_type() const { return pin_q() + ((cfg.max_features * 12 + 255) & ~size_t(255)); }
-    size_t pin_xyzd() const { return pin_type() + ((cfg.max_features + 255) & ~size_t(255)); }
-    size_t pin_acc() const { return pin_xyzd() + cfg.max_features * 16; }
-    size_t pin_und() const { return pin_acc() + ((cfg.max_features + 255) & ~size_t(255)); }
-    size_t pin_pw() const { return pin_und() + cfg.max_features * 8; }
-    size_t pin_total() const { return pin_pw() + cfg.max_features * 24 + 256; }
+    size_t pin_total() const { return pin_ins() + ((cfg.max_ins * sizeof(InsSample) + 255) & ~size_t(255)); }
 
     // ---- batch state ----
     DevBuf b_pts, b_ins, b_table, b_queries, b_kfs;
