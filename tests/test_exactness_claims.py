@@ -75,3 +75,23 @@ def test_polynomial_cell_coordinate_is_within_half_the_guard():
         worst = max(worst, float(np.max(np.abs(col - col_exact))), float(np.max(np.abs(row - row_exact))))
     # the reference itself evaluates the angles in f32 (atan2f): up to ~1e-7 rad = 2e-5 cell away from the f64 value
     assert worst + 2e-5 < CELL_GUARD / 2, worst
+
+
+def test_one_compare_bracket_test():
+    """key_brackets (device_math.cuh): for positive doubles t_lo <= t < t_hi is ONE unsigned 64-bit compare on the bit patterns,
+    (bits(t) - bits(t_lo)) < (bits(t_hi) - bits(t_lo)); with the fallback entry's (t_lo, t_hi) = (last sample, first sample) the
+    width wraps and the same compare is true exactly for the times OUTSIDE [first, last), negative times included."""
+    rng = np.random.default_rng(2)
+    n = 1_000_000
+    lo = rng.uniform(1e3, 6e5, n)
+    hi = lo + np.exp(rng.uniform(np.log(1e-4), np.log(10.0), n))
+    t = np.where(rng.random(n) < 0.5, rng.uniform(lo - 1.0, hi + 1.0), np.where(rng.random(n) < 0.5, lo, hi))
+    t = np.where(rng.random(n) < 0.02, -t, t)  # negative times wrap to huge unsigned values and miss
+    t = np.where(rng.random(n) < 0.05, np.nextafter(hi, 0), t)
+    b = lambda a: np.asarray(a, np.float64).view(np.uint64)  # noqa: E731
+    with np.errstate(over="ignore"):
+        inside = (b(t) - b(lo)) < (b(hi) - b(lo))
+        assert np.array_equal(inside, (lo <= t) & (t < hi))
+        first, last = lo, hi  # fallback entry: t_lo = last, t_hi = first
+        outside = (b(t) - b(last)) < (b(first) - b(last))
+        assert np.array_equal(outside, ~((first <= t) & (t < last)))
