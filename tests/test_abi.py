@@ -80,3 +80,17 @@ def test_result_slots_are_16_byte_multiples(built_lib):
     for n in list(range(0, 70)) + [288, 291, 6400, 375000, 375001, 10**7 + 3]:
         b = lib.levins_result_slot_bytes(n)
         assert b % 16 == 0 and b % 17 == 0 and b // 17 >= max(n, 1) and b // 17 < max(n, 1) + 16
+
+
+def test_header_is_plain_c():
+    """include/levins/abi.h is the drop-in boundary: it must compile as C99 (plain pointers and sizes, no C++ types) and as C++."""
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "levins", "abi.h")
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr],
+                ["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr]):
+        r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
