@@ -1,19 +1,23 @@
 // kernels.cuh -- the kernels of the LiDAR depth-enhancement path (sm_100a, hand-written, no libraries).
 //
-//   k_prepare      per keyframe: window search (le_vins.cc:413-437), keyframe pose (le_vins.cc:441-442), the
-//                  per-INS-interval table that replaces the per-point pose interpolation (misc.cc:62-103) and, in
-//                  the chunk descriptors of k_deskew_bin; grid (keyframes, slices)
+//   k_prepare      grid (keyframes, slices): window search (le_vins.cc:413-437), keyframe pose (le_vins.cc:441-442), the
+//                  per-INS-interval table that replaces the per-point pose interpolation (misc.cc:62-103) with its
+//                  frustum-cull records, and the chunk descriptors of k_deskew_bin
 //   k_deskew_bin   per point: range gate + deskew (le_vins.cc:445-464) fused with range-image binning
 //                  (tracking.cc:307-336) through a 64-bit atomicMin key (range bits | point index); persistent warps,
-//                  each with its own TMA ring
-//   k_associate    per feature (one warp): exact windowed 5-NN (tracking.cc:571);
-//                  in the fused path it also turns the z-buffer winners of its window into unit vectors + ranges
-//                  (tracking.cc:340-354) on the fly
-//   k_plane        per feature (one thread): threshold, QR plane fit, validity checks, depth (tracking.cc:573-631)
+//                  each with its own TMA ring; certified frustum cull in front of the f64 algebra
+//   k_associate    per feature (one warp): [undistort + pixel2unitcam (camera.cc:72-74,123-135)], exact windowed 5-NN
+//                  (tracking.cc:571); in the fused path it also turns the z-buffer winners of its window into unit
+//                  vectors + ranges (tracking.cc:340-354) on the fly
+//   k_plane        per feature (one thread): threshold, QR plane fit, validity checks, depth (tracking.cc:573-631),
+//                  [accept gate + cam2world (tracking.cc:431-439)], [stores into every rank's gathered block: exchange.cuh]
 //   k_count_cells  M per keyframe (side stream)
 //   k_finalize     stage-wise API only: per cell winner -> unit vector + range
-//   k_raw_count / k_raw_scan / k_raw_scatter   driver records -> PointXYZIT in the ring (lidar_converter.cc:35-256)
-// plus k_bin_cloud / k_compact / k_project / k_ring_append for the stage-wise ABI entry points.
+//   k_raw_count / k_raw_scatter   driver records -> PointXYZIT in the ring + ring bookkeeping (lidar_converter.cc:35-256)
+//   k_unpack       packed 16-byte host records -> PointXYZIT (batch upload)
+//   k_plane_estimation / k_point_to_plane_std / k_project   PointCloudCommon (pointcloud.cc:50-190), batched
+//   k_depth_factor / k_chi2   depth factor + chi-square culling of the optimiser (depth_factor.h:38-42, optimizer.cc:752-783)
+// plus k_bin_cloud / k_compact / k_ring_append for the stage-wise ABI entry points and k_peer_signal / k_peer_wait (exchange.cuh).
 #pragma once
 
 #include <type_traits>
