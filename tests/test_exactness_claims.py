@@ -1,10 +1,12 @@
-"""CPU checks of two "exact by construction" arguments of the kernels (csrc/device_math.cuh), restated in numpy with f32
+"""CPU checks of the "exact by construction" arguments of the kernels (csrc/device_math.cuh), restated in numpy with f32
 arithmetic.  The GPU tests check the kernels' results; these check the arguments themselves.
 
 1. outside_fov: the FOV gate of tracking.cc:311-314, fl32(|x| / |z|) > tan(45 deg) (= 0x1.fffffffffffffp-1 as a double),
    restated without the division as |x| - |z| >= -|z| 2^-25.
 2. the polynomial cell path: its cell coordinate is within cell_guard / 2 of the exact one, so every id it decides without the
    exact path (distance to a rounding boundary > cell_guard) is the reference's.
+3. the one-compare bracket test of the interval entries.
+4. the 9 x 13 window and the cell mask of k_associate hold every point within the acceptance radius of a query.
 """
 import numpy as np
 
@@ -95,3 +97,101 @@ def test_one_compare_bracket_test():
         first, last = lo, hi  # fallback entry: t_lo = last, t_hi = first
         outside = (b(t) - b(last)) < (b(first) - b(last))
         assert np.array_equal(outside, ~((first <= t) & (t < last)))
+
+
+# ---- 4. the windowed 5-NN of k_associate: the 9 x 13 window and the cell mask never drop a point that can matter ----
+def _query_cell_position(q):
+    """numpy twin of k_associate's query position in cell units (kernels.cuh, "The query's position in cell units")."""
+    qx, qy, qz = q[:, 0], q[:, 1], q[:, 2]
+    inv_ang = F(1.0 / ANGLE)
+    off = F(np.pi * 0.5 - 90.0 * np.pi / 180.0 * 0.5)
+    inside = (qz > 0) & (np.abs(qx) <= qz) & (np.abs(qy) <= qz)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        el_in = _atan_poly((qy / np.sqrt(_fma(qx, qx, (qz * qz).astype(F))).astype(F)).astype(F))
+        az_in = _atan_poly((qx / qz).astype(F))
+    rq_in = _fma(el_in, np.full_like(el_in, inv_ang), np.full_like(el_in, F(150.0)))
+    cq_in = _fma(-az_in, np.full_like(el_in, inv_ang), np.full_like(el_in, F(150.0)))
+    el_out = np.arctan2(qy, np.sqrt((qx * qx + qz * qz).astype(F)).astype(F)).astype(F)
+    az_out = np.arctan2(qz, qx).astype(F)
+    rq_out = ((el_out + off).astype(F) * inv_ang).astype(F)
+    cq_out = ((az_out - off).astype(F) * inv_ang).astype(F)
+    rq = np.where(inside, rq_in, rq_out).astype(F)
+    cq = np.where(inside, cq_in, cq_out).astype(F)
+    ael = np.abs(np.where(inside, el_in, el_out)).astype(F)
+    return rq, cq, ael
+
+
+def _reference_cell(p):
+    """tracking.cc:311-328 on f32 points: (kept, row, col)"""
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        gate = (z < 0) | (np.abs((x / z).astype(F)).astype(np.float64) > TAN) | (np.abs((y / z).astype(F)).astype(np.float64) > TAN)
+    half = np.pi * 0.5 - 90.0 * np.pi / 180.0 * 0.5
+    s = (x * x + z * z).astype(F)
+    row_angle = np.arctan2(y, np.sqrt(s).astype(F)).astype(F).astype(np.float64) + half
+    col_angle = np.arctan2(z, x).astype(F).astype(np.float64) - half
+    row = np.round(row_angle / ANGLE).astype(np.int64)
+    col = np.round(col_angle / ANGLE).astype(np.int64)
+    kept = ~gate & (row >= 0) & (col >= 0) & (row < 300) & (col < 300)
+    return kept, row, col
+
+
+def _rotate_about(q, axis, g):
+    """Rodrigues: rotate the unit vectors q by the angles g about the unit axes `axis` (f64)"""
+    c, s = np.cos(g)[:, None], np.sin(g)[:, None]
+    return q * c + np.cross(axis, q) * s + axis * np.sum(axis * q, axis=1, keepdims=True) * (1 - c)
+
+
+def test_association_window_and_mask_keep_every_point_within_the_acceptance_radius():
+    """tracking.cc:573 accepts a feature only if its 5th neighbour lies within the chord T = 3 sin(0.3 deg), so only points
+    within T of the query can influence a result.  Every such point that the range image can hold must lie (a) inside the
+    9 x 13 window around the query's cell and (b) inside the mask  dr^2 + cmin dc^2 <= 3.01^2  that k_associate applies to
+    the window's cells.  Queries inside and outside the 90-degree cone, points up to exactly T away, emphasis on the
+    corners of the image where the azimuth stretch 1 / cos(el) is largest."""
+    rng = np.random.default_rng(11)
+    n = 3_000_000
+    # query rays: u = x / z, v = y / z over a range a little wider than the image (camera FOV can exceed the range image)
+    u = rng.uniform(-1.25, 1.25, n)
+    v = rng.uniform(-1.25, 1.25, n)
+    edge = rng.random(n) < 0.4  # concentrate on the top / bottom rim, where cos(el) is smallest
+    v = np.where(edge, np.sign(v) * rng.uniform(0.9, 1.05, n), v)
+    u = np.where(edge & (rng.random(n) < 0.5), rng.uniform(-0.2, 0.2, n), u)
+    q64 = np.stack([u, v, np.ones(n)], axis=1)
+    q64 /= np.linalg.norm(q64, axis=1, keepdims=True)
+    q = q64.astype(F)  # the query the kernel sees (f32 unit ray, tracking.cc:395)
+    qn = q.astype(np.float64)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    # points: rotate the query by an arc g with chord 2 sin(g / 2) <= T about a random axis perpendicular to it
+    T = 3.0 * np.sin(ANGLE)
+    gmax = 2.0 * np.arcsin(T / 2.0)
+    g = gmax * np.where(rng.random(n) < 0.5, 1.0 - 1e-9, np.sqrt(rng.random(n)))
+    t = rng.normal(size=(n, 3))
+    t -= qn * np.sum(t * qn, axis=1, keepdims=True)
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    axis = np.cross(qn, t)
+    p_unit = _rotate_about(qn, axis, g)
+    rho = np.exp(rng.uniform(np.log(1.0), np.log(150.0), n))
+    p = (p_unit * rho[:, None]).astype(F)  # the deskewed point the range image bins (f32 camera-frame coordinates)
+    kept, row, col = _reference_cell(p)
+    # the unit-sphere point the search measures (tracking.cc:348-349) against the query, in f32 like L2_Simple<float>
+    pu = (p / np.sqrt(np.sum(p * p, axis=1, dtype=F)).astype(F)[:, None]).astype(F)
+    d = (pu - q).astype(F)
+    d2 = np.sum(d * d, axis=1, dtype=F)
+    matters = kept & (d2.astype(np.float64) <= T * T)
+    assert matters.sum() > 1_000_000
+
+    for poly_err in (0.0, +0.004, -0.004):  # the polynomial's error budget in cell units (see the test above)
+        rq, cq, ael = _query_cell_position(q)
+        rq = (rq + F(poly_err)).astype(F)
+        cq = (cq - F(poly_err)).astype(F)
+        rowq, colq = np.rint(rq).astype(np.int64), np.rint(cq).astype(np.int64)
+        drow, dcol = np.abs(row - rowq)[matters], np.abs(col - colq)[matters]
+        assert drow.max() <= 4 and dcol.max() <= 6, (int(drow.max()), int(dcol.max()))
+        cmin = (np.maximum(F(0), np.cos(ael) * np.cos(np.minimum(ael + F(0.016), F(1.5707963)))) * F(0.999)).astype(F)
+        dr = np.maximum(F(0), np.abs(row.astype(F) - rq) - F(0.51)).astype(F)
+        dc = np.maximum(F(0), np.abs(col.astype(F) - cq) - F(0.51)).astype(F)
+        inmask = (dr * dr + cmin * dc * dc).astype(F) <= F(9.0601)
+        assert inmask[matters].all(), int((~inmask[matters]).sum())
+    # the window is not oversized by much: offsets of 3-4 rows and 5 columns do occur, and the mask's left side reaches
+    # 8.96 of the 9.06 it allows
+    assert drow.max() >= 3 and dcol.max() >= 5
