@@ -7,6 +7,8 @@ arithmetic.  The GPU tests check the kernels' results; these check the arguments
    exact path (distance to a rounding boundary > cell_guard) is the reference's.
 3. the one-compare bracket test of the interval entries.
 4. the 9 x 13 window and the cell mask of k_associate hold every point within the acceptance radius of a query.
+5. the range gate restated on the squared norm (two f32 thresholds found by bisection).
+6. the 64-bit z-buffer key: its minimum is the reference's winner in any arrival order; stale generations read as empty.
 """
 import numpy as np
 
@@ -195,3 +197,117 @@ def test_association_window_and_mask_keep_every_point_within_the_acceptance_radi
     # the window is not oversized by much: offsets of 3-4 rows and 5 columns do occur, and the mask's left side reaches
     # 8.96 of the 9.06 it allows
     assert drow.max() >= 3 and dcol.max() >= 5
+
+
+# ---- 5. the range gate on the squared norm ----
+def _bits_to_f32(b):
+    return np.array(b, dtype=np.uint32).view(F)
+
+
+def _gate_thresholds(nearest, farthest):
+    """numpy twin of make_consts (csrc/levins_abi.cu): bisection over the ordered positive f32 patterns for the largest n2 that
+    is not "too far" and the smallest n2 that is not "too near" under  (double) sqrtf(n2) > farthest / < nearest."""
+    def root(b):
+        return float(np.sqrt(_bits_to_f32(b)))  # numpy's f32 sqrt is correctly rounded, like sqrtf and the device's sqrt.rn
+
+    lo, hi = 0, 0x7F7FFFFF
+    if root(hi) > farthest:
+        while hi - lo > 1:
+            mid = lo + (hi - lo) // 2
+            if root(mid) > farthest:
+                hi = mid
+            else:
+                lo = mid
+        n2_far = F(-1.0) if root(lo) > farthest else _bits_to_f32(lo)
+    else:
+        n2_far = _bits_to_f32(hi)
+    lo, hi = 0, 0x7F7FFFFF
+    if root(lo) < nearest:
+        while hi - lo > 1:
+            mid = lo + (hi - lo) // 2
+            if root(mid) < nearest:
+                lo = mid
+            else:
+                hi = mid
+        n2_near = _bits_to_f32(hi)
+    else:
+        n2_near = F(0.0)
+    return F(n2_near), F(n2_far)
+
+
+def test_range_gate_on_the_squared_norm_is_the_reference_gate():
+    """le_vins.cc:447-451: norm = getVector3fMap().norm() (f32 sqrt of the f32 squared norm), gated when
+    norm > FARTHEST_DEPTH or norm < NEAREST_DEPTH with the compare in double.  The kernels compare the squared norm with two
+    f32 thresholds instead; both forms agree on every f32 within +-2^16 patterns of each threshold and on a broad sample,
+    for the reference's constants and for thresholds that are not squares of floats."""
+    rng = np.random.default_rng(5)
+    for nearest, farthest in ((1.0, 200.0), (0.3, 120.5), (1.0 / 3.0, 77.7), (0.0, 1e30)):
+        n2_near, n2_far = _gate_thresholds(nearest, farthest)
+        around = []
+        for thr in (n2_near, n2_far):
+            b = int(np.array(thr, dtype=F).view(np.uint32))
+            around.append(np.arange(max(b - 65536, 0), min(b + 65536, 0x7F7FFFFF), dtype=np.int64).astype(np.uint32).view(F))
+        broad = np.exp(rng.uniform(np.log(1e-8), np.log(1e9), 2_000_000)).astype(F)
+        n2 = np.concatenate(around + [broad, np.zeros(1, F)])
+        norm = np.sqrt(n2).astype(np.float64)
+        reference = (norm > farthest) | (norm < nearest)
+        restated = (n2 > n2_far) | (n2 < n2_near)
+        assert np.array_equal(reference, restated), (nearest, farthest, int(np.sum(reference != restated)))
+        if farthest < 1e20:
+            assert 0.05 < reference.mean() < 0.95
+
+
+# ---- 6. the z-buffer key ----
+KEY_IDX_BITS = 25
+
+
+def _key_make(gen, rng_f32, idx):
+    return (np.uint64(gen) << np.uint64(56)) | (rng_f32.view(np.uint32).astype(np.uint64) << np.uint64(KEY_IDX_BITS)) | idx.astype(np.uint64)
+
+
+def test_zbuffer_key_minimum_is_the_reference_winner_and_stale_generations_read_as_empty():
+    """device_math.cuh key_make: [gen:8][f32 range bits:31][point index:25].  (a) The minimum key of a cell is the point the
+    reference's sequential loop keeps (tracking.cc:332: a strictly smaller f32 range replaces, so on equal ranges the first
+    index stays), whatever the order in which the points arrive.  (b) gen counts down from 254 (next_gen, levins_abi.cu), so
+    any key of the current use is smaller than every key a previous use left behind, and a cell whose minimum still carries
+    an older gen (or the 0xFF.. clear pattern) is empty."""
+    rng = np.random.default_rng(9)
+    n, cells = 400_000, 5_000
+    cell = rng.integers(0, cells, n)
+    # few distinct ranges per cell so that ties are common; include denormal-free tiny and large values
+    rngs = (rng.integers(1, 40, n).astype(F) * F(0.37)).astype(F)
+    rngs[rng.random(n) < 0.01] = F(1e-30)
+    rngs[rng.random(n) < 0.01] = F(3e38)
+    idx = np.arange(n, dtype=np.int64)
+    assert n < (1 << KEY_IDX_BITS) and np.all(rngs.view(np.uint32) < (1 << 31))
+
+    # reference: sequential, strictly-smaller replaces
+    best = np.full(cells, np.finfo(F).max, F)
+    win = np.full(cells, -1, np.int64)
+    for k in range(n):
+        c = cell[k]
+        if rngs[k] < best[c]:
+            best[c] = rngs[k]
+            win[c] = k
+
+    gen = 200
+    stale = _key_make(gen + 1, (rng.random(cells).astype(F) * F(1e-3)).astype(F), rng.integers(0, 1 << KEY_IDX_BITS, cells))  # nearer and older
+    stale[::7] = np.uint64(0xFFFFFFFFFFFFFFFF)  # cells nobody touched since the clear
+    for order in (np.arange(n), rng.permutation(n), np.arange(n)[::-1]):
+        z = stale.copy()
+        np.minimum.at(z, cell[order], _key_make(gen, rngs[order], idx[order]))  # what atomicMin leaves, in any arrival order
+        live = (z >> np.uint64(56)) == np.uint64(gen)
+        assert np.array_equal(live, win >= 0)
+        got = (z & np.uint64((1 << KEY_IDX_BITS) - 1)).astype(np.int64)
+        assert np.array_equal(got[live], win[live])
+        got_range = ((z >> np.uint64(KEY_IDX_BITS)) & np.uint64(0x7FFFFFFF)).astype(np.uint32).view(F)
+        assert np.array_equal(got_range[live], best[live])
+    # an untouched cell of this use: the stale key stays and is not live
+    z = stale.copy()
+    assert not np.any((z >> np.uint64(56)) == np.uint64(gen))
+    # the generation sequence: 254 after a clear, then down to 1, then clear again -- never 0xFF (the clear pattern) or 0
+    g, seen = 0, []
+    for _ in range(600):
+        g = 254 if (g <= 1 or g > 254) else g - 1
+        seen.append(g)
+    assert min(seen) == 1 and max(seen) == 254 and seen[0] == 254 and seen[253] == 1 and seen[254] == 254
