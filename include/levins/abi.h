@@ -10,7 +10,9 @@
  *
  * Threading: a context is bound to one GPU and is not thread-safe, except levins_append_scan(), which may
  * be called from another thread (the reference appends from the ROS callback thread under a mutex,
- * le_vins.cc:149-163).
+ * le_vins.cc:149-163).  As in the reference, whose stack loop holds that mutex (le_vins.cc:392), an append that arrives
+ * while levins_keyframe / levins_stack_deskew is running waits until that call has returned (the context's mutex is
+ * held across the call's device synchronisation: ~0.08 ms for a keyframe).
  */
 #ifndef LEVINS_ABI_H
 #define LEVINS_ABI_H
