@@ -311,3 +311,30 @@ def test_zbuffer_key_minimum_is_the_reference_winner_and_stale_generations_read_
         g = 254 if (g <= 1 or g > 254) else g - 1
         seen.append(g)
     assert min(seen) == 1 and max(seen) == 254 and seen[0] == 254 and seen[253] == 1 and seen[254] == 254
+
+
+# ---- the twins above restate THESE sources: a changed constant in the kernels must fail here, not pass silently ----
+def test_numpy_twins_use_the_constants_of_the_cuda_sources():
+    import os
+    import re
+
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "le-vins_b200", "csrc")
+    dm = open(os.path.join(csrc, "device_math.cuh")).read()
+    kn = open(os.path.join(csrc, "kernels.cuh")).read()
+    ab = open(os.path.join(csrc, "levins_abi.cu")).read()
+
+    body = dm[dm.index("float atan_poly(float t)"):]
+    body = body[:body.index("return t * p;")]
+    coeffs = [float(c) for c in re.findall(r"(-?\d+\.\d+(?:e-?\d+)?)f", body)]
+    twin = [0.0024566929787397385, -0.014401225373148918, 0.03978099301457405, -0.07234836369752884, 0.10498934984207153,
+            -0.14161226153373718, 0.19985906779766083, -0.33332598209381104, 0.9999998807907104]
+    assert coeffs == twin
+
+    assert re.search(r"constexpr int WIN_ROWS = 4;", kn) and re.search(r"constexpr int WIN_COLS = 6;", kn)
+    for lit in ("- 0.51f)", "<= 9.0601f", "ael + 0.016f", "* 0.999f", "150.0f"):
+        assert lit in kn, lit
+    assert "c.cell_guard = 4e-4f;" in ab and CELL_GUARD == 4e-4
+    assert "constexpr unsigned KEY_IDX_BITS = 25;" in dm and KEY_IDX_BITS == 25
+    assert "(unsigned long long) gen << 56" in dm
+    assert "*gen = 254;" in ab and "if (*gen <= 1 || *gen > 254)" in ab
+    assert "2.98023223876953125e-8f" in dm  # 2^-25 of the division-free FOV gate
