@@ -510,3 +510,49 @@ def test_undistort_points_equals_opencv(oracle):
         ref = cv2.undistortPoints(px.reshape(-1, 1, 2), K, np.array(dist).reshape(5, 1), None, K).reshape(-1, 2)
         got = oracle.undistort_points(intr, dist, px)
         assert got.tobytes() == ref.tobytes()
+
+
+def test_depth_factor_residual_jacobian_and_huber_cost(oracle):
+    """DepthFactor (depth_factor.h:38-42): r = (depth - 1 / invdepth) / std, AutoDiff Jacobian dr / d invdepth = 1 / (invdepth^2 std);
+    the loss at its call site (optimizer.cc:659-665) is Ceres' HuberLoss(a): rho(s) = s for s <= a^2, 2 a sqrt(s) - a^2 beyond,
+    cost = rho(r^2) / 2.  Checked against the closed forms, a central difference and the continuity of rho at s = a^2."""
+    rng = np.random.default_rng(21)
+    for _ in range(400):
+        depth = rng.uniform(1.0, 200.0)
+        invd = 1.0 / rng.uniform(0.5, 250.0)
+        sigma = rng.choice([0.1, 0.05, 1.0])
+        a = rng.choice([0.0, 1.0, 2.5])
+        r, j, c = oracle.depth_factor(depth, invd, sigma, a)
+        assert r == (depth - 1.0 / invd) / sigma
+        assert j == (1.0 / (invd * invd)) / sigma
+        h = invd * 1e-6
+        rp, _, _ = oracle.depth_factor(depth, invd + h, sigma, a)
+        rm, _, _ = oracle.depth_factor(depth, invd - h, sigma, a)
+        assert abs((rp - rm) / (2 * h) - j) <= 1e-6 * abs(j)
+        s = r * r
+        rho = s if (a <= 0 or s <= a * a) else 2.0 * a * np.sqrt(s) - a * a
+        assert c == 0.5 * rho
+        assert c <= 0.5 * s + 1e-12  # Huber never exceeds the squared loss
+    # continuity at the corner s = a^2 and linear growth beyond it
+    a, sigma, invd = 1.0, 0.1, 0.1
+    for eps in (-1e-9, 0.0, 1e-9):
+        r, _, c = oracle.depth_factor(10.0 + (a + eps) * sigma, invd, sigma, a)
+        assert abs(c - 0.5 * a * a) < 1e-7
+    _, _, c2 = oracle.depth_factor(10.0 + 3.0 * sigma, invd, sigma, a)
+    _, _, c4 = oracle.depth_factor(10.0 + 5.0 * sigma, invd, sigma, a)
+    assert abs((c4 - c2) - a * 2.0) < 1e-6  # d cost / d|r| = a beyond the corner
+
+
+def test_chi2_outlier_semantics(oracle):
+    """optimizer.cc:752-783: cost = r^T r of the 2-vector residual, outlier iff cost > 5.991 (strictly)."""
+    rng = np.random.default_rng(22)
+    for _ in range(300):
+        r = rng.normal(size=2) * 2.0
+        out, cost = oracle.chi2_outlier(r, 5.991)
+        assert cost == r[0] * r[0] + r[1] * r[1]
+        assert out == (cost > 5.991)
+    x = np.sqrt(5.991 / 2.0)
+    out, cost = oracle.chi2_outlier(np.array([x, x]), cost_probe := float(x * x + x * x))
+    assert not out and cost == cost_probe  # equal to the threshold is not an outlier
+    assert oracle.chi2_outlier(np.array([x, np.nextafter(x, 10.0)]), cost_probe)[0]
+    assert oracle.chi2_outlier(np.array([0.0, 0.0]))[0] is False
