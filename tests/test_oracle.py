@@ -556,3 +556,56 @@ def test_chi2_outlier_semantics(oracle):
     assert not out and cost == cost_probe  # equal to the threshold is not an outlier
     assert oracle.chi2_outlier(np.array([x, np.nextafter(x, 10.0)]), cost_probe)[0]
     assert oracle.chi2_outlier(np.array([0.0, 0.0]))[0] is False
+
+
+def _point_to_plane_std_numpy(pts, target, point_std):
+    """pointcloud.cc:111-190 restated with numpy (eigh instead of Eigen::EigenSolver; the formula does not depend on the
+    signs or the order of the eigenvectors)"""
+    P = np.stack([pts["x"], pts["y"], pts["z"]], -1).astype(np.float64)
+    t = np.array([target["x"], target["y"], target["z"]], np.float64)
+    n_pts = len(P)
+    inv = 1.0 / n_pts
+    var_p = np.eye(3) * point_std * point_std
+    center = P.sum(0) * inv
+    cov = (P.T @ P) * inv - np.outer(center, center)
+    w, V = np.linalg.eigh(cov)
+    i_min = int(np.argmin(w))
+    nv = V[:, i_min]
+    plane_cov = np.zeros((6, 6))
+    for pv in P:
+        F = np.zeros((3, 3))
+        for m in range(3):
+            if m != i_min:
+                F[m] = inv * (pv - center) / (w[i_min] - w[m]) @ (np.outer(V[:, m], nv) + np.outer(nv, V[:, m]))
+        J = np.zeros((6, 3))
+        J[:3] = V @ F
+        J[3:] = np.eye(3) * inv
+        plane_cov += J @ var_p @ J.T
+    j = np.concatenate([t - center, -nv])
+    return float(np.sqrt(j @ plane_cov @ j + nv @ var_p @ nv))
+
+
+def test_point_to_plane_std_vs_numpy(oracle):
+    rng = np.random.default_rng(33)
+    XYZI = oracle.XYZI
+    worst = 0.0
+    for trial in range(300):
+        normal = rng.normal(size=3)
+        normal /= np.linalg.norm(normal)
+        a = np.cross(normal, [1.0, 0.3, -0.2])
+        a /= np.linalg.norm(a)
+        b = np.cross(normal, a)
+        n_pts = 5 if trial % 3 else int(rng.integers(4, 12))
+        c = rng.uniform(-20, 20, 3)
+        uv = rng.uniform(-1.0, 1.0, (n_pts, 2)) * [1.0, 0.4]  # anisotropic patch: three well separated eigenvalues
+        P = c + uv[:, :1] * a + uv[:, 1:] * b + rng.normal(size=(n_pts, 1)) * 0.01 * normal
+        pts = np.zeros(n_pts, XYZI)
+        pts["x"], pts["y"], pts["z"] = P[:, 0], P[:, 1], P[:, 2]
+        tgt = np.zeros(1, XYZI)
+        tp = c + rng.uniform(-1, 1) * a + rng.uniform(-0.4, 0.4) * b + rng.normal() * 0.05 * normal
+        tgt["x"], tgt["y"], tgt["z"] = tp
+        got = oracle.point_to_plane_std(pts, tgt[0], 0.03)
+        want = _point_to_plane_std_numpy(pts, tgt[0], 0.03)
+        assert np.isfinite(got) and got >= 0.03 * (1 - 1e-9)  # never below the target point's own sigma along the normal
+        worst = max(worst, abs(got - want) / want)
+    assert worst < 1e-7, worst
