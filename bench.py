@@ -440,6 +440,7 @@ def run_gpu(args):
     alg_bytes_per_launch = 32.0 * n_proj_total / max(launches_per_step, 1)
     achieved = alg_bytes_per_launch / (deskew_launch_ms * 1e-3) / 1e9
     share = prof_ms / max(prof_ms.sum(), 1e-9)
+    stage3_ms = float(prof_ms[2] + prof_ms[3]) / 3.0  # k_plane + k_associate per step (3 profiled steps)
 
     # ---- streaming latency: append scans + fused keyframe through the ABI, wall clock per keyframe ----
     def secondary(fn, *a, **kw):
@@ -503,6 +504,9 @@ def run_gpu(args):
                     "e2e_input": "packed 16-byte records (x, y, z, u32 ns after the scan stamp), expanded to PointXYZIT on the device"},
             "lidar_pts_per_s": world * pts_per_step * args.steps / (ms_total * 1e-3),
             "keyframes_per_s": world * n_kf * args.steps / (ms_total * 1e-3),
+            "stage3_alone": {"features_per_s": world * nq / max(stage3_ms * 1e-3, 1e-12), "ms_per_step": stage3_ms,
+                             "kernels": "k_associate + k_plane, live CUDA events (SURVEY 8d: features/s also for stage 3 alone; in the "
+                                        "fused path k_associate deskews the winners of the cells it visits)"},
             "p50_keyframe_ms": p50.get("pageable") if p50 else None,
             "p50_keyframe_ms_pinned_scans": p50.get("pinned") if p50 else None,
             "streaming": p50,
